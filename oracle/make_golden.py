@@ -1,0 +1,274 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Every output array stored here was produced by the reference's own
+``_linear_regression_inner`` (python/glow/gwas/lin_reg.py:203-254) loaded through
+``oracle/refshim.py``; inputs are stored beside them so the GPU box (which has no reference
+tree) can replay the cases.  The fixtures are small (a few hundred KB in total).
+"""
+import gzip
+import io
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import refshim  # noqa: E402
+
+REF = refshim.REFERENCE_ROOT
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+STATS = ('effect', 'stderror', 'tvalue', 'pvalue')
+
+
+def read_vcf_states(path):
+    """Tiny VCF text reader: returns (contigs, starts(0-based), names, states int8 [G, N], sample ids).
+    states = number of alt alleles, -1 when any call is missing (genotype_states,
+    core/.../sql/expressions/VariantUtilExprs.scala:37-59)."""
+    opener = gzip.open if path.endswith('.gz') else open
+    contigs, starts, names, rows, samples = [], [], [], [], None
+    with opener(path, 'rt') as f:
+        for line in f:
+            if line.startswith('##'):
+                continue
+            parts = line.rstrip('\n').split('\t')
+            if line.startswith('#CHROM'):
+                samples = parts[9:]
+                continue
+            gt_idx = parts[8].split(':').index('GT')
+            row = np.empty(len(parts) - 9, dtype=np.int8)
+            for i, field in enumerate(parts[9:]):
+                gt = field.split(':')[gt_idx]
+                calls = re.split(r'[|/]', gt)
+                row[i] = -1 if any(c == '.' for c in calls) else sum(int(c) for c in calls)
+            contigs.append(parts[0])
+            starts.append(int(parts[1]) - 1)  # Glow's `start` is 0-based
+            names.append(parts[2])
+            rows.append(row)
+    return contigs, np.array(starts), names, np.stack(rows), samples
+
+
+def stats_matrix(df, P, G):
+    return {k: df[k].to_numpy(dtype=np.float64).reshape(P, G) for k in STATS if k in df}
+
+
+def run_ref(X_variant_major, phenotype_df, covariate_df=None, offset_df=None, extra=None, **kw):
+    pdf = pd.DataFrame({'values': list(np.asarray(X_variant_major, dtype=np.float64))})
+    if extra is not None:
+        for k, v in extra.items():
+            pdf[k] = v
+    out = refshim.reference_linear_regression(pdf, phenotype_df, covariate_df, offset_df, **kw)
+    return out
+
+
+def golden_docs():
+    """G1: docs/source/tertiary/regression-tests.rst:53-83."""
+    from oracle.linreg_oracle import mean_substitute
+    contigs, starts, names, states, samples = read_vcf_states(os.path.join(REF, 'test-data/gwas/genotypes.vcf.gz'))
+    cov = pd.read_csv(os.path.join(REF, 'test-data/gwas/covariates.csv.gz'), index_col=0)
+    phe = pd.read_csv(os.path.join(REF, 'test-data/gwas/continuous-phenotypes.csv.gz'), index_col=0)
+    off = pd.read_csv(os.path.join(REF, 'test-data/gwas/continuous-offsets.csv.gz'), index_col=0)
+    assert list(cov.index) == samples and list(phe.index) == samples
+    X = mean_substitute(states.astype(np.float64))
+    out = run_ref(X, phe, cov)
+    G, P = X.shape[0], phe.shape[1]
+    res = stats_matrix(out, P, G)
+    out_off = run_ref(X, phe, cov, off)
+    res_off = stats_matrix(out_off, P, G)
+    g = [i for i in range(G) if contigs[i] == '22' and starts[i] == 16050114][0]
+    row = {k: float(res[k][0, g]) for k in STATS}
+    expected = dict(effect=0.14722512852575978,
+                    stderror=0.14155327969643167,
+                    tvalue=1.0400686500623064,
+                    pvalue=0.2984087428847886)
+    for k in STATS:
+        assert abs(row[k] / expected[k] - 1) < 1e-12, (k, row[k], expected[k])
+    np.savez_compressed(os.path.join(OUT, 'docs_gwas.npz'),
+                        states=states,
+                        contigs=np.array(contigs),
+                        starts=starts,
+                        names=np.array(names),
+                        samples=np.array(samples),
+                        covariates=cov.to_numpy(np.float64),
+                        covariate_names=np.array(cov.columns).astype(str),
+                        phenotypes=phe.to_numpy(np.float64),
+                        phenotype_names=np.array(phe.columns).astype(str),
+                        offsets=off.to_numpy(np.float64),
+                        golden_variant=g,
+                        **{'ref_' + k: v
+                           for k, v in res.items()},
+                        **{'ref_off_' + k: v
+                           for k, v in res_off.items()})
+    print('docs_gwas: reference reproduces the docs row to',
+          max(abs(row[k] / expected[k] - 1) for k in STATS))
+
+
+def golden_doctest():
+    """G2: python/glow/gwas/lin_reg.py:42-51 (np.random.seed(42), genotype_states, -1 kept)."""
+    contigs, starts, names, states, samples = read_vcf_states(os.path.join(REF, 'test-data/1kg_sample.vcf'))
+    np.random.seed(42)
+    n_samples, n_phenotypes = 710, 3
+    assert states.shape == (1, n_samples)
+    phe = pd.DataFrame(np.random.random((n_samples, n_phenotypes)), columns=['p1', 'p2', 'p3'])
+    cov = pd.DataFrame(np.random.random((n_samples, n_phenotypes)))
+    out = run_ref(states.astype(np.float64), phe, cov)
+    res = stats_matrix(out, 3, 1)
+    assert f"{res['effect'][0, 0]:.4f}" == '0.0454' and f"{res['pvalue'][0, 0]:.4f}" == '0.0348'
+    np.savez_compressed(os.path.join(OUT, 'onekg_doctest.npz'),
+                        states=states,
+                        contig=np.array(contigs),
+                        start=starts,
+                        phenotypes=phe.to_numpy(),
+                        covariates=cov.to_numpy(),
+                        **{'ref_' + k: v
+                           for k, v in res.items()})
+    print('onekg_doctest:', {k: float(v[0, 0]) for k, v in res.items()})
+
+
+def golden_cars():
+    """G3: R `cars`, data inline at core/src/test/scala/io/projectglow/tertiary/LinearRegressionSuite.scala:187-251."""
+    src = open(os.path.join(REF, 'core/src/test/scala/io/projectglow/tertiary/LinearRegressionSuite.scala')).read()
+    block = src[src.index('private val cars'):src.index('.stripMargin')]
+    pairs = [(int(a), int(b)) for a, b in re.findall(r'\|\d+\s+(\d+)\s+(\d+)', block)]
+    speed = np.array([p[0] for p in pairs], dtype=np.float64)
+    dist = np.array([p[1] for p in pairs], dtype=np.float64)
+    assert len(pairs) == 50 and speed.sum() == 770 and dist.sum() == 2149, (len(pairs), speed.sum(), dist.sum())
+    phe = pd.DataFrame({'dist': dist})
+    out = run_ref(speed[None, :], phe)
+    res = stats_matrix(out, 1, 1)
+    np.savez_compressed(os.path.join(OUT, 'cars.npz'), speed=speed, dist=dist, **{'ref_' + k: v for k, v in res.items()})
+    print('cars:', {k: float(v[0, 0]) for k, v in res.items()})
+
+
+def golden_plink():
+    """G5: test-data/plink/five-samples-five-variants/bed-bim-fam/test.bed vs PlinkReaderSuite.scala:75-107."""
+    raw = open(os.path.join(REF, 'test-data/plink/five-samples-five-variants/bed-bim-fam/test.bed'), 'rb').read()
+    assert raw.hex() == '6c1b014b01bb02bb02bb02bb02'
+    # calls listed in PlinkReaderSuite.scala:75-107 -> genotype_states
+    expected = np.array([[0, 1, 2, -1, -1]] + [[0, 1, 0, 1, 1]] * 4, dtype=np.int8)
+    np.savez_compressed(os.path.join(OUT, 'plink_kat.npz'), bed=np.frombuffer(raw, dtype=np.uint8), states=expected)
+    print('plink_kat ok')
+
+
+def golden_random():
+    """Randomised cases in the style of python/glow/gwas/tests/test_lin_reg.py, run through the
+    unmodified reference kernel.  Inputs + outputs are stored; meta.json describes each case."""
+    rg = np.random.default_rng(20261019)
+    arrays, meta = {}, {}
+
+    def store(name, X, phe, cov, off, ref_df, kw, extra=None, contigs_per_variant=None):
+        P, G = phe.shape[1], X.shape[0]
+        arrays[f'{name}/X'] = X
+        arrays[f'{name}/phenotypes'] = phe.to_numpy(np.float64)
+        if cov is not None:
+            arrays[f'{name}/covariates'] = cov.to_numpy(np.float64)
+        if off is not None:
+            arrays[f'{name}/offsets'] = off.to_numpy(np.float64)
+        for k in STATS + ('n', 'sum_x', 'y_transpose_x'):
+            if k in ref_df:
+                arrays[f'{name}/ref_{k}'] = ref_df[k].to_numpy(np.float64)
+        arrays[f'{name}/ref_phenotype'] = ref_df['phenotype'].to_numpy().astype(str)
+        if 'idx' in ref_df:
+            arrays[f'{name}/ref_idx'] = ref_df['idx'].to_numpy()
+        m = dict(kw)
+        m.update(P=P, G=G, N=int(phe.shape[0]))
+        if contigs_per_variant is not None:
+            m['variant_contigs'] = list(contigs_per_variant)
+        meta[name] = m
+
+    # basic: uniform genotypes, covariates (test_multiple, test_lin_reg.py:186-191)
+    N, G, P = 100, 10, 25
+    X = rg.random((G, N))
+    phe = pd.DataFrame(rg.random((N, P)))
+    cov = pd.DataFrame(rg.random((N, 5)))
+    store('multiple', X, phe, cov, None, run_ref(X, phe, cov, extra={'idx': np.arange(G)}), {})
+
+    # missing phenotypes + verbose (test_verbose_output, :239-257)
+    N, G, P = 60, 7, 4
+    X = rg.random((G, N)) * 2
+    phe = pd.DataFrame(rg.random((N, P)))
+    phe.iloc[0, 0] = np.nan
+    phe.iloc[[1, 3, 5, 17], 1] = np.nan
+    phe.iloc[10:30, 2] = np.nan
+    cov = pd.DataFrame(rg.random((N, 3)))
+    store('missing_verbose', X, phe, cov, None,
+          run_ref(X, phe, cov, extra={'idx': np.arange(G)}, verbose_output=True), dict(verbose_output=True))
+
+    # no covariates / no intercept
+    N, G, P = 40, 5, 3
+    X = rg.random((G, N))
+    phe = pd.DataFrame(rg.random((N, P)))
+    cov = pd.DataFrame(rg.random((N, 2)))
+    store('no_intercept', X, phe, cov, None,
+          run_ref(X, phe, cov, extra={'idx': np.arange(G)}, add_intercept=False), dict(add_intercept=False))
+    store('intercept_only', X, phe, None, None, run_ref(X, phe, extra={'idx': np.arange(G)}), {})
+
+    # single offset (test_simple_offset, :340-355)
+    N, G, P = 25, 10, 6
+    X = rg.random((G, N))
+    phe = pd.DataFrame(rg.random((N, P)))
+    cov = pd.DataFrame(rg.random((N, 2)))
+    off = pd.DataFrame(rg.random((N, P)))
+    store('simple_offset', X, phe, cov, off, run_ref(X, phe, cov, off, extra={'idx': np.arange(G)}), {})
+
+    # LOCO offsets with missing phenotypes (test_multi_offset_with_missing, :422-447)
+    N, G, P = 50, 18, 8
+    contigs = ['chr1', 'chr2', 'chr3']
+    X = rg.random((G, N))
+    phe = pd.DataFrame(rg.random((N, P)))
+    miss = np.zeros(phe.shape)
+    np.fill_diagonal(miss, 1)
+    miss[:, -1] = 0
+    phe[miss.astype(bool)] = np.nan
+    cov = pd.DataFrame(rg.random((N, 4)))
+    off = pd.DataFrame(rg.random((N * 3, P)), index=pd.MultiIndex.from_product([phe.index, contigs]))
+    vc = (contigs * 6)
+    ref = run_ref(X, phe, cov, off, extra={'contigName': vc, 'idx': np.arange(G)})
+    store('loco_missing', X, phe, cov, off, ref, {}, contigs_per_variant=vc)
+
+    # intersect_samples: phenotype rows are a subset of genotype samples (:217-235)
+    N, G, P = 30, 6, 3
+    samples = [f's{i}' for i in range(N)]
+    X = rg.random((G, N))
+    keep = [i for i in range(N) if i not in (0, 7, 29)]
+    phe = pd.DataFrame(rg.random((N, P)), index=samples).iloc[keep]
+    phe.iloc[[1, 3], 1] = np.nan
+    cov = pd.DataFrame(rg.random((N, 3)), index=samples)
+    ref = run_ref(X, phe, cov, extra={'idx': np.arange(G)}, intersect_samples=True, genotype_sample_ids=samples)
+    arrays['intersect/keep'] = np.array(keep)
+    store('intersect', X, phe, cov, None, ref, dict(intersect_samples=True))
+
+    # genotype-like integer states incl. strong signal (small p-values) and an all-zero variant
+    N, G, P = 400, 24, 3
+    f = rg.uniform(0.02, 0.5, G)
+    X = rg.binomial(2, f[:, None], (G, N)).astype(np.float64)
+    X[5] = 0.0  # monomorphic -> NaN in the reference
+    cov = pd.DataFrame(rg.standard_normal((N, 4)))
+    Y = rg.standard_normal((N, P))
+    Y[:, 0] += 2.0 * X[0] + 0.5 * X[1]
+    Y[:, 1] += 0.3 * X[2]
+    phe = pd.DataFrame(Y, columns=['t0', 't1', 't2'])
+    ref = run_ref(X, phe, cov, extra={'idx': np.arange(G)})
+    store('hardcalls_signal', X, phe, cov, None, ref, {})
+
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, 'random_cases.npz'), **arrays)
+    with open(os.path.join(OUT, 'random_cases.json'), 'w') as fh:
+        json.dump(meta, fh, indent=1, sort_keys=True)
+    print('random_cases:', sorted(meta))
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    golden_docs()
+    golden_doctest()
+    golden_cars()
+    golden_plink()
+    golden_random()
