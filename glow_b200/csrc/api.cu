@@ -1,0 +1,699 @@
+// C ABI (include/glow_b200.h): state packing, lanes (streams + staging), block execution.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/glow_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace glr;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(GLR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(GLR_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  DevBuf geno, out, s_part, s_red, sxx_part, sxx, v1, d_part, d_red;
+  bool busy = false;
+  bool has_masked = false, has_prepass = false;
+  int launches = 0;
+  glr_timing timing{};
+};
+
+int pick_mt(int n_mtiles) {
+  const int opts[] = {1, 2, 3, 4, 6, 8};
+  for (int o : opts)
+    if (n_mtiles <= o) return o;
+  return 8;
+}
+int pick_mt_masked(int n_mtiles) {
+  const int opts[] = {1, 2, 4, 8};
+  for (int o : opts)
+    if (n_mtiles <= o) return o;
+  return 8;
+}
+
+}  // namespace
+
+struct glr_state {
+  int device = 0;
+  int64_t N = 0, Ng = 0;
+  int K = 0, P = 0, C = 1, verbose = 0;
+  int64_t dof = 0;
+  int64_t n_chunks = 0;
+  // pass-1 operand
+  int Mcols = 0, MT = 1, n_groups = 1;
+  int64_t w_contig_doubles = 0;
+  double* wpk = nullptr;  // [C][n_groups][n_chunks][8][MT][64]
+  // masked pass
+  int U = 0, MT2 = 1, n_groups2 = 0, KT2 = 0;
+  double* qb = nullptr;
+  double* mpk = nullptr;
+  // small per-phenotype arrays
+  int32_t* mask_id = nullptr;  // [P]
+  double* YdotY = nullptr;     // [C][P]
+  double* Y_scale = nullptr;   // [P]
+  double* n_obs = nullptr;     // [P]
+  int64_t* drop_idx = nullptr;
+  int64_t n_drop = 0;
+  PvalConst pc{};
+  std::vector<Lane> lanes;
+  int sm_count = 148;
+  int force_nt = 0, force_split = 0;
+};
+
+extern "C" {
+
+int glr_abi_version(void) { return GLR_ABI_VERSION; }
+const char* glr_last_error(void) { return g_err.c_str(); }
+
+int glr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+static int check_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(GLR_ERR_NO_DEVICE, "no CUDA device visible: glow_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(GLR_ERR_INVALID, "device ordinal out of range");
+  int major = 0;
+  CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10)
+    return fail(GLR_ERR_NO_DEVICE, "device is not compute capability 10.x (kernels are built for sm_100a only)");
+  CU(cudaSetDevice(device));
+  return 0;
+}
+
+int glr_state_destroy(glr_state* st) {
+  if (!st) return 0;
+  cudaSetDevice(st->device);
+  for (auto& l : st->lanes) {
+    if (l.stream) cudaStreamSynchronize(l.stream);
+    for (auto& e : l.ev)
+      if (e) cudaEventDestroy(e);
+    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.sxx_part, &l.sxx, &l.v1, &l.d_part, &l.d_red})
+      b->release();
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
+  for (void* p : {(void*)st->wpk, (void*)st->qb, (void*)st->mpk, (void*)st->mask_id, (void*)st->YdotY,
+                  (void*)st->Y_scale, (void*)st->n_obs, (void*)st->drop_idx})
+    if (p) cudaFree(p);
+  delete st;
+  return 0;
+}
+
+int glr_state_unique_masks(glr_state* st) { return st ? st->U : 0; }
+
+int glr_state_create(const glr_state_desc* d, glr_state** out) {
+  if (!d || !out) return fail(GLR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (d->abi_version != GLR_ABI_VERSION) return fail(GLR_ERR_INVALID, "ABI version mismatch");
+  if (d->n_samples <= 0 || d->n_covariates < 0 || d->n_phenotypes <= 0 || d->n_contigs <= 0)
+    return fail(GLR_ERR_INVALID, "bad dimensions");
+  if (d->n_geno_samples < d->n_samples) return fail(GLR_ERR_INVALID, "n_geno_samples < n_samples");
+  if (!d->Y || !d->Y_mask || !d->YdotY || !d->Y_scale || (d->n_covariates > 0 && !d->Q))
+    return fail(GLR_ERR_INVALID, "missing state array");
+  if (d->verbose && !d->Y_raw) return fail(GLR_ERR_INVALID, "verbose output needs Y_raw");
+  if (d->n_geno_samples != d->n_samples && !d->keep_idx)
+    return fail(GLR_ERR_INVALID, "keep_idx required when genotype rows are dropped");
+  int rc = check_device(d->device);
+  if (rc) return rc;
+
+  glr_state* st = new glr_state();
+  struct Guard {
+    glr_state* s;
+    ~Guard() {
+      if (s) glr_state_destroy(s);
+    }
+  } guard{st};
+
+  st->device = d->device;
+  st->N = d->n_samples;
+  st->Ng = d->n_geno_samples;
+  st->K = d->n_covariates;
+  st->P = d->n_phenotypes;
+  st->C = d->n_contigs;
+  st->verbose = d->verbose ? 1 : 0;
+  st->dof = d->dof;
+  st->pc = make_pval_const((double)d->dof);
+  st->n_chunks = ceil_div(st->Ng, kChunk);
+  CU(cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, d->device));
+  if (const char* e = getenv("GLR_NT")) st->force_nt = atoi(e);
+  if (const char* e = getenv("GLR_SPLIT")) st->force_split = atoi(e);
+
+  const int64_t N = st->N, Ng = st->Ng;
+  const int K = st->K, P = st->P, C = st->C;
+  const bool dev_in = d->memspace == GLR_MEM_DEVICE;
+  const cudaMemcpyKind in_kind = dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  cudaStream_t s0 = nullptr;  // default stream for the one-time packing
+
+  // ---- sample map (np.delete at lin_reg.py:228-229 as a gather) ----
+  int64_t* d_g2r = nullptr;
+  std::vector<int64_t> g2r;
+  if (d->keep_idx) {
+    g2r.assign(Ng, -1);
+    for (int64_t i = 0; i < N; ++i) {
+      const int64_t g = d->keep_idx[i];
+      if (g < 0 || g >= Ng || g2r[g] != -1) return fail(GLR_ERR_INVALID, "keep_idx must be unique and in range");
+      g2r[g] = i;
+    }
+    std::vector<int64_t> drop;
+    for (int64_t g = 0; g < Ng; ++g)
+      if (g2r[g] < 0) drop.push_back(g);
+    st->n_drop = (int64_t)drop.size();
+    CU(cudaMalloc(&d_g2r, Ng * sizeof(int64_t)));
+    CU(cudaMemcpy(d_g2r, g2r.data(), Ng * sizeof(int64_t), cudaMemcpyHostToDevice));
+    if (st->n_drop) {
+      CU(cudaMalloc(&st->drop_idx, drop.size() * sizeof(int64_t)));
+      CU(cudaMemcpy(st->drop_idx, drop.data(), drop.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+  }
+  struct TmpFree {
+    std::vector<void*> v;
+    ~TmpFree() {
+      for (void* p : v)
+        if (p) cudaFree(p);
+    }
+  } tmp;
+  tmp.v.push_back(d_g2r);
+
+  // ---- missingness patterns: phenotypes sharing a mask share one masked sum of squares ----
+  std::vector<double> h_mask;
+  const double* mask_host = d->Y_mask;
+  if (dev_in) {
+    h_mask.resize((size_t)N * P);
+    CU(cudaMemcpy(h_mask.data(), d->Y_mask, (size_t)N * P * sizeof(double), cudaMemcpyDeviceToHost));
+    mask_host = h_mask.data();
+  }
+  std::vector<uint64_t> h1(P, 1469598103934665603ull), h2(P, 0x9E3779B97F4A7C15ull);
+  std::vector<int64_t> nobs(P, 0);
+  for (int64_t s = 0; s < N; ++s) {
+    const double* row = mask_host + s * P;
+    for (int p = 0; p < P; ++p) {
+      const uint64_t bit = row[p] != 0.0;
+      nobs[p] += (int64_t)bit;
+      h1[p] = (h1[p] ^ bit) * 1099511628211ull;
+      h2[p] = (h2[p] + bit + 1) * 0xff51afd7ed558ccdull;
+      h2[p] ^= h2[p] >> 29;
+    }
+  }
+  std::vector<int32_t> mask_id(P, -1);
+  std::vector<int> rep;  // representative phenotype of each unique mask
+  {
+    struct KeyHash {
+      size_t operator()(const std::pair<uint64_t, uint64_t>& k) const { return (size_t)(k.first ^ (k.second * 31)); }
+    };
+    std::unordered_map<std::pair<uint64_t, uint64_t>, int, KeyHash> seen;
+    for (int p = 0; p < P; ++p) {
+      if (nobs[p] == N) continue;
+      auto key = std::make_pair(h1[p], h2[p]);
+      auto it = seen.find(key);
+      if (it == seen.end()) {
+        seen.emplace(key, (int)rep.size());
+        mask_id[p] = (int)rep.size();
+        rep.push_back(p);
+      } else {
+        mask_id[p] = it->second;
+      }
+    }
+  }
+  st->U = (int)rep.size();
+
+  // ---- small arrays ----
+  CU(cudaMalloc(&st->mask_id, P * sizeof(int32_t)));
+  CU(cudaMemcpy(st->mask_id, mask_id.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&st->YdotY, (size_t)C * P * sizeof(double)));
+  CU(cudaMemcpy(st->YdotY, d->YdotY, (size_t)C * P * sizeof(double), in_kind));
+  CU(cudaMalloc(&st->Y_scale, P * sizeof(double)));
+  CU(cudaMemcpy(st->Y_scale, d->Y_scale, P * sizeof(double), in_kind));
+  {
+    std::vector<double> nf(P);
+    for (int p = 0; p < P; ++p) nf[p] = (double)nobs[p];
+    CU(cudaMalloc(&st->n_obs, P * sizeof(double)));
+    CU(cudaMemcpy(st->n_obs, nf.data(), P * sizeof(double), cudaMemcpyHostToDevice));
+  }
+
+  // ---- row-major device copies used only for packing ----
+  double *dQ = nullptr, *dY = nullptr, *dM = nullptr, *dYraw = nullptr, *dT = nullptr;
+  if (K > 0) {
+    CU(cudaMalloc(&dQ, (size_t)N * K * sizeof(double)));
+    tmp.v.push_back(dQ);
+    CU(cudaMemcpy(dQ, d->Q, (size_t)N * K * sizeof(double), in_kind));
+    CU(cudaMalloc(&dT, (size_t)K * P * sizeof(double)));
+    tmp.v.push_back(dT);
+  }
+  CU(cudaMalloc(&dY, (size_t)N * P * sizeof(double)));
+  tmp.v.push_back(dY);
+  if (st->verbose) {
+    CU(cudaMalloc(&dM, (size_t)N * P * sizeof(double)));
+    tmp.v.push_back(dM);
+    CU(cudaMemcpy(dM, d->Y_mask, (size_t)N * P * sizeof(double), in_kind));
+    CU(cudaMalloc(&dYraw, (size_t)N * P * sizeof(double)));
+    tmp.v.push_back(dYraw);
+    CU(cudaMemcpy(dYraw, d->Y_raw, (size_t)N * P * sizeof(double), in_kind));
+  }
+
+  // ---- pass-1 operand W_c = [Q | Ytilde_c | mask | Yraw], Ytilde_c = (I - Q Q^T) Y_c ----
+  st->Mcols = K + P * (st->verbose ? 3 : 1);
+  const int n_mtiles = (int)ceil_div(st->Mcols, 8);
+  if (n_mtiles <= kMaxMT) {
+    st->MT = pick_mt(n_mtiles);
+    st->n_groups = 1;
+  } else {
+    st->MT = kMaxMT;
+    st->n_groups = (int)ceil_div(n_mtiles, kMaxMT);
+  }
+  st->w_contig_doubles = (int64_t)st->n_groups * st->n_chunks * kChunkGroups * st->MT * kAtomDoubles;
+  const size_t w_bytes = (size_t)C * st->w_contig_doubles * sizeof(double);
+  CU(cudaMalloc(&st->wpk, w_bytes));
+  CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
+  for (int c = 0; c < C; ++c) {
+    double* dst = st->wpk + (int64_t)c * st->w_contig_doubles;
+    CU(cudaMemcpyAsync(dY, d->Y + (int64_t)c * N * P, (size_t)N * P * sizeof(double), in_kind, s0));
+    if (K > 0) {
+      launch_qty(dQ, dY, N, K, P, dT, s0);
+      launch_residualize(dQ, dT, dY, N, K, P, s0);
+      launch_pack_a(dQ, N, K, 0, K, d_g2r, Ng, dst, 0, st->MT, st->n_chunks, s0);
+    }
+    launch_pack_a(dY, N, P, 0, P, d_g2r, Ng, dst, K, st->MT, st->n_chunks, s0);
+    if (st->verbose) {
+      launch_pack_a(dM, N, P, 0, P, d_g2r, Ng, dst, K + P, st->MT, st->n_chunks, s0);
+      launch_pack_a(dYraw, N, P, 0, P, d_g2r, Ng, dst, K + 2 * P, st->MT, st->n_chunks, s0);
+    }
+  }
+  CU(cudaGetLastError());
+
+  // ---- masked-pass operands ----
+  if (st->U > 0) {
+    const int KT = (int)ceil_div(std::max(K, 1), 4);
+    st->KT2 = (int)ceil_div(KT, 2);
+    if (2 * st->KT2 > 8)
+      return fail(GLR_ERR_INVALID,
+                  "phenotypes with missing values are supported with at most 32 covariates (incl. intercept)");
+    const int U = st->U;
+    const int n_mt2 = (int)ceil_div(U, 8);
+    if (n_mt2 <= kMaxMT) {
+      st->MT2 = pick_mt_masked(n_mt2);
+      st->n_groups2 = 1;
+    } else {
+      st->MT2 = kMaxMT;
+      st->n_groups2 = (int)ceil_div(n_mt2, kMaxMT);
+    }
+    const size_t qb_bytes = (size_t)st->n_chunks * kChunkGroups * st->KT2 * kAtomDoubles * sizeof(double);
+    CU(cudaMalloc(&st->qb, qb_bytes));
+    CU(cudaMemsetAsync(st->qb, 0, qb_bytes, s0));
+    if (K > 0) launch_pack_qb(dQ, N, K, d_g2r, Ng, st->qb, st->KT2, st->n_chunks, s0);
+    const size_t m_bytes =
+        (size_t)st->n_groups2 * st->n_chunks * kChunkGroups * st->MT2 * kAtomDoubles * sizeof(double);
+    CU(cudaMalloc(&st->mpk, m_bytes));
+    CU(cudaMemsetAsync(st->mpk, 0, m_bytes, s0));
+    // unique mask columns, row-major [N x U]
+    std::vector<double> mu((size_t)N * U);
+    for (int64_t s = 0; s < N; ++s)
+      for (int u = 0; u < U; ++u) mu[(size_t)s * U + u] = mask_host[s * P + rep[u]];
+    double* dMu = nullptr;
+    CU(cudaMalloc(&dMu, mu.size() * sizeof(double)));
+    tmp.v.push_back(dMu);
+    CU(cudaMemcpy(dMu, mu.data(), mu.size() * sizeof(double), cudaMemcpyHostToDevice));
+    launch_pack_a(dMu, N, U, 0, U, d_g2r, Ng, st->mpk, 0, st->MT2, st->n_chunks, s0);
+  }
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+
+  // ---- lanes ----
+  int n_lanes = d->n_lanes > 0 ? d->n_lanes : 2;
+  if (n_lanes > 8) n_lanes = 8;
+  st->lanes.resize(n_lanes);
+  for (auto& l : st->lanes) {
+    CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    for (auto& e : l.ev) CU(cudaEventCreate(&e));
+  }
+  guard.s = nullptr;
+  *out = st;
+  return 0;
+}
+
+static size_t row_bytes_of(int format, int64_t n) {
+  switch (format) {
+    case GLR_FMT_F64: return (size_t)n * 8;
+    case GLR_FMT_F32: return (size_t)n * 4;
+    case GLR_FMT_I8: return (size_t)n;
+    default: return (size_t)((n + 3) / 4);
+  }
+}
+
+int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const glr_block_out* o) {
+  if (!st || !b || !o) return fail(GLR_ERR_INVALID, "null argument");
+  if (lane_id < 0 || lane_id >= (int)st->lanes.size()) return fail(GLR_ERR_INVALID, "lane out of range");
+  Lane& L = st->lanes[lane_id];
+  if (L.busy) return fail(GLR_ERR_STATE, "lane already has a block in flight");
+  if (b->format < GLR_FMT_F64 || b->format > GLR_FMT_PLINK2) return fail(GLR_ERR_INVALID, "unknown genotype format");
+  if (b->contig < 0 || b->contig >= st->C) return fail(GLR_ERR_INVALID, "contig index out of range");
+  if (b->n_variants < 0) return fail(GLR_ERR_INVALID, "negative n_variants");
+  const int G = b->n_variants;
+  const size_t rb = row_bytes_of(b->format, st->Ng);
+  if (G > 0 && (!b->genotypes || (size_t)b->row_stride_bytes < rb))
+    return fail(GLR_ERR_INVALID, "genotype buffer missing or row stride smaller than a row");
+  if (G > 0 && (!o->effect || !o->stderror || !o->tvalue || !o->pvalue))
+    return fail(GLR_ERR_INVALID, "missing output array");
+  if (G > 0 && st->verbose && (!o->n || !o->sum_x || !o->y_transpose_x))
+    return fail(GLR_ERR_INVALID, "verbose state needs n / sum_x / y_transpose_x outputs");
+  if ((b->format == GLR_FMT_F64 && (b->row_stride_bytes % 8 || (uintptr_t)b->genotypes % 8)) ||
+      (b->format == GLR_FMT_F32 && (b->row_stride_bytes % 4 || (uintptr_t)b->genotypes % 4)))
+    return fail(GLR_ERR_INVALID, "genotype rows must be aligned to their element size");
+  CU(cudaSetDevice(st->device));
+  L.launches = 0;
+  L.has_masked = false;
+  L.has_prepass = false;
+  if (G == 0) {
+    L.busy = true;
+    for (auto& e : L.ev) CU(cudaEventRecord(e, L.stream));
+    return 0;
+  }
+  cudaStream_t s = L.stream;
+  const int P = st->P, K = st->K;
+
+  // ---- plan ----
+  int nt = 2;
+  if (b->format == GLR_FMT_PLINK2) {
+    nt = (ceil_div(G, 256) >= st->sm_count) ? 4 : 2;
+    if (st->force_nt == 2 || st->force_nt == 4) nt = st->force_nt;
+    if (st->MT > 4) nt = 2;  // 4 n-tiles x >4 m-tiles of accumulators would spill
+  }
+  const int tile = gram_tile_variants(nt);
+  const int64_t ldS = round_up(G, 256);
+  const int64_t ctas = ceil_div(G, tile) * st->n_groups;
+  int n_split = 1;
+  if (ctas < st->sm_count) {
+    n_split = (int)std::min<int64_t>(ceil_div(2 * st->sm_count, ctas), std::max<int64_t>(1, st->n_chunks / 8));
+    n_split = std::max(1, std::min(n_split, 64));
+  }
+  if (st->force_split > 0) n_split = (int)std::min<int64_t>(st->force_split, st->n_chunks);
+  const int64_t Mpad = (int64_t)st->n_groups * st->MT * 8;
+  const bool float_fmt = b->format == GLR_FMT_F64 || b->format == GLR_FMT_F32;
+
+  // ---- buffers ----
+  const uint8_t* d_geno = reinterpret_cast<const uint8_t*>(b->genotypes);
+  if (b->memspace == GLR_MEM_HOST) {
+    const size_t bytes = (size_t)(G - 1) * b->row_stride_bytes + rb;
+    if (int rc = L.geno.ensure(bytes + 64)) return rc;
+    CU(cudaMemcpyAsync(L.geno.p, b->genotypes, bytes, cudaMemcpyHostToDevice, s));
+    d_geno = L.geno.as<uint8_t>();
+  }
+  if (int rc = L.s_red.ensure((size_t)Mpad * ldS * 8)) return rc;
+  if (n_split > 1)
+    if (int rc = L.s_part.ensure((size_t)n_split * Mpad * ldS * 8)) return rc;
+  if (int rc = L.sxx.ensure((size_t)ldS * 8)) return rc;
+  if (int rc = L.v1.ensure((size_t)ldS * 8)) return rc;
+  if (float_fmt && n_split > 1)
+    if (int rc = L.sxx_part.ensure((size_t)n_split * ldS * 8)) return rc;
+  const int n_out = st->verbose ? 7 : 4;
+  double* outs[7] = {o->effect, o->stderror, o->tvalue, o->pvalue, o->n, o->sum_x, o->y_transpose_x};
+  double* d_outs[7];
+  const size_t out_elems = (size_t)P * G;
+  if (o->memspace == GLR_MEM_HOST) {
+    if (int rc = L.out.ensure(out_elems * 8 * n_out)) return rc;
+    for (int i = 0; i < n_out; ++i) d_outs[i] = L.out.as<double>() + i * out_elems;
+  } else {
+    for (int i = 0; i < n_out; ++i) d_outs[i] = outs[i];
+  }
+
+  BlockView x;
+  x.base = d_geno;
+  x.stride = b->row_stride_bytes;
+  x.n_variants = G;
+  x.format = b->format;
+  x.n_geno = st->Ng;
+  x.v1 = L.v1.as<double>();
+
+  CU(cudaEventRecord(L.ev[0], s));
+  // ---- pre-pass (A0): missing substitute + sum of squares from integer counts ----
+  if (!float_fmt) {
+    launch_prepass(x, b->missing_policy, L.v1.as<double>(), L.sxx.as<double>(), s);
+    L.has_prepass = true;
+    ++L.launches;
+  }
+  CU(cudaEventRecord(L.ev[1], s));
+  // ---- pass 1 (A1-A3): S = [Q | Ytilde | ...]^T X ----
+  GramParams gp;
+  gp.x = x;
+  gp.wpk = st->wpk + (int64_t)b->contig * st->w_contig_doubles;
+  gp.MT = st->MT;
+  gp.n_groups = st->n_groups;
+  gp.n_chunks = st->n_chunks;
+  gp.n_split = n_split;
+  gp.nt = nt;
+  gp.ldS = ldS;
+  gp.S = n_split > 1 ? L.s_part.as<double>() : L.s_red.as<double>();
+  gp.sxx_part = (float_fmt && n_split > 1) ? L.sxx_part.as<double>() : L.sxx.as<double>();
+  launch_gram(gp, s);
+  ++L.launches;
+  if (n_split > 1) {
+    launch_reduce_splits(L.s_part.as<double>(), L.s_red.as<double>(), Mpad, ldS, n_split, s);
+    ++L.launches;
+    if (float_fmt) {
+      launch_reduce_splits(L.sxx_part.as<double>(), L.sxx.as<double>(), 1, ldS, n_split, s);
+      ++L.launches;
+    }
+  }
+  if (st->n_drop > 0) {
+    launch_dropped_sumsq(x, st->drop_idx, st->n_drop, L.sxx.as<double>(), s);
+    ++L.launches;
+  }
+  CU(cudaEventRecord(L.ev[2], s));
+  // ---- pass 2 (A4 for phenotypes with missing samples): D = Mu^T (X - Q A)^2 ----
+  const double* d_D = nullptr;
+  if (st->U > 0) {
+    const int64_t Upad = (int64_t)st->n_groups2 * st->MT2 * 8;
+    const int tile2 = gram_tile_variants(2);
+    const int64_t ctas2 = ceil_div(G, tile2) * st->n_groups2;
+    int n_split2 = 1;
+    if (ctas2 < st->sm_count) {
+      n_split2 = (int)std::min<int64_t>(ceil_div(2 * st->sm_count, ctas2), std::max<int64_t>(1, st->n_chunks / 8));
+      n_split2 = std::max(1, std::min(n_split2, 64));
+    }
+    if (st->force_split > 0) n_split2 = (int)std::min<int64_t>(st->force_split, st->n_chunks);
+    if (int rc = L.d_red.ensure((size_t)Upad * ldS * 8)) return rc;
+    if (n_split2 > 1)
+      if (int rc = L.d_part.ensure((size_t)n_split2 * Upad * ldS * 8)) return rc;
+    MaskedParams mp;
+    mp.x = x;
+    mp.qb = st->qb;
+    mp.mpk = st->mpk;
+    mp.A = L.s_red.as<double>();
+    mp.K = K;
+    mp.KT2 = st->KT2;
+    mp.MT = st->MT2;
+    mp.n_groups = st->n_groups2;
+    mp.n_chunks = st->n_chunks;
+    mp.n_split = n_split2;
+    mp.ldS = ldS;
+    mp.D = n_split2 > 1 ? L.d_part.as<double>() : L.d_red.as<double>();
+    launch_masked(mp, s);
+    ++L.launches;
+    if (n_split2 > 1) {
+      launch_reduce_splits(L.d_part.as<double>(), L.d_red.as<double>(), Upad, ldS, n_split2, s);
+      ++L.launches;
+    }
+    d_D = L.d_red.as<double>();
+    L.has_masked = true;
+  }
+  CU(cudaEventRecord(L.ev[3], s));
+  // ---- epilogue (A5-A7) ----
+  EpilogueParams ep;
+  ep.S = L.s_red.as<double>();
+  ep.sxx = L.sxx.as<double>();
+  ep.D = d_D;
+  ep.mask_id = st->mask_id;
+  ep.YdotY = st->YdotY + (int64_t)b->contig * P;
+  ep.Y_scale = st->Y_scale;
+  ep.n_obs = st->n_obs;
+  ep.ldS = ldS;
+  ep.K = K;
+  ep.P = P;
+  ep.G = G;
+  ep.verbose = st->verbose;
+  ep.dof = (double)st->dof;
+  ep.pc = st->pc;
+  ep.effect = d_outs[0];
+  ep.stderror = d_outs[1];
+  ep.tvalue = d_outs[2];
+  ep.pvalue = d_outs[3];
+  ep.n = st->verbose ? d_outs[4] : nullptr;
+  ep.sum_x = st->verbose ? d_outs[5] : nullptr;
+  ep.ytx = st->verbose ? d_outs[6] : nullptr;
+  launch_epilogue(ep, s);
+  ++L.launches;
+  CU(cudaEventRecord(L.ev[4], s));
+  CU(cudaGetLastError());
+  if (o->memspace == GLR_MEM_HOST) {
+    for (int i = 0; i < n_out; ++i)
+      CU(cudaMemcpyAsync(outs[i], d_outs[i], out_elems * 8, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaEventRecord(L.ev[5], s));
+  L.busy = true;
+  return 0;
+}
+
+int glr_block_wait(glr_state* st, int lane_id) {
+  if (!st) return fail(GLR_ERR_INVALID, "null state");
+  if (lane_id < 0 || lane_id >= (int)st->lanes.size()) return fail(GLR_ERR_INVALID, "lane out of range");
+  Lane& L = st->lanes[lane_id];
+  if (!L.busy) return fail(GLR_ERR_STATE, "no block in flight on this lane");
+  L.busy = false;
+  CU(cudaSetDevice(st->device));
+  CU(cudaStreamSynchronize(L.stream));
+  glr_timing t{};
+  cudaEventElapsedTime(&t.total_ms, L.ev[0], L.ev[4]);
+  cudaEventElapsedTime(&t.prepass_ms, L.ev[0], L.ev[1]);
+  cudaEventElapsedTime(&t.gram_ms, L.ev[1], L.ev[2]);
+  cudaEventElapsedTime(&t.masked_ms, L.ev[2], L.ev[3]);
+  cudaEventElapsedTime(&t.epilogue_ms, L.ev[3], L.ev[4]);
+  t.kernel_launches = L.launches;
+  L.timing = t;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int glr_run_block(glr_state* st, const glr_block_desc* blk, const glr_block_out* out) {
+  int rc = glr_block_submit(st, 0, blk, out);
+  if (rc) return rc;
+  return glr_block_wait(st, 0);
+}
+
+int glr_block_timing(glr_state* st, int lane_id, glr_timing* t) {
+  if (!st || !t) return fail(GLR_ERR_INVALID, "null argument");
+  if (lane_id < 0 || lane_id >= (int)st->lanes.size()) return fail(GLR_ERR_INVALID, "lane out of range");
+  *t = st->lanes[lane_id].timing;
+  return 0;
+}
+
+int glr_lane_stream(glr_state* st, int lane_id, void** stream) {
+  if (!st || !stream) return fail(GLR_ERR_INVALID, "null argument");
+  if (lane_id < 0 || lane_id >= (int)st->lanes.size()) return fail(GLR_ERR_INVALID, "lane out of range");
+  *stream = (void*)st->lanes[lane_id].stream;
+  return 0;
+}
+
+int glr_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return fail(GLR_ERR_INVALID, "null argument");
+  CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+int glr_host_free(void* ptr) {
+  if (ptr) CU(cudaFreeHost(ptr));
+  return 0;
+}
+
+int glr_t_two_sided_pvalues(int device, const double* tvalues, int64_t n, double dof, double* pvalues) {
+  if (n < 0 || (n > 0 && (!tvalues || !pvalues))) return fail(GLR_ERR_INVALID, "bad arguments");
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  double *dt = nullptr, *dp = nullptr;
+  CU(cudaMalloc(&dt, n * sizeof(double)));
+  CU(cudaMalloc(&dp, n * sizeof(double)));
+  CU(cudaMemcpy(dt, tvalues, n * sizeof(double), cudaMemcpyHostToDevice));
+  launch_pvalues(dt, n, make_pval_const(dof), dp, nullptr);
+  cudaError_t e = cudaMemcpy(pvalues, dp, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dt);
+  cudaFree(dp);
+  if (e != cudaSuccess) return fail(GLR_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+int glr_decode_block(int device, const glr_block_desc* b, int64_t n_geno, double* out_values) {
+  if (!b || !out_values || n_geno <= 0 || b->n_variants < 0) return fail(GLR_ERR_INVALID, "bad arguments");
+  if (b->memspace != GLR_MEM_HOST) return fail(GLR_ERR_INVALID, "glr_decode_block takes host buffers");
+  int rc = check_device(device);
+  if (rc) return rc;
+  const int G = b->n_variants;
+  if (G == 0) return 0;
+  const size_t rb = row_bytes_of(b->format, n_geno);
+  if ((size_t)b->row_stride_bytes < rb) return fail(GLR_ERR_INVALID, "row stride smaller than a row");
+  const size_t bytes = (size_t)(G - 1) * b->row_stride_bytes + rb;
+  uint8_t* dg = nullptr;
+  double *dv1 = nullptr, *dsxx = nullptr, *dout = nullptr;
+  CU(cudaMalloc(&dg, bytes + 64));
+  CU(cudaMalloc(&dv1, G * sizeof(double)));
+  CU(cudaMalloc(&dsxx, G * sizeof(double)));
+  CU(cudaMalloc(&dout, (size_t)G * n_geno * sizeof(double)));
+  CU(cudaMemcpy(dg, b->genotypes, bytes, cudaMemcpyHostToDevice));
+  BlockView x;
+  x.base = dg;
+  x.stride = b->row_stride_bytes;
+  x.n_variants = G;
+  x.format = b->format;
+  x.n_geno = n_geno;
+  x.v1 = dv1;
+  if (b->format == GLR_FMT_I8 || b->format == GLR_FMT_PLINK2) launch_prepass(x, b->missing_policy, dv1, dsxx, nullptr);
+  launch_decode(x, dout, nullptr);
+  cudaError_t e = cudaMemcpy(out_values, dout, (size_t)G * n_geno * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dg);
+  cudaFree(dv1);
+  cudaFree(dsxx);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(GLR_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

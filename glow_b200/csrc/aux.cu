@@ -1,0 +1,343 @@
+// Memory-bound and once-per-call kernels: decode pre-pass, split reduction, statistics epilogue,
+// operand packing.  The FP64 tensor-core contractions live in contract.cuh.
+#include <algorithm>
+
+#include "contract.cuh"
+
+namespace glr {
+
+// ------------------------------------------------------------------------------------------------
+// element decode shared by the non-GEMM kernels (A0 semantics)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double decode_elem(const BlockView& x, const uint8_t* row, int64_t s, double miss) {
+  switch (x.format) {
+    case GLR_FMT_F64: return reinterpret_cast<const double*>(row)[s];
+    case GLR_FMT_F32: return (double)reinterpret_cast<const float*>(row)[s];
+    case GLR_FMT_I8: {
+      const int v = (int)reinterpret_cast<const int8_t*>(row)[s];
+      return v == -1 ? miss : (double)v;
+    }
+    default: {
+      const uint32_t code = (row[s >> 2] >> (2 * (s & 3))) & 3u;
+      return XLoader<GLR_FMT_PLINK2, 1>::dec(code, miss);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pre-pass (PLINK2 / I8): one CTA per variant; integer counts -> missing substitute + sum x^2.
+// HBM-bound: reads the block once (N/4 bytes per variant for 2-bit).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPreThreads = 256;
+
+__device__ __forceinline__ long long block_sum_ll(long long v, long long* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  long long t = 0;
+  for (int w = 0; w < kPreThreads / 32; ++w) t += sh[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(kPreThreads) prepass_kernel(BlockView x, int policy, double* v1, double* sxx) {
+  __shared__ long long sh[kPreThreads / 32];
+  const int g = blockIdx.x;
+  const uint8_t* row = x.base + (int64_t)g * x.stride;
+  const int64_t n = x.n_geno;
+  long long c_miss = 0, s1 = 0, s2 = 0;  // missing count, sum x, sum x^2 over non-missing
+  if (x.format == GLR_FMT_PLINK2) {
+    // codes: 00 -> 2, 01 -> missing, 10 -> 1, 11 -> 0
+    const int64_t full_bytes = n >> 2;
+    const uint8_t* p = row;
+    const uint8_t* pe = row + full_bytes;
+    const uint8_t* a0 = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+    if (a0 > pe) a0 = pe;
+    const uint8_t* a1 = a0 + ((pe - a0) & ~(int64_t)15);
+    long long c00 = 0, c01 = 0, c10 = 0;
+    // 16-byte aligned middle
+    const uint4* q = reinterpret_cast<const uint4*>(a0);
+    const int64_t nq = (a1 - a0) >> 4;
+    for (int64_t i = threadIdx.x; i < nq; i += kPreThreads) {
+      const uint4 w4 = __ldg(q + i);
+      const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t lo = ws[k] & 0x55555555u, hi = (ws[k] >> 1) & 0x55555555u;
+        c01 += __popc(lo & ~hi);
+        c10 += __popc(hi & ~lo);
+        c00 += __popc(~(lo | hi) & 0x55555555u);
+      }
+    }
+    // unaligned head / tail bytes and the final partial byte
+    const int64_t head = a0 - p, tail = pe - a1;
+    for (int64_t i = threadIdx.x; i < head + tail + 1; i += kPreThreads) {
+      const uint8_t* bp;
+      int valid = 4;
+      if (i < head) {
+        bp = p + i;
+      } else if (i < head + tail) {
+        bp = a1 + (i - head);
+      } else {
+        bp = pe;
+        valid = (int)(n & 3);
+      }
+      if (valid) {
+        const uint32_t b = *bp;
+        for (int k = 0; k < valid; ++k) {
+          const uint32_t code = (b >> (2 * k)) & 3u;
+          c00 += code == 0u;
+          c01 += code == 1u;
+          c10 += code == 2u;
+        }
+      }
+    }
+    c_miss = c01;
+    s1 = 2 * c00 + c10;
+    s2 = 4 * c00 + c10;
+  } else {  // I8
+    const int8_t* r8 = reinterpret_cast<const int8_t*>(row);
+    for (int64_t s = threadIdx.x; s < n; s += kPreThreads) {
+      const int v = r8[s];
+      if (v == -1) {
+        ++c_miss;
+      } else {
+        s1 += v;
+        s2 += v * v;
+      }
+    }
+  }
+  c_miss = block_sum_ll(c_miss, sh);
+  s1 = block_sum_ll(s1, sh);
+  s2 = block_sum_ll(s2, sh);
+  if (threadIdx.x == 0) {
+    double m = -1.0;
+    if (policy == GLR_MISSING_MEAN && c_miss < n) m = (double)s1 / (double)(n - c_miss);  // MeanSubstitute.scala:57-84
+    v1[g] = m;
+    sxx[g] = (double)s2 + (m * m) * (double)c_miss;
+  }
+}
+
+void launch_prepass(const BlockView& x, int missing_policy, double* v1, double* sxx, cudaStream_t st) {
+  if (x.n_variants <= 0) return;
+  prepass_kernel<<<x.n_variants, kPreThreads, 0, st>>>(x, missing_policy, v1, sxx);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void reduce_splits_kernel(const double* part, double* out, int64_t total, int n_split) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  double s = part[i];
+  for (int z = 1; z < n_split; ++z) s += part[(int64_t)z * total + i];
+  out[i] = s;
+}
+void launch_reduce_splits(const double* part, double* out, int64_t rows, int64_t ld, int n_split, cudaStream_t st) {
+  const int64_t total = rows * ld;
+  if (total <= 0) return;
+  reduce_splits_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, out, total, n_split);
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue: lin_reg.py:241-249 per (phenotype, variant); variants on x (coalesced), phenotypes
+// strided over y.  HBM-bound on the 4 x 8 B result writes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEpiThreads = 128;
+constexpr int kEpiPhenoPerBlock = 8;
+
+__global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpilogueParams p) {
+  const int v = blockIdx.x * kEpiThreads + threadIdx.x;
+  if (v >= p.G) return;
+  // XdotX for fully observed phenotypes: sum x^2 - |Q^T x|^2  (= |x - Q Q^T x|^2)
+  double a2 = 0.0;
+  for (int k = 0; k < p.K; ++k) {
+    const double a = p.S[(int64_t)k * p.ldS + v];
+    a2 = fma(a, a, a2);
+  }
+  const double xx_full = p.sxx[v] - a2;
+  const int p0 = blockIdx.y * kEpiPhenoPerBlock;
+  const int p1 = min(p.P, p0 + kEpiPhenoPerBlock);
+  for (int ph = p0; ph < p1; ++ph) {
+    const int mid = p.mask_id[ph];
+    const double XdotX = mid < 0 ? xx_full : p.D[(int64_t)mid * p.ldS + v];
+    const double XdotY = p.S[(int64_t)(p.K + ph) * p.ldS + v];
+    const double recip = 1.0 / XdotX;                                             // lin_reg.py:241
+    const double beta = XdotY * recip;                                            // :242
+    const double se = sqrt((p.YdotY[ph] * recip - beta * beta) / p.dof);          // :243
+    const double T = beta / se;                                                   // :244
+    const double pv = t_two_sided_pvalue(T, p.pc);                                // :245
+    const int64_t o = (int64_t)ph * p.G + v;
+    p.effect[o] = beta * p.Y_scale[ph];                                           // :247-248
+    p.stderror[o] = se * p.Y_scale[ph];                                           // :249
+    p.tvalue[o] = T;
+    p.pvalue[o] = pv;
+    if (p.verbose) {                                                              // :234-237
+      p.n[o] = p.n_obs[ph];
+      p.sum_x[o] = p.S[(int64_t)(p.K + p.P + ph) * p.ldS + v];
+      p.ytx[o] = p.S[(int64_t)(p.K + 2 * p.P + ph) * p.ldS + v];
+    }
+  }
+}
+void launch_epilogue(const EpilogueParams& p, cudaStream_t st) {
+  if (p.G <= 0 || p.P <= 0) return;
+  dim3 grid((unsigned)ceil_div(p.G, kEpiThreads), (unsigned)ceil_div(p.P, kEpiPhenoPerBlock));
+  epilogue_kernel<<<grid, kEpiThreads, 0, st>>>(p);
+}
+
+__global__ void pvalues_kernel(const double* t, int64_t n, PvalConst pc, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = t_two_sided_pvalue(t[i], pc);
+}
+void launch_pvalues(const double* t, int64_t n, PvalConst pc, double* p, cudaStream_t st) {
+  if (n <= 0) return;
+  pvalues_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(t, n, pc, p);
+}
+
+__global__ void decode_kernel(BlockView x, double* out) {
+  const int g = blockIdx.y;
+  const uint8_t* row = x.base + (int64_t)g * x.stride;
+  const double miss = (x.format == GLR_FMT_I8 || x.format == GLR_FMT_PLINK2) ? x.v1[g] : 0.0;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < x.n_geno; s += (int64_t)gridDim.x * blockDim.x)
+    out[(int64_t)g * x.n_geno + s] = decode_elem(x, row, s, miss);
+}
+void launch_decode(const BlockView& x, double* out, cudaStream_t st) {
+  if (x.n_variants <= 0 || x.n_geno <= 0) return;
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(x.n_geno, 256), (int64_t)64), (unsigned)x.n_variants);
+  decode_kernel<<<grid, 256, 0, st>>>(x, out);
+}
+
+__global__ void dropped_sumsq_kernel(BlockView x, const int64_t* drop_idx, int64_t n_drop, double* sxx) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= x.n_variants) return;
+  const uint8_t* row = x.base + (int64_t)g * x.stride;
+  const double miss = (x.format == GLR_FMT_I8 || x.format == GLR_FMT_PLINK2) ? x.v1[g] : 0.0;
+  double s = 0.0;
+  for (int64_t i = 0; i < n_drop; ++i) {
+    const double v = decode_elem(x, row, drop_idx[i], miss);
+    s = fma(v, v, s);
+  }
+  sxx[g] -= s;
+}
+void launch_dropped_sumsq(const BlockView& x, const int64_t* drop_idx, int64_t n_drop, double* sxx, cudaStream_t st) {
+  if (x.n_variants <= 0 || n_drop <= 0) return;
+  dropped_sumsq_kernel<<<(unsigned)ceil_div(x.n_variants, 128), 128, 0, st>>>(x, drop_idx, n_drop, sxx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// state packing (runs once per linear_regression call)
+// ------------------------------------------------------------------------------------------------
+// T[k][p] = sum_s Q[s][k] Y[s][p]; one CTA per (p, k), fixed-order tree reduction (deterministic)
+__global__ void __launch_bounds__(256) qty_kernel(const double* Q, const double* Y, int64_t N, int K, int P, double* T) {
+  __shared__ double sh[256];
+  const int ph = blockIdx.x, k = blockIdx.y;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += 256) s = fma(Q[i * K + k], Y[i * P + ph], s);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) T[(int64_t)k * P + ph] = sh[0];
+}
+void launch_qty(const double* Q, const double* Y, int64_t N, int K, int P, double* T, cudaStream_t st) {
+  if (K <= 0 || P <= 0) return;
+  qty_kernel<<<dim3((unsigned)P, (unsigned)K), 256, 0, st>>>(Q, Y, N, K, P, T);
+}
+__global__ void residualize_kernel(const double* Q, const double* T, double* Y, int64_t N, int K, int P) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * P) return;
+  const int64_t s = i / P;
+  const int ph = (int)(i % P);
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) acc = fma(Q[s * K + k], T[(int64_t)k * P + ph], acc);
+  Y[i] -= acc;
+}
+void launch_residualize(const double* Q, const double* T, double* Y, int64_t N, int K, int P, cudaStream_t st) {
+  if (N * P <= 0) return;
+  residualize_kernel<<<(unsigned)ceil_div(N * P, 256), 256, 0, st>>>(Q, T, Y, N, K, P);
+}
+
+// dst layout: [group][chunk][8 sample groups][MT][64]; element (lane*2 + h) of an atom =
+// M[s0 + 2*(lane&3) + h][col0 + (lane>>2)]
+__global__ void pack_a_kernel(const double* src, int64_t N, int64_t ld, int c0, int ncols, const int64_t* geno_to_row,
+                              int64_t Ng, double* dst, int dst_col0, int MT, int64_t n_chunks) {
+  const int64_t total = (int64_t)ncols * n_chunks * kChunk;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % ncols);       // source column (fastest: coalesced reads of a row)
+  const int64_t sg = i / ncols;         // genotype-sample index, padded
+  double v = 0.0;
+  if (sg < Ng) {
+    const int64_t row = geno_to_row ? geno_to_row[sg] : sg;
+    if (row >= 0 && row < N) v = src[row * ld + c0 + c];
+  }
+  const int dcol = dst_col0 + c;
+  const int group = dcol / (MT * 8), mt = (dcol / 8) % MT, r = dcol % 8;
+  const int64_t chunk = sg / kChunk;
+  const int g = (int)((sg % kChunk) / kGroup);
+  const int w = (int)(sg % kGroup);
+  const int j = w >> 1, h = w & 1;
+  const int64_t atom = ((group * n_chunks + chunk) * kChunkGroups + g) * MT + mt;
+  dst[atom * kAtomDoubles + (4 * r + j) * 2 + h] = v;
+}
+void launch_pack_a(const double* src, int64_t N, int64_t ld, int c0, int ncols, const int64_t* geno_to_row,
+                   int64_t Ng, double* dst, int dst_col0, int MT, int64_t n_chunks, cudaStream_t st) {
+  const int64_t total = (int64_t)ncols * n_chunks * kChunk;
+  if (total <= 0) return;
+  pack_a_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(src, N, ld, c0, ncols, geno_to_row, Ng, dst, dst_col0,
+                                                                 MT, n_chunks);
+}
+
+// dst layout: [chunk][8 sample groups][KT2][64]; element (lane*2 + h) = Q[s0 + (lane>>2)][4*(2*k2 + h) + (lane&3)]
+__global__ void pack_qb_kernel(const double* Q, int64_t N, int K, const int64_t* geno_to_row, int64_t Ng, double* dst,
+                               int KT2, int64_t n_chunks) {
+  const int kpad = KT2 * 8;
+  const int64_t total = (int64_t)kpad * n_chunks * kChunk;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % kpad);
+  const int64_t sg = i / kpad;
+  double v = 0.0;
+  if (sg < Ng && k < K) {
+    const int64_t row = geno_to_row ? geno_to_row[sg] : sg;
+    if (row >= 0 && row < N) v = Q[row * K + k];
+  }
+  const int64_t chunk = sg / kChunk;
+  const int g = (int)((sg % kChunk) / kGroup);
+  const int n = (int)(sg % kGroup);          // sample within group = output column of the residual product
+  const int kk = k >> 2, jj = k & 3;         // k-step, lane column
+  const int k2 = kk >> 1, h = kk & 1;
+  const int64_t atom = (chunk * kChunkGroups + g) * KT2 + k2;
+  dst[atom * kAtomDoubles + (4 * n + jj) * 2 + h] = v;
+}
+void launch_pack_qb(const double* Q, int64_t N, int K, const int64_t* geno_to_row, int64_t Ng, double* dst, int KT2,
+                    int64_t n_chunks, cudaStream_t st) {
+  const int64_t total = (int64_t)KT2 * 8 * n_chunks * kChunk;
+  if (total <= 0) return;
+  pack_qb_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(Q, N, K, geno_to_row, Ng, dst, KT2, n_chunks);
+}
+
+// ------------------------------------------------------------------------------------------------
+int gram_tile_variants(int nt) { return kWarps * nt * 8; }
+
+void launch_gram(const GramParams& p, cudaStream_t st) {
+  if (p.x.n_variants <= 0) return;
+  switch (p.x.format) {
+    case GLR_FMT_F64: launch_gram_f64(p, st); break;
+    case GLR_FMT_F32: launch_gram_f32(p, st); break;
+    case GLR_FMT_I8: launch_gram_i8(p, st); break;
+    default: launch_gram_p2(p, st); break;
+  }
+}
+void launch_masked(const MaskedParams& p, cudaStream_t st) {
+  if (p.x.n_variants <= 0) return;
+  switch (p.x.format) {
+    case GLR_FMT_F64: launch_masked_f64(p, st); break;
+    case GLR_FMT_F32: launch_masked_f32(p, st); break;
+    case GLR_FMT_I8: launch_masked_i8(p, st); break;
+    default: launch_masked_p2(p, st); break;
+  }
+}
+
+}  // namespace glr

@@ -1,0 +1,537 @@
+// FP64 tensor-core contraction kernels with the genotype decode fused into the operand load.
+//
+//   gram_kernel   : S = W^T X              (pass 1; W = [Q | Ytilde | verbose columns], packed)
+//   masked_kernel : D = Mu^T (X - Q A)^2   (pass 2; only for phenotypes with missing samples)
+//
+// Replaces np.column_stack + _residualize_in_place + `Y.T @ X` + the masked einsum of
+// python/glow/gwas/lin_reg.py:226-241 (and functions.py:136-143, :78-82).
+//
+// CTA = 8 consumer warps + 1 producer warp.  The producer streams the packed, shared operand
+// (W / Q / masks) through a 4-stage shared-memory ring with bulk async copies (TMA engine,
+// cp.async.bulk + mbarrier complete_tx); consumers wait on the stage's "full" barrier, read their
+// A fragments with conflict-free 16-byte LDS and release the stage on its "empty" barrier.
+// The genotype operand never touches shared memory: each lane loads exactly the bytes of its own
+// B fragments from global/L2 (2-bit: one 16-byte row segment per 64 samples) one unit ahead of use
+// and decodes them in registers.
+#pragma once
+#include "../../include/glow_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace glr {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = (kWarps + 1) * 32;
+constexpr int kStages = 4;
+constexpr int kBarBytes = 128;  // full[4] + empty[4] mbarriers, padded
+
+// ------------------------------------------------------------------------------------------------
+// Genotype loaders: one per format.  A "unit" is UG sample groups (8 samples each) for all NT
+// n-tiles of the warp.  load() fills the `nxt` registers, advance() makes them current, get()
+// decodes the two values this lane owns in group g of the current unit (samples 2j, 2j+1 of the
+// group).  Samples at or beyond n_geno decode to a finite value (0 for float formats): the packed
+// shared operand is zero there, so they contribute nothing.
+// ------------------------------------------------------------------------------------------------
+template <int FMT, int NT>
+struct XLoader;
+
+template <int NT>
+struct XLoader<GLR_FMT_PLINK2, NT> {
+  static constexpr int UG = 8;  // one 64-sample chunk = 16 bytes per variant
+  const uint8_t* row[NT];
+  double v1[NT];
+  uint32_t cur[NT][5], nxt[NT][5];
+  uint32_t sh_cur[NT], sh_nxt[NT];
+  int64_t row_bytes;
+  int nib_shift;
+
+  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j) {
+    row_bytes = (x.n_geno + 3) >> 2;
+    nib_shift = 4 * j;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      int v = min(v0 + nt * 8 + r, x.n_variants - 1);
+      row[nt] = x.base + (int64_t)v * x.stride;
+      v1[nt] = x.v1[v];
+    }
+  }
+  __device__ __forceinline__ void load(int64_t s0) {
+    const int64_t b0 = s0 >> 2;
+    const bool fast = b0 + 19 <= row_bytes;  // every word touched lies inside the row
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const uint8_t* p = row[nt] + b0;
+      if (fast) {
+        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nxt[nt][i] = __ldg(q + i);
+        nxt[nt][4] = a ? __ldg(q + 4) : 0u;
+        sh_nxt[nt] = a * 8;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int64_t off = b0 + i * 4 + b;
+            // beyond the row: 0xFF = code 11 everywhere = 0.0
+            const uint32_t byte = off < row_bytes ? (uint32_t)__ldg(row[nt] + off) : 0xFFu;
+            w |= byte << (8 * b);
+          }
+          nxt[nt][i] = w;
+        }
+        nxt[nt][4] = 0u;
+        sh_nxt[nt] = 0;
+      }
+    }
+  }
+  __device__ __forceinline__ void advance() {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) cur[nt][i] = nxt[nt][i];
+      sh_cur[nt] = sh_nxt[nt];
+    }
+  }
+  static __device__ __forceinline__ double dec(uint32_t code, double miss) {
+    // 00 -> 2, 01 -> missing, 10 -> 1, 11 -> 0  (PlinkRowToInternalRowConverter.scala:40-47 + genotype_states)
+    const int hi = (code == 0u) ? 0x40000000 : ((code == 2u) ? 0x3FF00000 : 0);
+    const double v = __hiloint2double(hi, 0);
+    return (code == 1u) ? miss : v;
+  }
+  __device__ __forceinline__ void get(int g, int nt, double& xa, double& xb) const {
+    const int i = g >> 1;
+    const uint32_t w = __funnelshift_r(cur[nt][i], cur[nt][i + 1], sh_cur[nt]);
+    const uint32_t nib = (w >> (16 * (g & 1) + nib_shift)) & 15u;
+    xa = dec(nib & 3u, v1[nt]);
+    xb = dec(nib >> 2, v1[nt]);
+  }
+};
+
+// float64 / float32 arrays
+template <typename T, int NT>
+struct XLoaderFloat {
+  static constexpr int UG = 4;
+  using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+  const T* row[NT];
+  T2 cur[NT][UG], nxt[NT][UG];
+  int64_t n;
+  int joff;
+  bool vec;
+
+  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j) {
+    n = x.n_geno;
+    joff = 2 * j;
+    vec = ((reinterpret_cast<uintptr_t>(x.base) | (uintptr_t)x.stride) & (2 * sizeof(T) - 1)) == 0;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      int v = min(v0 + nt * 8 + r, x.n_variants - 1);
+      row[nt] = reinterpret_cast<const T*>(x.base + (int64_t)v * x.stride);
+    }
+  }
+  __device__ __forceinline__ void load(int64_t s0) {
+    const bool fast = s0 + UG * 8 <= n;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int g = 0; g < UG; ++g) {
+        const int64_t s = s0 + 8 * g + joff;
+        const T* p = row[nt] + s;
+        T2 v;
+        if (fast && vec) {
+          v = __ldg(reinterpret_cast<const T2*>(p));
+        } else if (fast) {
+          v.x = __ldg(p);
+          v.y = __ldg(p + 1);
+        } else {
+          v.x = s < n ? __ldg(p) : T(0);
+          v.y = s + 1 < n ? __ldg(p + 1) : T(0);
+        }
+        nxt[nt][g] = v;
+      }
+    }
+  }
+  __device__ __forceinline__ void advance() {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int g = 0; g < UG; ++g) cur[nt][g] = nxt[nt][g];
+  }
+  __device__ __forceinline__ void get(int g, int nt, double& xa, double& xb) const {
+    xa = (double)cur[nt][g].x;
+    xb = (double)cur[nt][g].y;
+  }
+};
+template <int NT>
+struct XLoader<GLR_FMT_F64, NT> : XLoaderFloat<double, NT> {};
+template <int NT>
+struct XLoader<GLR_FMT_F32, NT> : XLoaderFloat<float, NT> {};
+
+// int8 genotype states, -1 = missing
+template <int NT>
+struct XLoader<GLR_FMT_I8, NT> {
+  static constexpr int UG = 8;
+  const int8_t* row[NT];
+  double v1[NT];
+  int cur[NT][UG], nxt[NT][UG];  // two int8 packed in the low 16 bits
+  int64_t n;
+  int joff;
+
+  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j) {
+    n = x.n_geno;
+    joff = 2 * j;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      int v = min(v0 + nt * 8 + r, x.n_variants - 1);
+      row[nt] = reinterpret_cast<const int8_t*>(x.base + (int64_t)v * x.stride);
+      v1[nt] = x.v1[v];
+    }
+  }
+  __device__ __forceinline__ void load(int64_t s0) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int g = 0; g < UG; ++g) {
+        const int64_t s = s0 + 8 * g + joff;
+        const int a = s < n ? (int)__ldg(row[nt] + s) : 0;
+        const int b = s + 1 < n ? (int)__ldg(row[nt] + s + 1) : 0;
+        nxt[nt][g] = (a & 0xFF) | ((b & 0xFF) << 8);
+      }
+    }
+  }
+  __device__ __forceinline__ void advance() {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int g = 0; g < UG; ++g) cur[nt][g] = nxt[nt][g];
+  }
+  __device__ __forceinline__ void get(int g, int nt, double& xa, double& xb) const {
+    const int a = (int)(int8_t)(cur[nt][g] & 0xFF);
+    const int b = (int)(int8_t)((cur[nt][g] >> 8) & 0xFF);
+    xa = a == -1 ? v1[nt] : (double)a;
+    xb = b == -1 ? v1[nt] : (double)b;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory ring
+// ------------------------------------------------------------------------------------------------
+struct Ring {
+  uint64_t* full;
+  uint64_t* empty;
+  __device__ __forceinline__ void init(unsigned char* smem, int tid) {
+    full = reinterpret_cast<uint64_t*>(smem);
+    empty = full + kStages;
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], kWarps);
+      }
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// pass 1
+// ------------------------------------------------------------------------------------------------
+template <int FMT, int MT, int NT>
+__global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kStageDoubles = kChunkGroups * MT * kAtomDoubles;
+  constexpr uint32_t kStageBytes = kStageDoubles * 8;
+  using Loader = XLoader<FMT, NT>;
+  constexpr int UG = Loader::UG;
+  constexpr int UPC = kChunkGroups / UG;  // units per chunk
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Ring ring;
+  ring.init(smem, tid);
+  double* wst = reinterpret_cast<double*>(smem + kBarBytes);
+
+  const int64_t cps = ceil_div(p.n_chunks, p.n_split);
+  const int64_t c_begin = (int64_t)blockIdx.z * cps;
+  const int64_t c_end = min(p.n_chunks, c_begin + cps);
+  const int64_t n_it = c_end > c_begin ? c_end - c_begin : 0;
+
+  if (warp == kWarps) {  // producer warp: one lane drives the TMA engine
+    if (lane == 0) {
+      const double* src = p.wpk + ((int64_t)blockIdx.y * p.n_chunks + c_begin) * kStageDoubles;
+      for (int64_t it = 0; it < n_it; ++it) {
+        const int s = (int)(it % kStages);
+        if (it >= kStages) mbar_wait(&ring.empty[s], (uint32_t)((it / kStages) & 1) ^ 1u);
+        mbar_expect_tx(&ring.full[s], kStageBytes);
+        bulk_g2s(wst + (int64_t)s * kStageDoubles, src + it * kStageDoubles, kStageBytes, &ring.full[s]);
+      }
+    }
+    return;
+  }
+
+  const int r = lane >> 2, j = lane & 3;
+  const int v_warp = blockIdx.x * (kWarps * NT * 8) + warp * (NT * 8);
+  Loader ld;
+  ld.init(p.x, v_warp, r, j);
+
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  double sq[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) sq[nt] = 0.0;
+  const bool want_sq = (FMT == GLR_FMT_F64 || FMT == GLR_FMT_F32) && blockIdx.y == 0;
+
+  const int64_t t_total = n_it * UPC;
+  const int64_t s_begin = c_begin * kChunk;
+  if (t_total > 0) ld.load(s_begin);
+  for (int64_t it = 0; it < n_it; ++it) {
+    const int s = (int)(it % kStages);
+    mbar_wait(&ring.full[s], (uint32_t)((it / kStages) & 1));
+    const double* st = wst + (int64_t)s * kStageDoubles;
+#pragma unroll
+    for (int u = 0; u < UPC; ++u) {
+      ld.advance();
+      const int64_t t = it * UPC + u + 1;
+      if (t < t_total) ld.load(s_begin + t * (UG * kGroup));
+#pragma unroll
+      for (int g = 0; g < UG; ++g) {
+        const double2* ap = reinterpret_cast<const double2*>(st + (int64_t)(u * UG + g) * MT * kAtomDoubles) + lane;
+        double2 a[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) a[mt] = ap[mt * 32];
+        double xa[NT], xb[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) ld.get(g, nt, xa[nt], xb[nt]);
+        if (FMT == GLR_FMT_F64 || FMT == GLR_FMT_F32) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) sq[nt] = fma(xa[nt], xa[nt], fma(xb[nt], xb[nt], sq[nt]));
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, xa[nt]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, xb[nt]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[s]);
+  }
+
+  // C fragment: lane (r, j) holds rows r of each m-tile, variants 2j, 2j+1 of each n-tile
+  const int64_t rows = (int64_t)p.n_groups * MT * 8;
+  double* Sz = p.S + (int64_t)blockIdx.z * rows * p.ldS;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int64_t row = ((int64_t)blockIdx.y * MT + mt) * 8 + r;
+      const int64_t col = v_warp + nt * 8 + 2 * j;
+      *reinterpret_cast<double2*>(Sz + row * p.ldS + col) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+  if (want_sq) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      double v = sq[nt];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (j == 0) p.sxx_part[(int64_t)blockIdx.z * p.ldS + v_warp + nt * 8 + r] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: residualise in registers with DMMA, square, contract with the 0/1 masks
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaskedNT = 2;
+constexpr int kMaxKT = 8;  // K <= 32 covariates in the masked pass
+
+template <int FMT, int MT>
+__global__ void __launch_bounds__(kThreads, 1) masked_kernel(const MaskedParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NT = kMaskedNT;
+  using Loader = XLoader<FMT, NT>;
+  constexpr int UG = Loader::UG;
+  constexpr int UPC = kChunkGroups / UG;
+
+  const int KT2 = p.KT2;
+  const int mStageDoubles = kChunkGroups * MT * kAtomDoubles;
+  const int qStageDoubles = kChunkGroups * KT2 * kAtomDoubles;
+  const int stageDoubles = mStageDoubles + qStageDoubles;
+  const uint32_t stageBytes = (uint32_t)stageDoubles * 8;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Ring ring;
+  ring.init(smem, tid);
+  double* stage0 = reinterpret_cast<double*>(smem + kBarBytes);
+  double* negA_s = stage0 + (int64_t)kStages * stageDoubles;  // [kWarps][NT][2*KT2][32]
+
+  const int64_t cps = ceil_div(p.n_chunks, p.n_split);
+  const int64_t c_begin = (int64_t)blockIdx.z * cps;
+  const int64_t c_end = min(p.n_chunks, c_begin + cps);
+  const int64_t n_it = c_end > c_begin ? c_end - c_begin : 0;
+
+  if (warp == kWarps) {
+    if (lane == 0) {
+      const double* msrc = p.mpk + ((int64_t)blockIdx.y * p.n_chunks + c_begin) * mStageDoubles;
+      const double* qsrc = p.qb + c_begin * qStageDoubles;
+      for (int64_t it = 0; it < n_it; ++it) {
+        const int s = (int)(it % kStages);
+        if (it >= kStages) mbar_wait(&ring.empty[s], (uint32_t)((it / kStages) & 1) ^ 1u);
+        mbar_expect_tx(&ring.full[s], stageBytes);
+        double* dst = stage0 + (int64_t)s * stageDoubles;
+        bulk_g2s(dst, msrc + it * mStageDoubles, (uint32_t)mStageDoubles * 8, &ring.full[s]);
+        bulk_g2s(dst + mStageDoubles, qsrc + it * qStageDoubles, (uint32_t)qStageDoubles * 8, &ring.full[s]);
+      }
+    }
+    return;
+  }
+
+  const int r = lane >> 2, j = lane & 3;
+  const int v_warp = blockIdx.x * (kWarps * NT * 8) + warp * (NT * 8);
+  Loader ld;
+  ld.init(p.x, v_warp, r, j);
+
+  // A operand of the residual product: lane (r, j) holds -a[4*kk + j][variant r] for k-step kk
+  double* negA = negA_s + (int64_t)warp * NT * 2 * KT2 * 32;
+  for (int nt = 0; nt < NT; ++nt)
+    for (int kk = 0; kk < 2 * KT2; ++kk) {
+      const int k = 4 * kk + j;
+      const int64_t v = v_warp + nt * 8 + r;
+      negA[(nt * 2 * KT2 + kk) * 32 + lane] = k < p.K ? -p.A[(int64_t)k * p.ldS + v] : 0.0;
+    }
+  __syncwarp();
+
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  const int64_t t_total = n_it * UPC;
+  const int64_t s_begin = c_begin * kChunk;
+  if (t_total > 0) ld.load(s_begin);
+  for (int64_t it = 0; it < n_it; ++it) {
+    const int s = (int)(it % kStages);
+    mbar_wait(&ring.full[s], (uint32_t)((it / kStages) & 1));
+    const double* mst = stage0 + (int64_t)s * stageDoubles;
+    const double* qst = mst + mStageDoubles;
+#pragma unroll
+    for (int u = 0; u < UPC; ++u) {
+      ld.advance();
+      const int64_t t = it * UPC + u + 1;
+      if (t < t_total) ld.load(s_begin + t * (UG * kGroup));
+#pragma unroll
+      for (int g = 0; g < UG; ++g) {
+        const int gg = u * UG + g;
+        double ra[NT], rb[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) ld.get(g, nt, ra[nt], rb[nt]);
+        // r = x - sum_k Q[s][k] a[k][v]: C[variant][sample] += (-a)^T[variant][k] * Q^T[k][sample]
+        const double2* qp = reinterpret_cast<const double2*>(qst + (int64_t)gg * KT2 * kAtomDoubles) + lane;
+        for (int k2 = 0; k2 < KT2; ++k2) {
+          const double2 qv = qp[k2 * 32];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const double a0 = negA[(nt * 2 * KT2 + 2 * k2) * 32 + lane];
+            const double a1 = negA[(nt * 2 * KT2 + 2 * k2 + 1) * 32 + lane];
+            dmma884(ra[nt], rb[nt], a0, qv.x);
+            dmma884(ra[nt], rb[nt], a1, qv.y);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          ra[nt] *= ra[nt];
+          rb[nt] *= rb[nt];
+        }
+        const double2* mp = reinterpret_cast<const double2*>(mst + (int64_t)gg * MT * kAtomDoubles) + lane;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const double2 m = mp[mt * 32];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            dmma884(acc[mt][nt][0], acc[mt][nt][1], m.x, ra[nt]);
+            dmma884(acc[mt][nt][0], acc[mt][nt][1], m.y, rb[nt]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[s]);
+  }
+
+  const int64_t rows = (int64_t)p.n_groups * MT * 8;
+  double* Dz = p.D + (int64_t)blockIdx.z * rows * p.ldS;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int64_t row = ((int64_t)blockIdx.y * MT + mt) * 8 + r;
+      const int64_t col = v_warp + nt * 8 + 2 * j;
+      *reinterpret_cast<double2*>(Dz + row * p.ldS + col) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-format dispatch (instantiated in gram_<fmt>.cu so the formats compile in parallel)
+// ------------------------------------------------------------------------------------------------
+template <int FMT, int MT, int NT>
+void launch_gram_inst(const GramParams& p, cudaStream_t st) {
+  const int tile = kWarps * NT * 8;
+  dim3 grid((unsigned)ceil_div(p.x.n_variants, tile), (unsigned)p.n_groups, (unsigned)p.n_split);
+  const size_t smem = kBarBytes + (size_t)kStages * kChunkGroups * MT * kAtomDoubles * 8;
+  auto kern = gram_kernel<FMT, MT, NT>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, kThreads, smem, st>>>(p);
+}
+
+template <int FMT, int NT>
+void launch_gram_mt(const GramParams& p, cudaStream_t st) {
+  switch (p.MT) {
+    case 1: launch_gram_inst<FMT, 1, NT>(p, st); break;
+    case 2: launch_gram_inst<FMT, 2, NT>(p, st); break;
+    case 3: launch_gram_inst<FMT, 3, NT>(p, st); break;
+    case 4: launch_gram_inst<FMT, 4, NT>(p, st); break;
+    case 6: launch_gram_inst<FMT, 6, NT>(p, st); break;
+    default: launch_gram_inst<FMT, 8, NT>(p, st); break;
+  }
+}
+
+template <int FMT, int MT>
+void launch_masked_inst(const MaskedParams& p, cudaStream_t st) {
+  const int tile = kWarps * kMaskedNT * 8;
+  dim3 grid((unsigned)ceil_div(p.x.n_variants, tile), (unsigned)p.n_groups, (unsigned)p.n_split);
+  const size_t stage = (size_t)kChunkGroups * (MT + p.KT2) * kAtomDoubles * 8;
+  const size_t smem = kBarBytes + kStages * stage + (size_t)kWarps * kMaskedNT * 2 * p.KT2 * 32 * 8;
+  auto kern = masked_kernel<FMT, MT>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, kThreads, smem, st>>>(p);
+}
+
+template <int FMT>
+void launch_masked_mt(const MaskedParams& p, cudaStream_t st) {
+  switch (p.MT) {
+    case 1: launch_masked_inst<FMT, 1>(p, st); break;
+    case 2: launch_masked_inst<FMT, 2>(p, st); break;
+    case 4: launch_masked_inst<FMT, 4>(p, st); break;
+    default: launch_masked_inst<FMT, 8>(p, st); break;
+  }
+}
+
+// defined one per format translation unit
+void launch_gram_f64(const GramParams& p, cudaStream_t st);
+void launch_gram_f32(const GramParams& p, cudaStream_t st);
+void launch_gram_i8(const GramParams& p, cudaStream_t st);
+void launch_gram_p2(const GramParams& p, cudaStream_t st);
+void launch_masked_f64(const MaskedParams& p, cudaStream_t st);
+void launch_masked_f32(const MaskedParams& p, cudaStream_t st);
+void launch_masked_i8(const MaskedParams& p, cudaStream_t st);
+void launch_masked_p2(const MaskedParams& p, cudaStream_t st);
+
+}  // namespace glr

@@ -1,0 +1,9 @@
+// Instantiates the contraction kernels for GLR_FMT_F64 (one translation unit per format so they build in parallel).
+#include "contract.cuh"
+
+namespace glr {
+void launch_gram_f64(const GramParams& p, cudaStream_t st) {
+  launch_gram_mt<GLR_FMT_F64, 2>(p, st);
+}
+void launch_masked_f64(const MaskedParams& p, cudaStream_t st) { launch_masked_mt<GLR_FMT_F64>(p, st); }
+}  // namespace glr

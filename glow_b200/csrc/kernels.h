@@ -1,0 +1,104 @@
+// Host-callable launchers of the CUDA kernels (internal; the public surface is include/glow_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pvalue.cuh"
+
+namespace glr {
+
+// Device-side view of one genotype block (A0/A1: replaces np.column_stack at lin_reg.py:226-227
+// by reading the variant-major rows directly as the GEMM operand).
+struct BlockView {
+  const uint8_t* base;
+  int64_t stride;     // bytes between variants
+  int32_t n_variants; // G_b
+  int32_t format;     // glr_format
+  int64_t n_geno;     // samples per variant (genotype-array length)
+  const double* v1;   // [G_b] value substituted for a missing call (I8 / PLINK2), else unused
+};
+
+// ---- pre-pass: per-variant missing substitute and sum of squares (I8 / PLINK2) ------------------
+// v1[g]  = mean of non-missing (policy MEAN; -1 if all missing) or -1
+// sxx[g] = sum_s x^2 with missing replaced by v1[g]
+void launch_prepass(const BlockView& x, int missing_policy, double* v1, double* sxx, cudaStream_t st);
+
+// ---- pass 1: S = W^T X on FP64 tensor cores ----------------------------------------------------
+struct GramParams {
+  BlockView x;
+  const double* wpk;   // packed W of this contig: [group][chunk][8 groups][MT][64]
+  int32_t MT;          // m-tiles per column group (1,2,3,4,6,8)
+  int32_t n_groups;    // column groups
+  int64_t n_chunks;    // 64-sample chunks (W is zero padded to a whole chunk)
+  int32_t n_split;     // split of the sample range across CTAs (deterministic 2-stage reduce)
+  int32_t nt;          // n-tiles (8 variants) per warp: 2 or 4
+  double* S;           // [n_split][n_groups*MT*8][ldS]
+  double* sxx_part;    // [n_split][ldS]   (F64 / F32 only, written by column group 0)
+  int64_t ldS;         // >= G_b rounded up to the CTA tile
+};
+int gram_tile_variants(int nt);  // variants per CTA
+void launch_gram(const GramParams& p, cudaStream_t st);
+
+// ---- pass 2 (only when some phenotype has missing samples): D = Mu^T (X - Q A)^2 ----------------
+struct MaskedParams {
+  BlockView x;
+  const double* qb;    // packed Q, B-operand layout: [chunk][8 groups][KT2][64]  (KT2 = pairs of k-steps)
+  const double* mpk;   // packed unique masks: [group][chunk][8][MT][64]
+  const double* A;     // coefficients Q^T X: rows 0..K-1 of the reduced S, [K][ldS]
+  int32_t K;
+  int32_t KT2;         // ceil(ceil(K/4)/2)
+  int32_t MT;
+  int32_t n_groups;
+  int64_t n_chunks;
+  int32_t n_split;
+  double* D;           // [n_split][n_groups*MT*8][ldS]
+  int64_t ldS;
+};
+void launch_masked(const MaskedParams& p, cudaStream_t st);
+
+// sums the n_split partial slabs in fixed order: out[r][v] = sum_z part[z][r][v]
+void launch_reduce_splits(const double* part, double* out, int64_t rows, int64_t ld, int n_split, cudaStream_t st);
+
+// ---- epilogue: A5-A7 (lin_reg.py:241-249) --------------------------------------------------------
+struct EpilogueParams {
+  const double* S;       // reduced [Mpad][ldS]; rows 0..K-1 = Q^T X, K..K+P-1 = Ytilde^T X,
+                         // (verbose) K+P..K+2P-1 = mask^T X, K+2P..K+3P-1 = Yraw^T X
+  const double* sxx;     // [ldS]
+  const double* D;       // reduced [Upad][ldS] or nullptr
+  const int32_t* mask_id;// [P]: -1 = fully observed phenotype, else row of D
+  const double* YdotY;   // [P] of this contig
+  const double* Y_scale; // [P]
+  const double* n_obs;   // [P] non-missing count per phenotype (verbose)
+  int64_t ldS;
+  int32_t K, P, G;
+  int32_t verbose;
+  double dof;
+  PvalConst pc;
+  double *effect, *stderror, *tvalue, *pvalue;  // [P][G]
+  double *n, *sum_x, *ytx;                      // verbose, [P][G]
+};
+void launch_epilogue(const EpilogueParams& p, cudaStream_t st);
+
+void launch_pvalues(const double* t, int64_t n, PvalConst pc, double* p, cudaStream_t st);
+void launch_decode(const BlockView& x, double* out, cudaStream_t st);  // out [G_b][n_geno]
+// sum over the listed (dropped) samples of x^2, subtracted from sxx when rows are dropped
+void launch_dropped_sumsq(const BlockView& x, const int64_t* drop_idx, int64_t n_drop, double* sxx, cudaStream_t st);
+
+// ---- state packing (once per call of linear_regression) -----------------------------------------
+struct PackDims {
+  int64_t N, Ng;
+  int32_t K, P;
+};
+// T = Q^T Y (K x P)
+void launch_qty(const double* Q, const double* Y, int64_t N, int K, int P, double* T, cudaStream_t st);
+// Ytilde = Y - Q T
+void launch_residualize(const double* Q, const double* T, double* Y, int64_t N, int K, int P, cudaStream_t st);
+// Packs columns [c0, c0+ncols) of a row-major [N x ld] matrix into pair-atom A layout at column
+// offset `dst_col0` of a packed operand with `MT` m-tiles per group.
+void launch_pack_a(const double* src, int64_t N, int64_t ld, int c0, int ncols, const int64_t* geno_to_row,
+                   int64_t Ng, double* dst, int dst_col0, int MT, int64_t n_chunks, cudaStream_t st);
+// Packs Q into the masked-pass B layout.
+void launch_pack_qb(const double* Q, int64_t N, int K, const int64_t* geno_to_row, int64_t Ng, double* dst, int KT2,
+                    int64_t n_chunks, cudaStream_t st);
+
+}  // namespace glr

@@ -1,0 +1,252 @@
+"""Device engine: owns one glr_state handle (one GPU) and runs genotype blocks through the CUDA path.
+
+This is the only place that talks to the C ABI for regression blocks.  There is no CPU fallback:
+constructing a DeviceState without the built library or without an sm_100 device raises.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+
+FORMATS = {'f64': _capi.FMT_F64, 'f32': _capi.FMT_F32, 'i8': _capi.FMT_I8, 'plink2': _capi.FMT_PLINK2}
+_ROW_BYTES = {
+    _capi.FMT_F64: lambda n: 8 * n,
+    _capi.FMT_F32: lambda n: 4 * n,
+    _capi.FMT_I8: lambda n: n,
+    _capi.FMT_PLINK2: lambda n: (n + 3) // 4,
+}
+STAT_NAMES = ('effect', 'stderror', 'tvalue', 'pvalue')
+VERBOSE_NAMES = ('n', 'sum_x', 'y_transpose_x')
+
+
+@dataclass
+class GenotypeBlock:
+    """One block of variants in a device-consumable encoding (variant-major rows)."""
+    data: np.ndarray  # 2-D, C-contiguous rows: float64/float32/int8 [G, Ng] or uint8 [G, ceil(Ng/4)]
+    format: str  # 'f64' | 'f32' | 'i8' | 'plink2'
+    missing: str = 'minus_one'  # 'minus_one' (genotype_states) | 'mean' (mean_substitute)
+
+
+def as_block(values, dt=np.float64) -> GenotypeBlock:
+    """Turns the `_glow_regression_values` column of a pandas block (a sequence of per-variant
+    arrays, lin_reg.py:226) into one contiguous variant-major matrix.  No transpose: the device
+    consumes variant-major rows directly (replaces np.column_stack, lin_reg.py:227)."""
+    if isinstance(values, GenotypeBlock):
+        return values
+    arr = values if isinstance(values, np.ndarray) and values.ndim == 2 else None
+    if arr is None:
+        seq = list(values)
+        if len(seq) == 0:
+            arr = np.empty((0, 0), dtype=dt)
+        else:
+            arr = np.stack([np.asarray(v) for v in seq])
+    if arr.dtype == np.int8:
+        return GenotypeBlock(np.ascontiguousarray(arr), 'i8')
+    want = np.dtype(dt)
+    arr = np.ascontiguousarray(arr, dtype=want)
+    return GenotypeBlock(arr, 'f32' if want == np.float32 else 'f64')
+
+
+class DeviceState:
+    """Replica of the regression state on one GPU (Q, per-contig Y, masks, scales, dof)."""
+
+    def __init__(self,
+                 Q: np.ndarray,
+                 Y: np.ndarray,
+                 Y_mask: np.ndarray,
+                 YdotY: np.ndarray,
+                 Y_scale: np.ndarray,
+                 dof: int,
+                 Y_raw: Optional[np.ndarray] = None,
+                 keep_idx: Optional[np.ndarray] = None,
+                 n_geno_samples: Optional[int] = None,
+                 device: int = 0,
+                 n_lanes: int = 2,
+                 memspace: int = _capi.MEM_HOST,
+                 dims: Optional[Tuple[int, int, int, int]] = None):
+        """Host arrays (float64, C order): Q [N,K]; Y [C,N,P] or [N,P]; Y_mask [N,P]; YdotY [C,P] or [P];
+        Y_scale [P].  With memspace=MEM_DEVICE the array arguments are integer device addresses and
+        ``dims`` = (N, K, P, C) must be given."""
+        self._lib = _capi.load()
+        self._handle = C.c_void_p()
+        if memspace == _capi.MEM_HOST:
+            Q = np.ascontiguousarray(Q, dtype=np.float64)
+            Y = np.ascontiguousarray(Y, dtype=np.float64)
+            if Y.ndim == 2:
+                Y = Y[None]
+            Y_mask = np.ascontiguousarray(Y_mask, dtype=np.float64)
+            YdotY = np.ascontiguousarray(np.atleast_2d(YdotY), dtype=np.float64)
+            Y_scale = np.ascontiguousarray(Y_scale, dtype=np.float64)
+            n_contigs, N, P = Y.shape
+            K = Q.shape[1] if Q.ndim == 2 else 0
+            if Q.size and Q.shape[0] != N:
+                raise ValueError('Q and Y must have the same number of rows')
+            if Y_mask.shape != (N, P) or YdotY.shape != (n_contigs, P) or Y_scale.shape != (P, ):
+                raise ValueError('inconsistent state array shapes')
+            if Y_raw is not None:
+                Y_raw = np.ascontiguousarray(Y_raw, dtype=np.float64)
+            addr = lambda a: None if a is None or a.size == 0 else a.ctypes.data
+            ptrs = dict(Q=addr(Q), Y=addr(Y), Y_mask=addr(Y_mask), YdotY=addr(YdotY), Y_scale=addr(Y_scale),
+                        Y_raw=addr(Y_raw))
+            self._keep = (Q, Y, Y_mask, YdotY, Y_scale, Y_raw)
+        else:
+            N, K, P, n_contigs = dims
+            ptrs = dict(Q=Q, Y=Y, Y_mask=Y_mask, YdotY=YdotY, Y_scale=Y_scale, Y_raw=Y_raw)
+        if keep_idx is not None:
+            keep_idx = np.ascontiguousarray(keep_idx, dtype=np.int64)
+            if keep_idx.shape != (N, ):
+                raise ValueError('keep_idx must have one entry per phenotype row')
+        self.N, self.K, self.P, self.n_contigs = int(N), int(K), int(P), int(n_contigs)
+        self.Ng = int(n_geno_samples) if n_geno_samples is not None else self.N
+        self.verbose = Y_raw is not None
+        self.device = device
+        self.n_lanes = n_lanes
+        d = _capi.StateDesc(abi_version=_capi.GLR_ABI_VERSION,
+                            device=device,
+                            n_samples=self.N,
+                            n_geno_samples=self.Ng,
+                            n_covariates=self.K,
+                            n_phenotypes=self.P,
+                            n_contigs=self.n_contigs,
+                            verbose=int(self.verbose),
+                            Q=ptrs['Q'],
+                            Y=ptrs['Y'],
+                            Y_mask=ptrs['Y_mask'],
+                            YdotY=ptrs['YdotY'],
+                            Y_scale=ptrs['Y_scale'],
+                            Y_raw=ptrs['Y_raw'],
+                            keep_idx=None if keep_idx is None else keep_idx.ctypes.data,
+                            dof=int(dof),
+                            max_block_variants=0,
+                            n_lanes=n_lanes,
+                            memspace=memspace)
+        _capi.check(self._lib.glr_state_create(C.byref(d), C.byref(self._handle)))
+        self._pending: Dict[int, tuple] = {}
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_handle', None) is not None and self._handle.value:
+            self._lib.glr_state_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def unique_masks(self) -> int:
+        return int(self._lib.glr_state_unique_masks(self._handle))
+
+    def _block_desc(self, fmt: int, addr: int, stride: int, G: int, contig: int, missing: str, memspace: int):
+        return _capi.BlockDesc(format=fmt,
+                               memspace=memspace,
+                               genotypes=addr,
+                               row_stride_bytes=stride,
+                               n_variants=G,
+                               contig=contig,
+                               missing_policy=_capi.MISSING_MEAN if missing == 'mean' else _capi.MISSING_AS_MINUS_ONE)
+
+    def _check_block(self, block: GenotypeBlock):
+        fmt = FORMATS[block.format]
+        data = block.data
+        if data.ndim != 2 or (data.size and not data.flags['C_CONTIGUOUS']):
+            raise ValueError('genotype block must be a C-contiguous 2-D array')
+        need = _ROW_BYTES[fmt](self.Ng)
+        have = data.shape[1] * data.dtype.itemsize
+        if data.shape[0] and have != need:
+            raise ValueError(f'genotype rows have {have} bytes, expected {need} for {self.Ng} samples '
+                             f'in format {block.format}')
+        return fmt, data
+
+    def submit(self, lane: int, block: GenotypeBlock, contig: int = 0, out: Optional[Dict[str, np.ndarray]] = None):
+        """Queues one block on a lane (H2D copy, kernels, D2H copy all asynchronous)."""
+        fmt, data = self._check_block(block)
+        G = int(data.shape[0])
+        names = STAT_NAMES + (VERBOSE_NAMES if self.verbose else ())
+        if out is None:
+            out = {k: np.empty((self.P, G), dtype=np.float64) for k in names}
+        bd = self._block_desc(fmt, data.ctypes.data if G else None, data.strides[0] if G else 0, G, contig,
+                              block.missing, _capi.MEM_HOST)
+        bo = _capi.BlockOut(memspace=_capi.MEM_HOST, **{k: out[k].ctypes.data if G else None for k in names})
+        _capi.check(self._lib.glr_block_submit(self._handle, lane, C.byref(bd), C.byref(bo)))
+        self._pending[lane] = (out, data)  # keep host buffers alive until wait()
+        return out
+
+    def wait(self, lane: int) -> Dict[str, np.ndarray]:
+        _capi.check(self._lib.glr_block_wait(self._handle, lane))
+        out, _ = self._pending.pop(lane)
+        return out
+
+    def run(self, block: GenotypeBlock, contig: int = 0) -> Dict[str, np.ndarray]:
+        """One block, synchronously: the device counterpart of lin_reg.py:226-249.
+        Returns P x G_b float64 arrays."""
+        self.submit(0, block, contig)
+        return self.wait(0)
+
+    def run_device(self, fmt: str, geno_addr: int, stride: int, G: int, out_addrs: Dict[str, int], contig: int = 0,
+                   missing: str = 'mean', lane: int = 0, wait: bool = True):
+        """Block and results already resident in HBM (device addresses)."""
+        names = STAT_NAMES + (VERBOSE_NAMES if self.verbose else ())
+        bd = self._block_desc(FORMATS[fmt], geno_addr, stride, G, contig, missing, _capi.MEM_DEVICE)
+        bo = _capi.BlockOut(memspace=_capi.MEM_DEVICE, **{k: out_addrs[k] for k in names})
+        _capi.check(self._lib.glr_block_submit(self._handle, lane, C.byref(bd), C.byref(bo)))
+        if wait:
+            _capi.check(self._lib.glr_block_wait(self._handle, lane))
+
+    def wait_device(self, lane: int = 0):
+        _capi.check(self._lib.glr_block_wait(self._handle, lane))
+
+    def timing(self, lane: int = 0) -> Dict[str, float]:
+        t = _capi.Timing()
+        _capi.check(self._lib.glr_block_timing(self._handle, lane, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in _capi.Timing._fields_ if k != 'reserved'}
+
+    def lane_stream(self, lane: int = 0) -> int:
+        s = C.c_void_p()
+        _capi.check(self._lib.glr_lane_stream(self._handle, lane, C.byref(s)))
+        return s.value or 0
+
+    def run_pipelined(self, blocks: Iterable[Tuple[GenotypeBlock, int]]) -> Iterator[Dict[str, np.ndarray]]:
+        """Streams (block, contig) pairs through the lanes so that the H2D copy of block i+1
+        overlaps the kernels of block i; yields results in submission order."""
+        inflight: List[int] = []
+        lane = 0
+        for block, contig in blocks:
+            if len(inflight) == self.n_lanes:
+                yield self.wait(inflight.pop(0))
+            self.submit(lane, block, contig)
+            inflight.append(lane)
+            lane = (lane + 1) % self.n_lanes
+        while inflight:
+            yield self.wait(inflight.pop(0))
+
+
+def t_two_sided_pvalues(t: np.ndarray, dof: float, device: int = 0) -> np.ndarray:
+    """2 * t.sf(|t|, dof) on the device (lin_reg.py:245)."""
+    lib = _capi.load()
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    out = np.empty_like(t)
+    _capi.check(lib.glr_t_two_sided_pvalues(device, t.ctypes.data, t.size, float(dof), out.ctypes.data))
+    return out
+
+
+def decode_block(block: GenotypeBlock, n_samples: int, device: int = 0) -> np.ndarray:
+    """Device decode of a packed block to float64 [G, N] (A0 semantics)."""
+    lib = _capi.load()
+    data = np.ascontiguousarray(block.data)
+    G = data.shape[0]
+    out = np.empty((G, n_samples), dtype=np.float64)
+    bd = _capi.BlockDesc(format=FORMATS[block.format],
+                         memspace=_capi.MEM_HOST,
+                         genotypes=data.ctypes.data if G else None,
+                         row_stride_bytes=data.strides[0] if G else 0,
+                         n_variants=G,
+                         contig=0,
+                         missing_policy=_capi.MISSING_MEAN if block.missing == 'mean' else _capi.MISSING_AS_MINUS_ONE)
+    _capi.check(lib.glr_decode_block(device, C.byref(bd), n_samples, out.ctypes.data))
+    return out

@@ -1,0 +1,315 @@
+"""B200-native drop-in for ``glow.gwas.linear_regression`` (reference: python/glow/gwas/lin_reg.py).
+
+Same signature, validation, output schema and row order.  The driver-side preparation
+(lin_reg.py:118-163: QR of the covariates, phenotype centring / residualisation / scaling, per-contig
+offsets) stays on the host in numpy, exactly as in the reference; everything inside the block loop
+(``_linear_regression_inner``, lin_reg.py:203-254) runs in hand-written sm_100a CUDA through the C
+ABI in include/glow_b200.h.  There is no CPU fallback for the block loop.
+
+``genotype_df`` may be
+  * a pandas DataFrame (one block) or an iterable of pandas DataFrames (a stream of blocks): the
+    result is one pandas DataFrame;
+  * a pyspark DataFrame (when pyspark is installed): the same block function runs under
+    ``mapInPandas`` exactly like the reference (lin_reg.py:277-284) and a Spark DataFrame is returned;
+  * a :class:`glow_b200.sources.GenotypeSource` (e.g. a PLINK .bed file): packed blocks go to the
+    device undecoded and the 2-bit decode / mean substitution is fused into the GEMM operand load.
+"""
+from dataclasses import dataclass, field
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Union
+
+import numpy as np
+import pandas as pd
+
+from . import functions as gwas_fx
+from .functions import _VALUES_COLUMN_NAME, _get_indices_to_drop, _get_contigs_from_loco_df
+from ..engine import DeviceState, GenotypeBlock, as_block, STAT_NAMES, VERBOSE_NAMES
+
+__all__ = ['linear_regression']
+
+
+@dataclass
+class YState:
+    """State that varies per contig (lin_reg.py:166-172) plus the device replica it lives in."""
+    Y: np.ndarray
+    YdotY: np.ndarray
+    _engine: Optional[DeviceState] = field(default=None, repr=False, compare=False)
+    _contig_index: int = 0
+
+    def __getstate__(self):
+        # the device replica never crosses a process boundary (Spark closure pickling,
+        # lin_reg.py:277-284): each worker rebuilds it lazily in _linear_regression_inner
+        return {'Y': self.Y, 'YdotY': self.YdotY, '_engine': None, '_contig_index': 0}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+
+def linear_regression(genotype_df,
+                      phenotype_df: pd.DataFrame,
+                      covariate_df: pd.DataFrame = pd.DataFrame({}),
+                      offset_df: pd.DataFrame = pd.DataFrame({}),
+                      contigs: Optional[List[str]] = None,
+                      add_intercept: bool = True,
+                      values_column: Union[str, Any] = 'values',
+                      dt: type = np.float64,
+                      verbose_output: bool = False,
+                      intersect_samples: bool = False,
+                      genotype_sample_ids: Optional[List[str]] = None,
+                      device: int = 0):
+    """Linear-regression association test of every variant against every phenotype.
+
+    Arguments, defaults, validation errors and the output columns are those of the reference
+    (lin_reg.py:18-116); ``device`` (CUDA ordinal) is the only addition.
+
+    Output columns: all columns of ``genotype_df`` except the values column and ``genotypes``,
+    then ``effect, stderror, tvalue, pvalue, phenotype`` [+ ``n, sum_x, y_transpose_x`` when
+    ``verbose_output``]; within a block rows are phenotype-major, variant-minor.
+    """
+    spark_input = gwas_fx._is_spark_df(genotype_df)
+    if spark_input:
+        gwas_fx._check_spark_version(genotype_df.sparkSession)
+
+    gwas_fx._validate_covariates_and_phenotypes(covariate_df,
+                                                phenotype_df,
+                                                is_binary=False,
+                                                intersect_samples=intersect_samples)
+    np_dt = gwas_fx._regression_dtype(dt)
+    if isinstance(values_column, str) and values_column == gwas_fx._GENOTYPES_COLUMN_NAME:
+        raise ValueError(f'The values column should not be called "{gwas_fx._GENOTYPES_COLUMN_NAME}"')
+
+    gt_indices_to_drop = None
+    _covs = covariate_df
+    if intersect_samples:  # lin_reg.py:131-140
+        if not genotype_sample_ids:
+            raise ValueError('genotype_sample_ids required when intersect_samples enabled')
+        _covs = covariate_df.loc[phenotype_df.index, :]
+        gt_indices_to_drop = _get_indices_to_drop(phenotype_df, genotype_sample_ids)
+        if not offset_df.empty:
+            if offset_df.index.nlevels == 1:
+                offset_df = offset_df.reindex(phenotype_df.index)
+            elif offset_df.index.nlevels == 2:
+                offset_df = offset_df[offset_df.index.get_level_values(0).isin(phenotype_df.index)]
+
+    C = _covs.to_numpy(np_dt, copy=True)
+    if add_intercept:
+        C = gwas_fx._add_intercept(C, phenotype_df.shape[0]).astype(np_dt, copy=False)
+
+    # covariate basis and phenotype residuals (lin_reg.py:146-155)
+    Q = np.linalg.qr(C)[0]
+    Y = phenotype_df.to_numpy(np_dt, copy=True)
+    Y_mask = (~np.isnan(Y)).astype(np_dt)
+    Y = np.nan_to_num(Y, copy=False)
+    Y_for_verbose_output = np.copy(Y) if verbose_output else None
+    Y -= Y.mean(axis=0)
+    Y = gwas_fx._residualize_in_place(Y, Q) * Y_mask
+    Y_scale = np.sqrt(np.sum(Y**2, axis=0) / (Y_mask.sum(axis=0) - Q.shape[1]))
+    Y /= Y_scale[None, :]
+
+    Y_state = _create_YState(Y, phenotype_df, offset_df, Y_mask, np_dt, contigs)
+    dof = C.shape[0] - C.shape[1] - 1  # lin_reg.py:159
+
+    n_geno = len(genotype_sample_ids) if (intersect_samples and genotype_sample_ids) else phenotype_df.shape[0]
+    _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output, gt_indices_to_drop, n_geno, device)
+
+    return _generate_linreg_output(genotype_df, np_dt, values_column, Y_state, Y_mask, Y_scale, Q, dof, phenotype_df,
+                                   Y_for_verbose_output, verbose_output, gt_indices_to_drop)
+
+
+def _create_YState(Y, phenotype_df, offset_df, Y_mask, dt, contigs) -> Union[YState, Dict[str, YState]]:
+    """lin_reg.py:175-188."""
+    offset_type = gwas_fx._validate_offset(phenotype_df, offset_df)
+    if offset_type != gwas_fx._OffsetType.LOCO_OFFSET:
+        return _create_one_YState(Y, phenotype_df, offset_df, Y_mask, dt)
+    if contigs is None:
+        contigs = _get_contigs_from_loco_df(offset_df)
+    return {
+        contig: _create_one_YState(Y, phenotype_df, offset_df.xs(contig, level=1), Y_mask, dt)
+        for contig in contigs
+    }
+
+
+def _create_one_YState(Y, phenotype_df, offset_df, Y_mask, dt) -> YState:
+    """lin_reg.py:191-199.  The offset is subtracted from the residualised, scaled phenotypes and
+    the result re-masked; it is NOT residualised or rescaled."""
+    if not offset_df.empty:
+        base_Y = pd.DataFrame(Y, phenotype_df.index, phenotype_df.columns)
+        Yc = (base_Y - offset_df).reindex(phenotype_df.index).to_numpy(dt).copy()
+    else:
+        Yc = np.array(Y, dtype=dt, copy=True)
+    Yc *= Y_mask
+    return YState(Yc, np.sum(Yc * Yc, axis=0))
+
+
+def _keep_index(n_geno: int, gt_indices_to_drop) -> Optional[np.ndarray]:
+    if gt_indices_to_drop is None or not np.size(gt_indices_to_drop):
+        return None
+    keep = np.ones(n_geno, dtype=bool)
+    keep[np.asarray(gt_indices_to_drop, dtype=np.int64)] = False
+    return np.flatnonzero(keep).astype(np.int64)
+
+
+def _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output, gt_indices_to_drop, n_geno, device=0):
+    """Builds the device replica of (Q, Y per contig, mask, scale, dof): what the reference ships to
+    every Spark worker by closure capture (lin_reg.py:277-284)."""
+    states = list(Y_state.values()) if isinstance(Y_state, dict) else [Y_state]
+    keep = _keep_index(n_geno, gt_indices_to_drop)
+    if keep is not None and keep.size != states[0].Y.shape[0]:
+        raise ValueError('after dropping the samples absent from phenotype_df the genotype arrays must have one '
+                         'entry per phenotype row')
+    engine = DeviceState(Q=np.asarray(Q, dtype=np.float64),
+                         Y=np.stack([np.asarray(s.Y, dtype=np.float64) for s in states]),
+                         Y_mask=np.asarray(Y_mask, dtype=np.float64),
+                         YdotY=np.stack([np.asarray(s.YdotY, dtype=np.float64) for s in states]),
+                         Y_scale=np.asarray(Y_scale, dtype=np.float64),
+                         dof=int(dof),
+                         Y_raw=None if Y_for_verbose_output is None else np.asarray(Y_for_verbose_output, np.float64),
+                         keep_idx=keep,
+                         n_geno_samples=n_geno,
+                         device=device)
+    for i, s in enumerate(states):
+        s._engine = engine
+        s._contig_index = i
+    return engine
+
+
+def _assemble(genotype_pdf: pd.DataFrame, res: Dict[str, np.ndarray], phenotype_names, verbose_output, out_dt):
+    """Result frame of one block (lin_reg.py:231-252): pass-through columns replicated once per
+    phenotype, statistics raveled phenotype-major."""
+    num_genotypes = genotype_pdf.shape[0]
+    P = res['effect'].shape[0]
+    out_df = pd.concat([genotype_pdf] * P) if P else genotype_pdf.iloc[0:0]
+    if verbose_output:
+        out_df['n'] = np.ravel(res['n']).astype(np.int32)
+        out_df['sum_x'] = np.ravel(res['sum_x']).astype(out_dt, copy=False)
+        out_df['y_transpose_x'] = np.ravel(res['y_transpose_x']).astype(out_dt, copy=False)
+    for k in STAT_NAMES:
+        out_df[k] = np.ravel(res[k]).astype(out_dt, copy=False)
+    out_df['phenotype'] = np.repeat(np.asarray(list(phenotype_names), dtype=object), num_genotypes)
+    return out_df
+
+
+def _linear_regression_inner(genotype_pdf: pd.DataFrame, Y_state: YState, Y_mask, Y_scale, Q, dof: int,
+                             phenotype_names: pd.Series, Y_for_verbose_output, verbose_output,
+                             gt_indices_to_drop) -> pd.DataFrame:
+    """Same contract as the reference's block kernel (lin_reg.py:203-254): one pandas block with a
+    ``_glow_regression_values`` column in, the result frame out.  The arithmetic of lin_reg.py:226-249
+    runs on the device; if ``Y_state`` has no device replica yet (callers that build the state by
+    hand, like the reference's unit tests), one is created and cached on it."""
+    values = genotype_pdf[_VALUES_COLUMN_NAME]
+    first = values.iloc[0] if len(values) else None
+    if isinstance(first, GenotypeBlock):
+        block = first
+    else:
+        block = as_block(values.array if hasattr(values, 'array') else values, np.asarray(Y_scale).dtype)
+    n_geno = block.data.shape[1] if block.format != 'plink2' else None
+    if Y_state._engine is None:
+        n_rows = Y_state.Y.shape[0]
+        n_drop = 0 if gt_indices_to_drop is None else int(np.size(gt_indices_to_drop))
+        _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output if verbose_output else None,
+                       gt_indices_to_drop, n_rows + n_drop)
+    res = Y_state._engine.run(block, Y_state._contig_index)
+    rest = genotype_pdf.drop(columns=[_VALUES_COLUMN_NAME])
+    out_dt = np.asarray(Y_scale).dtype
+    return _assemble(rest, res, phenotype_names, bool(verbose_output), out_dt)
+
+
+def _output_columns(input_columns, verbose_output) -> List[str]:
+    """Column order of the result (lin_reg.py:260-275, functions.py:24-27)."""
+    cols = [c for c in input_columns if c not in (_VALUES_COLUMN_NAME, gwas_fx._GENOTYPES_COLUMN_NAME)]
+    if verbose_output:
+        cols += ['n', 'sum_x', 'y_transpose_x']
+    return cols + ['effect', 'stderror', 'tvalue', 'pvalue', 'phenotype']
+
+
+def _generate_linreg_output(genotype_df, np_dt, values_column, Y_state, Y_mask, Y_scale, Q, dof, phenotype_df,
+                            Y_for_verbose_output, verbose_output, gt_indices_to_drop):
+    """lin_reg.py:257-284."""
+    phenotype_names = phenotype_df.columns.to_series().astype('str')
+    args = (Y_mask, Y_scale, Q, dof, phenotype_names, Y_for_verbose_output, verbose_output, gt_indices_to_drop)
+
+    def map_func(pdf_iterator):
+        for pdf in pdf_iterator:
+            yield gwas_fx._loco_dispatch(pdf, Y_state, _linear_regression_inner, *args)
+
+    if gwas_fx._is_spark_df(genotype_df):
+        return _spark_map(genotype_df, np_dt, values_column, map_func, verbose_output)
+
+    from ..sources import GenotypeSource
+    if isinstance(genotype_df, GenotypeSource):
+        return _run_source(genotype_df, Y_state, phenotype_names, verbose_output, np_dt)
+
+    blocks = [genotype_df] if isinstance(genotype_df, pd.DataFrame) else genotype_df
+    prepared = (gwas_fx._prepare_genotype_pdf(pdf, values_column, np_dt) for pdf in blocks)
+    parts = list(map_func(prepared))
+    if not parts:
+        return pd.DataFrame(columns=_output_columns([], verbose_output))
+    out = pd.concat(parts) if len(parts) > 1 else parts[0]
+    # exact reference column order: pass-through columns, then results (verbose columns last)
+    passthrough = [c for c in out.columns if c not in STAT_NAMES + VERBOSE_NAMES + ('phenotype', )]
+    ordered = passthrough + list(STAT_NAMES) + ['phenotype'] + (list(VERBOSE_NAMES) if verbose_output else [])
+    return out[ordered]
+
+
+def _run_source(source, Y_state, phenotype_names, verbose_output, np_dt) -> pd.DataFrame:
+    """Packed blocks (e.g. PLINK 2-bit) pipelined through the device lanes: the H2D copy of block
+    i+1 overlaps the kernels of block i; LOCO blocks are split by contig like _loco_dispatch."""
+    is_loco = isinstance(Y_state, dict)
+    engine = (next(iter(Y_state.values())) if is_loco else Y_state)._engine
+
+    def work():
+        for meta, block in source.blocks():
+            if is_loco:
+                for contig in pd.unique(meta['contigName']):
+                    sel = (meta['contigName'] == contig).to_numpy()
+                    sub = GenotypeBlock(np.ascontiguousarray(block.data[sel]), block.format, block.missing)
+                    yield meta[sel], sub, Y_state[contig]._contig_index
+            else:
+                yield meta, block, 0
+
+    metas = []
+
+    def feed():
+        for meta, block, ci in work():
+            metas.append(meta)
+            yield block, ci
+
+    parts = []
+    for res in engine.run_pipelined(feed()):
+        meta = metas.pop(0)
+        parts.append(_assemble(meta, res, phenotype_names, verbose_output, np_dt))
+    if not parts:
+        return pd.DataFrame(columns=_output_columns([], verbose_output))
+    out = pd.concat(parts)
+    passthrough = [c for c in out.columns if c not in STAT_NAMES + VERBOSE_NAMES + ('phenotype', )]
+    return out[passthrough + list(STAT_NAMES) + ['phenotype'] + (list(VERBOSE_NAMES) if verbose_output else [])]
+
+
+def _spark_map(genotype_df, np_dt, values_column, map_func, verbose_output):
+    """Spark wiring of the reference (functions.py:56-68, lin_reg.py:259-284).  Only reachable when
+    pyspark is installed; each Python worker loads libglow_b200.so and drives its own GPU."""
+    from pyspark.sql import functions as fx
+    from pyspark.sql.types import (ArrayType, DoubleType, FloatType, IntegerType, StringType, StructField,
+                                   StructType)
+    sql_type = FloatType() if np_dt == np.float32 else DoubleType()
+    if isinstance(values_column, str):
+        out = genotype_df.withColumn(_VALUES_COLUMN_NAME,
+                                     fx.col(values_column).cast(ArrayType(sql_type))).drop(values_column)
+    else:
+        out = genotype_df.withColumn(_VALUES_COLUMN_NAME, values_column.cast(ArrayType(sql_type)))
+    if gwas_fx._GENOTYPES_COLUMN_NAME in [f.name for f in genotype_df.schema]:
+        out = out.drop(gwas_fx._GENOTYPES_COLUMN_NAME)
+    result_fields = [
+        StructField('effect', sql_type),
+        StructField('stderror', sql_type),
+        StructField('tvalue', sql_type),
+        StructField('pvalue', sql_type),
+        StructField('phenotype', StringType())
+    ]
+    if verbose_output:
+        result_fields += [
+            StructField('n', IntegerType()),
+            StructField('sum_x', sql_type),
+            StructField('y_transpose_x', sql_type)
+        ]
+    fields = [f for f in out.schema.fields if f.name != _VALUES_COLUMN_NAME] + result_fields
+    return out.mapInPandas(map_func, StructType(fields))

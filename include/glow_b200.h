@@ -1,0 +1,169 @@
+/*
+ * glow_b200.h -- C ABI of the B200-native linear-regression GWAS block kernel.
+ *
+ * The reference (projectglow/glow) has no FFI for this path: the seam is the Python call
+ *   _linear_regression_inner(genotype_pdf, Y_state, Y_mask, Y_scale, Q, dof, phenotype_names,
+ *                            Y_for_verbose_output, verbose_output, gt_indices_to_drop)
+ * at python/glow/gwas/lin_reg.py:203-254, reached from map_func (lin_reg.py:277-282) through
+ * _loco_dispatch (python/glow/gwas/functions.py:92-101).  Each entry point below cites the
+ * reference lines it replaces.  All functions are extern "C", take plain pointers and sizes, never
+ * throw, and return 0 on success or a negative glr_status; glr_last_error() gives the message of
+ * the last failure on the calling thread.
+ *
+ * Ownership: the caller owns every buffer it passes; the library owns all device memory behind a
+ * handle.  Calls on one handle must be serialised by the caller; distinct handles (one per GPU)
+ * may be driven from distinct host threads.
+ */
+#ifndef GLOW_B200_H
+#define GLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLR_ABI_VERSION 1
+
+typedef enum glr_status {
+  GLR_OK = 0,
+  GLR_ERR_INVALID = -1,  /* bad argument (maps to Python ValueError) */
+  GLR_ERR_CUDA = -2,     /* CUDA runtime failure */
+  GLR_ERR_NO_DEVICE = -3,/* no usable sm_100 device: the product path has no CPU fallback */
+  GLR_ERR_STATE = -4     /* call sequence error (e.g. wait on an idle lane) */
+} glr_status;
+
+/* Genotype block encodings.  One block = G_b variants, variant-major: variant g starts at
+ * genotypes + g * row_stride_bytes. */
+typedef enum glr_format {
+  /* N doubles per variant: the `_glow_regression_values` array<double> column
+   * (functions.py:56-68), i.e. the rows np.column_stack gathers at lin_reg.py:226-227. */
+  GLR_FMT_F64 = 0,
+  /* N floats per variant (dt=np.float32 input arrays, functions.py:47-53); widened to f64. */
+  GLR_FMT_F32 = 1,
+  /* N int8 per variant: genotype_states output, -1 = missing
+   * (core/.../sql/expressions/VariantUtilExprs.scala:37-59). */
+  GLR_FMT_I8 = 2,
+  /* PLINK .bed variant-major block, ceil(N/4) bytes per variant, sample s in byte s/4 bits
+   * 2(s%4): code 00 -> 2, 01 -> missing, 10 -> 1, 11 -> 0
+   * (core/.../plink/PlinkRowToInternalRowConverter.scala:40-47,56-66; PlinkFileFormat.scala:282-284). */
+  GLR_FMT_PLINK2 = 3
+} glr_format;
+
+typedef enum glr_memspace { GLR_MEM_HOST = 0, GLR_MEM_DEVICE = 1 } glr_memspace;
+
+/* How missing calls (-1 in I8, code 01 in PLINK2) become numbers. */
+typedef enum glr_missing_policy {
+  GLR_MISSING_AS_MINUS_ONE = 0, /* genotype_states semantics: the value -1 enters the regression */
+  GLR_MISSING_MEAN = 1          /* mean_substitute(genotype_states(..)):
+                                   core/.../sql/expressions/MeanSubstitute.scala:39-108; all-missing -> -1 */
+} glr_missing_policy;
+
+typedef struct glr_state glr_state; /* opaque */
+
+/* Driver-side state: what map_func closes over at lin_reg.py:277-282.
+ * All matrices are row-major float64 in PHENOTYPE sample order. */
+typedef struct glr_state_desc {
+  int32_t abi_version;     /* GLR_ABI_VERSION */
+  int32_t device;          /* CUDA device ordinal */
+  int64_t n_samples;       /* N  = rows of Q / Y (after intersect_samples) */
+  int64_t n_geno_samples;  /* length of each genotype array (>= N); == N unless rows are dropped */
+  int32_t n_covariates;    /* K  = columns of Q (covariates + intercept) */
+  int32_t n_phenotypes;    /* P */
+  int32_t n_contigs;       /* C  = 1 unless LOCO offsets (one YState per contig, lin_reg.py:166-199) */
+  int32_t verbose;         /* also produce n / sum_x / y_transpose_x (lin_reg.py:234-237) */
+  const double* Q;         /* [N x K]   lin_reg.py:147 */
+  const double* Y;         /* [C][N x P] YState.Y per contig, lin_reg.py:194-199 */
+  const double* Y_mask;    /* [N x P]   0/1, lin_reg.py:149 */
+  const double* YdotY;     /* [C][P]    YState.YdotY */
+  const double* Y_scale;   /* [P]       lin_reg.py:154 */
+  const double* Y_raw;     /* [N x P]   Y_for_verbose_output (zero-filled raw phenotypes) or NULL */
+  const int64_t* keep_idx; /* [N] genotype-array index of each phenotype row (np.delete at
+                              lin_reg.py:228-229 expressed as a gather), or NULL for identity */
+  int64_t dof;             /* N - K - 1, lin_reg.py:159 */
+  int32_t max_block_variants; /* hint for workspace sizing (grown on demand) */
+  int32_t n_lanes;         /* independent in-flight blocks (streams); 0 -> default 2 */
+  int32_t memspace;        /* glr_memspace of Q, Y, Y_mask, YdotY, Y_scale, Y_raw (keep_idx is always
+                              host): GLR_MEM_DEVICE lets ranks != 0 build their replica straight
+                              from the buffer an NCCL broadcast filled, without a host round trip */
+  int32_t reserved;
+} glr_state_desc;
+
+/* One genotype block in, = the `genotype_pdf` argument of _linear_regression_inner. */
+typedef struct glr_block_desc {
+  int32_t format;           /* glr_format */
+  int32_t memspace;         /* glr_memspace of `genotypes` */
+  const void* genotypes;
+  int64_t row_stride_bytes; /* distance between consecutive variants */
+  int32_t n_variants;       /* G_b */
+  int32_t contig;           /* index into the C YStates (0 when C == 1): _loco_dispatch, functions.py:92-101 */
+  int32_t missing_policy;   /* glr_missing_policy (I8 / PLINK2 only) */
+  int32_t reserved;
+} glr_block_desc;
+
+/* Results out: four (seven if verbose) [P x G_b] row-major arrays = the P x G_b matrices the
+ * reference ravels into its output columns (lin_reg.py:247-252): phenotype-major, variant-minor. */
+typedef struct glr_block_out {
+  int32_t memspace; /* glr_memspace of all output pointers */
+  int32_t reserved;
+  double* effect;   /* betas * Y_scale */
+  double* stderror; /* standard_error * Y_scale */
+  double* tvalue;
+  double* pvalue;
+  double* n;             /* verbose only, may be NULL */
+  double* sum_x;         /* verbose only */
+  double* y_transpose_x; /* verbose only */
+} glr_block_out;
+
+typedef struct glr_timing {
+  float total_ms;    /* first kernel start -> last kernel end of the block (CUDA events) */
+  float prepass_ms;  /* count / impute pre-pass */
+  float gram_ms;     /* DMMA contraction kernel(s) */
+  float masked_ms;   /* masked sum-of-squares kernel (0 when every phenotype is fully observed) */
+  float epilogue_ms; /* statistics + p-values */
+  int32_t kernel_launches;
+  int32_t reserved;
+} glr_timing;
+
+int glr_abi_version(void);
+const char* glr_last_error(void);
+/* Number of visible CUDA devices of compute capability 10.x; <= 0 means the library cannot run. */
+int glr_device_count(void);
+
+/* Replaces the closure capture + broadcast of (Y_state, Y_mask, Y_scale, Q, dof) at
+ * lin_reg.py:157-163,277-284.  Copies the arrays to `device` and packs them for the kernels. */
+int glr_state_create(const glr_state_desc* desc, glr_state** out);
+int glr_state_destroy(glr_state* st);
+/* Number of distinct non-trivial missingness patterns among the phenotypes (0 = every phenotype
+ * fully observed, the masked pass is skipped). */
+int glr_state_unique_masks(glr_state* st);
+
+/* Replaces one call of _linear_regression_inner (lin_reg.py:203-254).  Synchronous:
+ * submit on lane 0 + wait. */
+int glr_run_block(glr_state* st, const glr_block_desc* blk, const glr_block_out* out);
+/* Asynchronous form: lanes are independent streams with their own staging buffers so the H2D
+ * copy of block i+1 overlaps the kernels of block i.  Host buffers must stay valid (and should
+ * be pinned, see glr_host_alloc) until glr_block_wait returns. */
+int glr_block_submit(glr_state* st, int lane, const glr_block_desc* blk, const glr_block_out* out);
+int glr_block_wait(glr_state* st, int lane);
+/* CUDA-event timings of the last completed block on `lane`. */
+int glr_block_timing(glr_state* st, int lane, glr_timing* t);
+/* The CUDA stream (cudaStream_t) a lane launches on, for callers that time with their own events. */
+int glr_lane_stream(glr_state* st, int lane, void** stream);
+
+/* Pinned host memory for block staging. */
+int glr_host_alloc(size_t bytes, void** ptr);
+int glr_host_free(void* ptr);
+
+/* Standalone A6: p = 2 * t.sf(|t|, dof) (lin_reg.py:245) for n device-computed values; host in/out.
+ * Exposed so the special-function kernel can be tested against scipy/mpmath directly. */
+int glr_t_two_sided_pvalues(int device, const double* tvalues, int64_t n, double dof, double* pvalues);
+/* Standalone A0: decode a packed block to float64 [G_b x N] on the device (host in/out);
+ * tests the fused decode against PlinkReaderSuite / MeanSubstitute semantics. */
+int glr_decode_block(int device, const glr_block_desc* blk, int64_t n_geno_samples, double* out_values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLOW_B200_H */
