@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument('--e2e-subblocks', type=int, default=4)
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-peak', action='store_true', help='do not run the cuBLAS DGEMM peak measurement (ncu runs)')
     ap.add_argument('--cpu-block-variants', type=int, default=128)
     return ap.parse_args()
 
@@ -281,21 +282,15 @@ def main():
     G = args.variants_per_step
 
     # ---- state: rank 0 prepares it on the host, ONE NCCL broadcast replicates it ----
-    sizes = [n * K, n * P, n * P, P, P]
-    flat = torch.empty(sum(sizes) + 1, dtype=torch.float64, device=dev)
+    from glow_b200 import dist as gdist
     host = None
+    st_in = None
     if rank == 0:
         host = host_state(n)
         Q, Y, mask, ydy, scale, dof = host
-        flat.copy_(torch.from_numpy(np.concatenate([Q.ravel(), Y.ravel(), mask.ravel(), ydy, scale, [float(dof)]])))
-    if world > 1:
-        dist.broadcast(flat, src=0)
-    offs = np.cumsum([0] + sizes)
-    base = flat.data_ptr()
-    dof = int(flat[-1].item())
-    state = DeviceState(Q=base + 8 * int(offs[0]), Y=base + 8 * int(offs[1]), Y_mask=base + 8 * int(offs[2]),
-                        YdotY=base + 8 * int(offs[3]), Y_scale=base + 8 * int(offs[4]), dof=dof, device=local_rank,
-                        n_lanes=2, memspace=_capi.MEM_DEVICE, dims=(n, K, P, 1))
+        st_in = dict(Q=Q, Y=Y, Y_mask=mask, YdotY=ydy, Y_scale=scale, dof=dof)
+    flat, header = gdist.broadcast_state(st_in, src=0, device=dev)
+    state = gdist.device_state_from_flat(flat, header, local_rank, n_lanes=2)
 
     # ---- synthetic batch, resident in HBM ----
     packed = gen_packed_device(torch, G, n, SEED + 17 * rank, dev)
@@ -385,7 +380,9 @@ def main():
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e_val = world * gs * nsub * P * args.steps / float(t_e.item())
         # the device-resident and host paths must agree bit for bit
-        same = bool(np.array_equal(host_out[0]['tvalue'], outs['tvalue'][:, :gs].cpu().numpy(), equal_nan=True))
+        # the host path (smaller sub-blocks, split reduction order) must agree with the resident path
+        same = bool(np.allclose(host_out[0]['tvalue'], outs['tvalue'][:, :gs].cpu().numpy(), rtol=1e-9, atol=1e-12,
+                                equal_nan=True))
         e2e = {
             'value': e2e_val,
             'unit': 'tests/s',
@@ -413,7 +410,7 @@ def main():
         a = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
         b = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
         best = 1e9
-        for i in range(7):
+        for i in range(0 if args.skip_peak else 7):
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             torch.matmul(a, b)
@@ -421,16 +418,18 @@ def main():
             torch.cuda.synchronize()
             if i >= 2:
                 best = min(best, s0.elapsed_time(s1))
-        fp64_peak = 2 * 8192**3 / (best / 1e3) / 1e12
+        fp64_peak = 2 * 8192**3 / (best / 1e3) / 1e12 if not args.skip_peak else float('nan')
         del a, b
-        mt_cols = ((K + P + 7) // 8) * 8
-        flops_alg = 2.0 * n * (K + P) * G  # executed formulation: [Q | Ytilde]^T X
-        flops_issued = 2.0 * n * mt_cols * G  # incl. the zero padding columns of the 8-wide m-tiles
+        cols = K + P
+        dmma_cols = (cols // 8) * 8 if 1 <= cols % 8 <= 3 and cols // 8 >= 1 else ((cols + 7) // 8) * 8
+        flops_alg = 2.0 * n * cols * G  # executed formulation: [Q | Ytilde]^T X
+        flops_issued = 2.0 * n * max(dmma_cols, cols) * G  # DMMA columns (incl. zero padding) + FMA tail columns
         flops_ref = float(n) * (4 * K + 4 * P + 2) * G  # reference formulation, SURVEY.md section 8(d)
         gram_s = stage['gram_ms'] / 1e3
         achieved = flops_alg / gram_s / 1e12
         roof = {
-            'kernel': 'gram_kernel<PLINK2, MT=3, NT=4> (mma.sync.m8n8k4.f64 DMMA, fused 2-bit decode)',
+            'kernel': 'gram_kernel<PLINK2, MT=2, NT=2, TAIL=2, WARPS=16> (mma.sync.m8n8k4.f64 DMMA for 16 of the 18 '
+                      'columns, FP64 FMA for the 2 tail columns, fused 2-bit decode)',
             'bound': 'tensor',
             'achieved': achieved,
             'peak': fp64_peak,

@@ -89,7 +89,8 @@ struct glr_state {
   int64_t dof = 0;
   int64_t n_chunks = 0;
   // pass-1 operand
-  int Mcols = 0, MT = 1, n_groups = 1;
+  int Mcols = 0, MT = 1, n_groups = 1, tail = 0;
+  int64_t s_rows = 0;  // rows of the S workspace
   int64_t w_contig_doubles = 0;
   double* wpk = nullptr;  // [C][n_groups][n_chunks][8][MT][64]
   // masked pass
@@ -106,7 +107,7 @@ struct glr_state {
   PvalConst pc{};
   std::vector<Lane> lanes;
   int sm_count = 148;
-  int force_nt = 0, force_split = 0;
+  int force_split = 0, force_warps = 0;
 };
 
 extern "C" {
@@ -197,8 +198,8 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   st->pc = make_pval_const((double)d->dof);
   st->n_chunks = ceil_div(st->Ng, kChunk);
   CU(cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, d->device));
-  if (const char* e = getenv("GLR_NT")) st->force_nt = atoi(e);
   if (const char* e = getenv("GLR_SPLIT")) st->force_split = atoi(e);
+  if (const char* e = getenv("GLR_WARPS")) st->force_warps = atoi(e);
 
   const int64_t N = st->N, Ng = st->Ng;
   const int K = st->K, P = st->P, C = st->C;
@@ -315,14 +316,23 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   // ---- pass-1 operand W_c = [Q | Ytilde_c | mask | Yraw], Ytilde_c = (I - Q Q^T) Y_c ----
   st->Mcols = K + P * (st->verbose ? 3 : 1);
   const int n_mtiles = (int)ceil_div(st->Mcols, 8);
-  if (n_mtiles <= kMaxMT) {
+  const int full_tiles = st->Mcols / 8, rem_cols = st->Mcols % 8;
+  const bool no_tail = getenv("GLR_NO_TAIL") != nullptr;
+  if (!no_tail && full_tiles >= 1 && full_tiles <= 4 && rem_cols >= 1 && rem_cols <= 3) {
+    // 8*MT + 1..3 columns: the remainder goes through FP64 FMAs instead of a zero-padded m-tile
+    st->MT = full_tiles;
+    st->tail = rem_cols;
+    st->n_groups = 1;
+  } else if (n_mtiles <= kMaxMT) {
     st->MT = pick_mt(n_mtiles);
     st->n_groups = 1;
   } else {
     st->MT = kMaxMT;
     st->n_groups = (int)ceil_div(n_mtiles, kMaxMT);
   }
-  st->w_contig_doubles = (int64_t)st->n_groups * st->n_chunks * kChunkGroups * st->MT * kAtomDoubles;
+  st->s_rows = (int64_t)st->n_groups * st->MT * 8 + (st->tail ? 8 : 0);
+  st->w_contig_doubles =
+      (int64_t)st->n_groups * st->n_chunks * kChunkGroups * (st->MT * kAtomDoubles + st->tail * kGroup);
   const size_t w_bytes = (size_t)C * st->w_contig_doubles * sizeof(double);
   CU(cudaMalloc(&st->wpk, w_bytes));
   CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
@@ -332,12 +342,12 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     if (K > 0) {
       launch_qty(dQ, dY, N, K, P, dT, s0);
       launch_residualize(dQ, dT, dY, N, K, P, s0);
-      launch_pack_a(dQ, N, K, 0, K, d_g2r, Ng, dst, 0, st->MT, st->n_chunks, s0);
+      launch_pack_a(dQ, N, K, 0, K, d_g2r, Ng, dst, 0, st->MT, st->tail, st->n_chunks, s0);
     }
-    launch_pack_a(dY, N, P, 0, P, d_g2r, Ng, dst, K, st->MT, st->n_chunks, s0);
+    launch_pack_a(dY, N, P, 0, P, d_g2r, Ng, dst, K, st->MT, st->tail, st->n_chunks, s0);
     if (st->verbose) {
-      launch_pack_a(dM, N, P, 0, P, d_g2r, Ng, dst, K + P, st->MT, st->n_chunks, s0);
-      launch_pack_a(dYraw, N, P, 0, P, d_g2r, Ng, dst, K + 2 * P, st->MT, st->n_chunks, s0);
+      launch_pack_a(dM, N, P, 0, P, d_g2r, Ng, dst, K + P, st->MT, st->tail, st->n_chunks, s0);
+      launch_pack_a(dYraw, N, P, 0, P, d_g2r, Ng, dst, K + 2 * P, st->MT, st->tail, st->n_chunks, s0);
     }
   }
   CU(cudaGetLastError());
@@ -374,7 +384,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     CU(cudaMalloc(&dMu, mu.size() * sizeof(double)));
     tmp.v.push_back(dMu);
     CU(cudaMemcpy(dMu, mu.data(), mu.size() * sizeof(double), cudaMemcpyHostToDevice));
-    launch_pack_a(dMu, N, U, 0, U, d_g2r, Ng, st->mpk, 0, st->MT2, st->n_chunks, s0);
+    launch_pack_a(dMu, N, U, 0, U, d_g2r, Ng, st->mpk, 0, st->MT2, 0, st->n_chunks, s0);
   }
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
@@ -433,13 +443,10 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   const int P = st->P, K = st->K;
 
   // ---- plan ----
-  int nt = 2;
-  if (b->format == GLR_FMT_PLINK2) {
-    nt = (ceil_div(G, 256) >= st->sm_count) ? 4 : 2;
-    if (st->force_nt == 2 || st->force_nt == 4) nt = st->force_nt;
-    if (st->MT > 4) nt = 2;  // 4 n-tiles x >4 m-tiles of accumulators would spill
-  }
-  const int tile = gram_tile_variants(nt);
+  const int nt = 2;
+  int warps = 8;
+  if (b->format == GLR_FMT_PLINK2 && st->force_warps != 8) warps = 16;
+  const int tile = gram_tile_variants(nt, warps);
   const int64_t ldS = round_up(G, 256);
   const int64_t ctas = ceil_div(G, tile) * st->n_groups;
   int n_split = 1;
@@ -448,7 +455,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
     n_split = std::max(1, std::min(n_split, 64));
   }
   if (st->force_split > 0) n_split = (int)std::min<int64_t>(st->force_split, st->n_chunks);
-  const int64_t Mpad = (int64_t)st->n_groups * st->MT * 8;
+  const int64_t Mpad = st->s_rows;
   const bool float_fmt = b->format == GLR_FMT_F64 || b->format == GLR_FMT_F32;
 
   // ---- buffers ----
@@ -498,10 +505,12 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   gp.x = x;
   gp.wpk = st->wpk + (int64_t)b->contig * st->w_contig_doubles;
   gp.MT = st->MT;
+  gp.tail = st->tail;
   gp.n_groups = st->n_groups;
   gp.n_chunks = st->n_chunks;
   gp.n_split = n_split;
   gp.nt = nt;
+  gp.warps = warps;
   gp.ldS = ldS;
   gp.S = n_split > 1 ? L.s_part.as<double>() : L.s_red.as<double>();
   gp.sxx_part = (float_fmt && n_split > 1) ? L.sxx_part.as<double>() : L.sxx.as<double>();

@@ -261,7 +261,7 @@ void launch_residualize(const double* Q, const double* T, double* Y, int64_t N, 
 // dst layout: [group][chunk][8 sample groups][MT][64]; element (lane*2 + h) of an atom =
 // M[s0 + 2*(lane&3) + h][col0 + (lane>>2)]
 __global__ void pack_a_kernel(const double* src, int64_t N, int64_t ld, int c0, int ncols, const int64_t* geno_to_row,
-                              int64_t Ng, double* dst, int dst_col0, int MT, int64_t n_chunks) {
+                              int64_t Ng, double* dst, int dst_col0, int MT, int tail, int64_t n_chunks) {
   const int64_t total = (int64_t)ncols * n_chunks * kChunk;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -273,20 +273,25 @@ __global__ void pack_a_kernel(const double* src, int64_t N, int64_t ld, int c0, 
     if (row >= 0 && row < N) v = src[row * ld + c0 + c];
   }
   const int dcol = dst_col0 + c;
-  const int group = dcol / (MT * 8), mt = (dcol / 8) % MT, r = dcol % 8;
   const int64_t chunk = sg / kChunk;
   const int g = (int)((sg % kChunk) / kGroup);
   const int w = (int)(sg % kGroup);
+  const int64_t stage_doubles = (int64_t)kChunkGroups * (MT * kAtomDoubles + tail * kGroup);
+  if (tail > 0 && dcol >= MT * 8) {  // tail column (single column group)
+    const int t = dcol - MT * 8;
+    dst[chunk * stage_doubles + (int64_t)kChunkGroups * MT * kAtomDoubles + (g * tail + t) * kGroup + w] = v;
+    return;
+  }
+  const int group = dcol / (MT * 8), mt = (dcol / 8) % MT, r = dcol % 8;
   const int j = w >> 1, h = w & 1;
-  const int64_t atom = ((group * n_chunks + chunk) * kChunkGroups + g) * MT + mt;
-  dst[atom * kAtomDoubles + (4 * r + j) * 2 + h] = v;
+  dst[(group * n_chunks + chunk) * stage_doubles + ((int64_t)g * MT + mt) * kAtomDoubles + (4 * r + j) * 2 + h] = v;
 }
 void launch_pack_a(const double* src, int64_t N, int64_t ld, int c0, int ncols, const int64_t* geno_to_row,
-                   int64_t Ng, double* dst, int dst_col0, int MT, int64_t n_chunks, cudaStream_t st) {
+                   int64_t Ng, double* dst, int dst_col0, int MT, int tail, int64_t n_chunks, cudaStream_t st) {
   const int64_t total = (int64_t)ncols * n_chunks * kChunk;
   if (total <= 0) return;
   pack_a_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(src, N, ld, c0, ncols, geno_to_row, Ng, dst, dst_col0,
-                                                                 MT, n_chunks);
+                                                                 MT, tail, n_chunks);
 }
 
 // dst layout: [chunk][8 sample groups][KT2][64]; element (lane*2 + h) = Q[s0 + (lane>>2)][4*(2*k2 + h) + (lane&3)]
@@ -319,7 +324,7 @@ void launch_pack_qb(const double* Q, int64_t N, int K, const int64_t* geno_to_ro
 }
 
 // ------------------------------------------------------------------------------------------------
-int gram_tile_variants(int nt) { return kWarps * nt * 8; }
+int gram_tile_variants(int nt, int warps) { return warps * nt * 8; }
 
 void launch_gram(const GramParams& p, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;

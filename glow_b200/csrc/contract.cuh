@@ -220,14 +220,14 @@ struct XLoader<GLR_FMT_I8, NT> {
 struct Ring {
   uint64_t* full;
   uint64_t* empty;
-  __device__ __forceinline__ void init(unsigned char* smem, int tid) {
+  __device__ __forceinline__ void init(unsigned char* smem, int tid, int n_consumer_warps) {
     full = reinterpret_cast<uint64_t*>(smem);
     empty = full + kStages;
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&empty[s], kWarps);
+        mbar_init(&empty[s], n_consumer_warps);
       }
       mbar_fence_init();
     }
@@ -238,10 +238,13 @@ struct Ring {
 // ------------------------------------------------------------------------------------------------
 // pass 1
 // ------------------------------------------------------------------------------------------------
-template <int FMT, int MT, int NT>
-__global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
+// TAIL = 0..3 extra columns beyond the MT m-tiles, accumulated with plain FP64 FMAs on the lane's
+// own two samples (then reduced over the 4 lanes that share a variant): a column count of 8*MT + 1..3
+// does not pay for a whole zero-padded m-tile of DMMAs.
+template <int FMT, int MT, int NT, int TAIL, int WARPS>
+__global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int kStageDoubles = kChunkGroups * MT * kAtomDoubles;
+  constexpr int kStageDoubles = kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup);
   constexpr uint32_t kStageBytes = kStageDoubles * 8;
   using Loader = XLoader<FMT, NT>;
   constexpr int UG = Loader::UG;
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Ring ring;
-  ring.init(smem, tid);
+  ring.init(smem, tid, WARPS);
   double* wst = reinterpret_cast<double*>(smem + kBarBytes);
 
   const int64_t cps = ceil_div(p.n_chunks, p.n_split);
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
   const int64_t c_end = min(p.n_chunks, c_begin + cps);
   const int64_t n_it = c_end > c_begin ? c_end - c_begin : 0;
 
-  if (warp == kWarps) {  // producer warp: one lane drives the TMA engine
+  if (warp == WARPS) {  // producer warp: one lane drives the TMA engine
     if (lane == 0) {
       const double* src = p.wpk + ((int64_t)blockIdx.y * p.n_chunks + c_begin) * kStageDoubles;
       for (int64_t it = 0; it < n_it; ++it) {
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
   }
 
   const int r = lane >> 2, j = lane & 3;
-  const int v_warp = blockIdx.x * (kWarps * NT * 8) + warp * (NT * 8);
+  const int v_warp = blockIdx.x * (WARPS * NT * 8) + warp * (NT * 8);
   Loader ld;
   ld.init(p.x, v_warp, r, j);
 
@@ -283,6 +286,11 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
   double sq[NT];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) sq[nt] = 0.0;
+  double tacc[TAIL > 0 ? TAIL : 1][NT];
+#pragma unroll
+  for (int t = 0; t < (TAIL > 0 ? TAIL : 1); ++t)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) tacc[t][nt] = 0.0;
   const bool want_sq = (FMT == GLR_FMT_F64 || FMT == GLR_FMT_F32) && blockIdx.y == 0;
 
   const int64_t t_total = n_it * UPC;
@@ -292,6 +300,19 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
     const int s = (int)(it % kStages);
     mbar_wait(&ring.full[s], (uint32_t)((it / kStages) & 1));
     const double* st = wst + (int64_t)s * kStageDoubles;
+    // A fragments (and tail weights) are fetched one sample group ahead of their DMMAs
+    double2 a_nxt[MT];
+    double2 w_nxt[TAIL > 0 ? TAIL : 1];
+    {
+      const double2* ap = reinterpret_cast<const double2*>(st) + lane;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a_nxt[mt] = ap[mt * 32];
+      if (TAIL > 0) {
+        const double2* tp = reinterpret_cast<const double2*>(st + kChunkGroups * MT * kAtomDoubles) + j;
+#pragma unroll
+        for (int t = 0; t < TAIL; ++t) w_nxt[t] = tp[t * 4];
+      }
+    }
 #pragma unroll
     for (int u = 0; u < UPC; ++u) {
       ld.advance();
@@ -299,10 +320,24 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
       if (t < t_total) ld.load(s_begin + t * (UG * kGroup));
 #pragma unroll
       for (int g = 0; g < UG; ++g) {
-        const double2* ap = reinterpret_cast<const double2*>(st + (int64_t)(u * UG + g) * MT * kAtomDoubles) + lane;
+        const int gg = u * UG + g;
         double2 a[MT];
+        double2 w[TAIL > 0 ? TAIL : 1];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) a[mt] = ap[mt * 32];
+        for (int mt = 0; mt < MT; ++mt) a[mt] = a_nxt[mt];
+#pragma unroll
+        for (int t2 = 0; t2 < (TAIL > 0 ? TAIL : 1); ++t2) w[t2] = w_nxt[t2];
+        if (gg + 1 < kChunkGroups) {
+          const double2* ap = reinterpret_cast<const double2*>(st + (int64_t)(gg + 1) * MT * kAtomDoubles) + lane;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) a_nxt[mt] = ap[mt * 32];
+          if (TAIL > 0) {
+            const double2* tp =
+                reinterpret_cast<const double2*>(st + kChunkGroups * MT * kAtomDoubles + (gg + 1) * TAIL * kGroup) + j;
+#pragma unroll
+            for (int t2 = 0; t2 < TAIL; ++t2) w_nxt[t2] = tp[t2 * 4];
+          }
+        }
         double xa[NT], xb[NT];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) ld.get(g, nt, xa[nt], xb[nt]);
@@ -314,6 +349,12 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, xa[nt]);
+        if (TAIL > 0) {
+#pragma unroll
+          for (int t2 = 0; t2 < TAIL; ++t2)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) tacc[t2][nt] = fma(w[t2].x, xa[nt], fma(w[t2].y, xb[nt], tacc[t2][nt]));
+        }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -325,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
   }
 
   // C fragment: lane (r, j) holds rows r of each m-tile, variants 2j, 2j+1 of each n-tile
-  const int64_t rows = (int64_t)p.n_groups * MT * 8;
+  const int64_t rows = (int64_t)p.n_groups * MT * 8 + (TAIL > 0 ? 8 : 0);
   double* Sz = p.S + (int64_t)blockIdx.z * rows * p.ldS;
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
@@ -335,6 +376,17 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams p) {
       const int64_t col = v_warp + nt * 8 + 2 * j;
       *reinterpret_cast<double2*>(Sz + row * p.ldS + col) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
     }
+  if (TAIL > 0) {
+#pragma unroll
+    for (int t = 0; t < TAIL; ++t)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        double v = tacc[t][nt];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (j == 0) Sz[((int64_t)MT * 8 + t) * p.ldS + v_warp + nt * 8 + r] = v;
+      }
+  }
   if (want_sq) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -368,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) masked_kernel(const MaskedParams 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Ring ring;
-  ring.init(smem, tid);
+  ring.init(smem, tid, kWarps);
   double* stage0 = reinterpret_cast<double*>(smem + kBarBytes);
   double* negA_s = stage0 + (int64_t)kStages * stageDoubles;  // [kWarps][NT][2*KT2][32]
 
@@ -481,25 +533,39 @@ __global__ void __launch_bounds__(kThreads, 1) masked_kernel(const MaskedParams 
 // ------------------------------------------------------------------------------------------------
 // per-format dispatch (instantiated in gram_<fmt>.cu so the formats compile in parallel)
 // ------------------------------------------------------------------------------------------------
-template <int FMT, int MT, int NT>
+template <int FMT, int MT, int NT, int TAIL, int WARPS = kWarps>
 void launch_gram_inst(const GramParams& p, cudaStream_t st) {
-  const int tile = kWarps * NT * 8;
+  const int tile = WARPS * NT * 8;
   dim3 grid((unsigned)ceil_div(p.x.n_variants, tile), (unsigned)p.n_groups, (unsigned)p.n_split);
-  const size_t smem = kBarBytes + (size_t)kStages * kChunkGroups * MT * kAtomDoubles * 8;
-  auto kern = gram_kernel<FMT, MT, NT>;
+  const size_t smem = kBarBytes + (size_t)kStages * kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup) * 8;
+  auto kern = gram_kernel<FMT, MT, NT, TAIL, WARPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<grid, kThreads, smem, st>>>(p);
+  kern<<<grid, (WARPS + 1) * 32, smem, st>>>(p);
 }
 
-template <int FMT, int NT>
+// tail columns are instantiated for MT <= 4 only (TAILS = false: formats that never use them)
+template <int FMT, int MT, int NT, bool TAILS, int WARPS>
+void launch_gram_tail(const GramParams& p, cudaStream_t st) {
+  if constexpr (TAILS && MT <= 4) {
+    switch (p.tail) {
+      case 1: launch_gram_inst<FMT, MT, NT, 1, WARPS>(p, st); return;
+      case 2: launch_gram_inst<FMT, MT, NT, 2, WARPS>(p, st); return;
+      case 3: launch_gram_inst<FMT, MT, NT, 3, WARPS>(p, st); return;
+      default: break;
+    }
+  }
+  launch_gram_inst<FMT, MT, NT, 0, WARPS>(p, st);
+}
+
+template <int FMT, int NT, bool TAILS, int WARPS = kWarps>
 void launch_gram_mt(const GramParams& p, cudaStream_t st) {
   switch (p.MT) {
-    case 1: launch_gram_inst<FMT, 1, NT>(p, st); break;
-    case 2: launch_gram_inst<FMT, 2, NT>(p, st); break;
-    case 3: launch_gram_inst<FMT, 3, NT>(p, st); break;
-    case 4: launch_gram_inst<FMT, 4, NT>(p, st); break;
-    case 6: launch_gram_inst<FMT, 6, NT>(p, st); break;
-    default: launch_gram_inst<FMT, 8, NT>(p, st); break;
+    case 1: launch_gram_tail<FMT, 1, NT, TAILS, WARPS>(p, st); break;
+    case 2: launch_gram_tail<FMT, 2, NT, TAILS, WARPS>(p, st); break;
+    case 3: launch_gram_tail<FMT, 3, NT, TAILS, WARPS>(p, st); break;
+    case 4: launch_gram_tail<FMT, 4, NT, TAILS, WARPS>(p, st); break;
+    case 6: launch_gram_tail<FMT, 6, NT, TAILS, WARPS>(p, st); break;
+    default: launch_gram_tail<FMT, 8, NT, TAILS, WARPS>(p, st); break;
   }
 }
 

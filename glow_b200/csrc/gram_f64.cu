@@ -3,7 +3,7 @@
 
 namespace glr {
 void launch_gram_f64(const GramParams& p, cudaStream_t st) {
-  launch_gram_mt<GLR_FMT_F64, 2>(p, st);
+  launch_gram_mt<GLR_FMT_F64, 2, true>(p, st);
 }
 void launch_masked_f64(const MaskedParams& p, cudaStream_t st) { launch_masked_mt<GLR_FMT_F64>(p, st); }
 }  // namespace glr

@@ -3,7 +3,7 @@
 
 namespace glr {
 void launch_gram_i8(const GramParams& p, cudaStream_t st) {
-  launch_gram_mt<GLR_FMT_I8, 2>(p, st);
+  launch_gram_mt<GLR_FMT_I8, 2, true>(p, st);
 }
 void launch_masked_i8(const MaskedParams& p, cudaStream_t st) { launch_masked_mt<GLR_FMT_I8>(p, st); }
 }  // namespace glr

@@ -28,15 +28,17 @@ struct GramParams {
   BlockView x;
   const double* wpk;   // packed W of this contig: [group][chunk][8 groups][MT][64]
   int32_t MT;          // m-tiles per column group (1,2,3,4,6,8)
+  int32_t tail;        // 0..3 extra columns accumulated with FP64 FMAs (single column group, MT <= 4)
   int32_t n_groups;    // column groups
   int64_t n_chunks;    // 64-sample chunks (W is zero padded to a whole chunk)
   int32_t n_split;     // split of the sample range across CTAs (deterministic 2-stage reduce)
   int32_t nt;          // n-tiles (8 variants) per warp: 2 or 4
-  double* S;           // [n_split][n_groups*MT*8][ldS]
+  int32_t warps;       // consumer warps per CTA: 8, or 16 (PLINK2 with nt == 2 only)
+  double* S;           // [n_split][n_groups*MT*8 (+8 if tail)][ldS]
   double* sxx_part;    // [n_split][ldS]   (F64 / F32 only, written by column group 0)
   int64_t ldS;         // >= G_b rounded up to the CTA tile
 };
-int gram_tile_variants(int nt);  // variants per CTA
+int gram_tile_variants(int nt, int warps = 8);  // variants per CTA
 void launch_gram(const GramParams& p, cudaStream_t st);
 
 // ---- pass 2 (only when some phenotype has missing samples): D = Mu^T (X - Q A)^2 ----------------
@@ -95,8 +97,10 @@ void launch_qty(const double* Q, const double* Y, int64_t N, int K, int P, doubl
 void launch_residualize(const double* Q, const double* T, double* Y, int64_t N, int K, int P, cudaStream_t st);
 // Packs columns [c0, c0+ncols) of a row-major [N x ld] matrix into pair-atom A layout at column
 // offset `dst_col0` of a packed operand with `MT` m-tiles per group.
+// `tail` extra columns (dst columns >= 8*MT, single group) are stored per stage after the atoms as
+// [8 sample groups][tail][8 samples] in natural sample order.
 void launch_pack_a(const double* src, int64_t N, int64_t ld, int c0, int ncols, const int64_t* geno_to_row,
-                   int64_t Ng, double* dst, int dst_col0, int MT, int64_t n_chunks, cudaStream_t st);
+                   int64_t Ng, double* dst, int dst_col0, int MT, int tail, int64_t n_chunks, cudaStream_t st);
 // Packs Q into the masked-pass B layout.
 void launch_pack_qb(const double* Q, int64_t N, int K, const int64_t* geno_to_row, int64_t Ng, double* dst, int KT2,
                     int64_t n_chunks, cudaStream_t st);

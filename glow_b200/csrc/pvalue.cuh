@@ -60,7 +60,7 @@ __device__ __forceinline__ double t_two_sided_pvalue(double t, const PvalConst& 
     for (int n = 0; n < 2000; ++n) {
       term *= (a + 0.5 + n) / (1.5 + n) * y;
       s += term;
-      if (term < 1e-17 * s) break;
+      if (term < 1e-16 * s) break;
     }
     const double q = exp(0.5 * log(y) + a * lx + c.logc_ser) * s;
     return 1.0 - q;
@@ -90,7 +90,7 @@ __device__ __forceinline__ double t_two_sided_pvalue(double t, const PvalConst& 
     d = 1.0 / d;
     const double del = d * cc;
     h *= del;
-    if (fabs(del - 1.0) < 2e-16) break;
+    if (fabs(del - 1.0) < 4e-15) break;  // a few ulps: |del - 1| can hover at 1-2 ulp forever
   }
   return exp(a * lx + 0.5 * log(y) + c.logc_cf) * h;
 }

@@ -1,0 +1,223 @@
+"""CPU-side tests: the C ABI exports what include/glow_b200.h declares, host logic mirrors the
+reference's validation behaviour, and the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, 'include', 'glow_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(glr_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from glow_b200 import _capi
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    declared = _header_functions()
+    assert 'glr_state_create' in declared and 'glr_run_block' in declared
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/glow_b200.h but not exported'
+    assert sorted(_capi.SYMBOLS) == declared  # the ctypes binding covers exactly the header
+    assert _capi.load().glr_abi_version() == _capi.GLR_ABI_VERSION
+
+
+def test_ctypes_structs_match_header_layout():
+    # compile a tiny C program that prints sizeof/offsetof of the ABI structs and compare with ctypes
+    from glow_b200 import _capi
+    prog = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "glow_b200.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu\n", sizeof(glr_state_desc), sizeof(glr_block_desc), sizeof(glr_block_out), sizeof(glr_timing));
+      printf("%zu %zu %zu %zu\n", offsetof(glr_state_desc, Q), offsetof(glr_state_desc, dof), offsetof(glr_state_desc, memspace), offsetof(glr_block_desc, row_stride_bytes));
+      return 0;
+    }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, 'a.c')
+        open(c, 'w').write(prog)
+        exe = os.path.join(d, 'a.out')
+        subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    sizes = [int(x) for x in out]
+    assert sizes[:4] == [ctypes.sizeof(_capi.StateDesc), ctypes.sizeof(_capi.BlockDesc), ctypes.sizeof(_capi.BlockOut),
+                         ctypes.sizeof(_capi.Timing)]
+    assert sizes[4:] == [_capi.StateDesc.Q.offset, _capi.StateDesc.dof.offset, _capi.StateDesc.memspace.offset,
+                         _capi.BlockDesc.row_stride_bytes.offset]
+
+
+def _no_gpu():
+    from glow_b200 import _capi
+    return _capi.load().glr_device_count() <= 0
+
+
+@pytest.mark.skipif(not _no_gpu(), reason='only meaningful on a machine without a GPU')
+def test_fails_loudly_without_gpu():
+    import glow_b200
+    from glow_b200._capi import GlowB200Error
+    rg = np.random.default_rng(0)
+    with pytest.raises(GlowB200Error, match='no CPU fallback'):
+        glow_b200.gwas.linear_regression(pd.DataFrame({'values': list(rg.random((3, 10)))}),
+                                         pd.DataFrame(rg.random((10, 2))))
+
+
+def test_product_code_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'glow_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle', txt, flags=re.M) or 'linreg_oracle' in txt:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+
+
+# ---- validation errors raised before any device work (reference: test_lin_reg.py:311-336,454-509,565-586) ----
+def _lr(*a, **k):
+    import glow_b200
+    return glow_b200.gwas.linear_regression(*a, **k)
+
+
+def _frames(rg, n=10, g=3, p=5, k=2):
+    return (pd.DataFrame({'values': list(rg.random((g, n)))}), pd.DataFrame(rg.random((n, p))),
+            pd.DataFrame(rg.random((n, k))))
+
+
+def test_validates_missing_covariates(rg):
+    gdf, phe, cov = _frames(rg)
+    cov.loc[0, 0] = np.nan
+    with pytest.raises(ValueError):
+        _lr(gdf, phe, cov)
+
+
+def test_validate_same_number_of_rows(rg):
+    gdf, phe, _ = _frames(rg, n=4)
+    with pytest.raises(ValueError):
+        _lr(gdf, phe, pd.DataFrame(rg.random((5, 2))))
+
+
+def test_too_many_missing(rg):
+    gdf, phe, cov = _frames(rg, n=25, p=24, k=10)
+    missing = np.triu(np.ones(phe.shape))
+    missing[:, -1] = 0
+    phe[missing.astype('bool')] = np.nan
+    with pytest.raises(ValueError):
+        _lr(gdf, phe, cov)
+
+
+def test_bad_datatype(rg):
+    gdf, phe, cov = _frames(rg)
+    with pytest.raises(ValueError):
+        _lr(gdf, phe, cov, dt=np.int32)
+
+
+def test_bad_column_name(rg):
+    gdf, phe, cov = _frames(rg)
+    with pytest.raises(ValueError):
+        _lr(gdf.rename(columns={'values': 'genotypes'}), phe, cov, values_column='genotypes')
+
+
+def test_offset_wrong_columns(rg):
+    gdf, phe, _ = _frames(rg, n=25, p=10)
+    off = pd.DataFrame(rg.random((25, 10)), columns=range(10, 20))
+    with pytest.raises(ValueError):
+        _lr(gdf, phe, offset_df=off)
+
+
+def test_offset_wrong_index(rg):
+    gdf, phe, _ = _frames(rg, n=25, p=10)
+    off = pd.DataFrame(rg.random((25, 10)), index=range(1, 26))
+    with pytest.raises(ValueError):
+        _lr(gdf, phe, offset_df=off)
+
+
+def test_offset_wrong_multi_index(rg):
+    gdf, phe, _ = _frames(rg, n=25, p=10)
+    off = pd.DataFrame(rg.random((50, 10)), pd.MultiIndex.from_product([range(1, 26), ['chr1', 'chr2']]))
+    with pytest.raises(ValueError):
+        _lr(gdf, phe, offset_df=off)
+
+
+def test_intersect_requires_sample_ids(rg):
+    gdf, phe, cov = _frames(rg)
+    with pytest.raises(ValueError):
+        _lr(gdf, phe, cov, intersect_samples=True)
+
+
+def test_subset_contigs_states(rg):
+    # test_lin_reg.py:607-620
+    from glow_b200.gwas import lin_reg as lr
+    n, p = 25, 25
+    contigs = ['chr1', 'chr2', 'chr3']
+    phe = pd.DataFrame(rg.random((n, p)))
+    off = pd.DataFrame(rg.random((n * 3, p)), index=pd.MultiIndex.from_product([phe.index, contigs]))
+    mask = (~np.isnan(phe.to_numpy())).astype(np.float64)
+    st = lr._create_YState(phe.to_numpy(), phe, off, mask, np.float64, None)
+    assert set(st.keys()) == set(contigs)
+    st = lr._create_YState(phe.to_numpy(), phe, off, mask, np.float64, ['chr1', 'chr3'])
+    assert set(st.keys()) == {'chr1', 'chr3'}
+    # the per-contig states follow lin_reg.py:194-199
+    from oracle import linreg_oracle as orc
+    ref = orc.prepare_state(phe, None, off)
+    ours = lr._create_YState(ref.y_state['chr1'].Y * 0 + _prepared_Y(phe), phe, off, mask, np.float64, None)
+    for c in contigs:
+        np.testing.assert_allclose(ours[c].Y, ref.y_state[c].Y, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(ours[c].YdotY, ref.y_state[c].YdotY, rtol=1e-12)
+
+
+def _prepared_Y(phe):
+    from glow_b200.gwas import functions as fx
+    C = fx._add_intercept(np.empty((phe.shape[0], 0)), phe.shape[0])
+    Q = np.linalg.qr(C)[0]
+    Y = phe.to_numpy(np.float64, copy=True)
+    m = (~np.isnan(Y)).astype(np.float64)
+    Y = np.nan_to_num(Y)
+    Y -= Y.mean(axis=0)
+    Y = fx._residualize_in_place(Y, Q) * m
+    return Y / np.sqrt(np.sum(Y**2, axis=0) / (m.sum(axis=0) - Q.shape[1]))[None, :]
+
+
+def test_loco_dispatch_first_appearance_order():
+    from glow_b200.gwas import functions as fx
+    pdf = pd.DataFrame({'contigName': ['b', 'a', 'b', 'c', 'a'], 'i': range(5)})
+    seen = []
+
+    def f(sub, state):
+        seen.append((state, sub['i'].tolist()))
+        return sub
+
+    out = fx._loco_dispatch(pdf, {'a': 'A', 'b': 'B', 'c': 'C'}, f)
+    assert seen == [('B', [0, 2]), ('A', [1, 4]), ('C', [3])]
+    assert out['i'].tolist() == [0, 2, 1, 4, 3]
+
+
+def test_get_indices_to_drop_and_keep_index():
+    from glow_b200.gwas import functions as fx
+    from glow_b200.gwas.lin_reg import _keep_index
+    phe = pd.DataFrame({'y': [1.0, 2.0, 3.0]}, index=['s1', 's3', 's4'])
+    drop = fx._get_indices_to_drop(phe, ['s0', 's1', 's2', 's3', 's4'])
+    assert drop.tolist() == [0, 2]
+    assert _keep_index(5, drop).tolist() == [1, 3, 4]
+    assert _keep_index(5, np.array([], dtype=np.int64)) is None
+
+
+def test_plink_source_and_block_checks(golden_dir):
+    import glow_b200
+    d = np.load(os.path.join(golden_dir, 'plink_kat.npz'))
+    src = glow_b200.PlinkBedSource(d['bed'].tobytes(), 5)
+    metas = list(src.blocks())
+    assert metas[0][1].format == 'plink2' and metas[0][1].data.shape == (5, 2)
+    with pytest.raises(ValueError):
+        glow_b200.PlinkBedSource(b'\x00\x00\x00' + d['bed'][3:].tobytes(), 5)
+    with pytest.raises(ValueError):
+        glow_b200.PlinkBedSource(d['bed'].tobytes(), 9)  # 10 payload bytes are not a multiple of ceil(9/4) = 3
