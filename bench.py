@@ -165,11 +165,22 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference block kernel on the host cores
 # --------------------------------------------------------------------------------------------------
+def use_all_host_cores():
+    """BLAS on every host core, also under torchrun (which exports OMP_NUM_THREADS=1)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+    return os.cpu_count()
+
+
 def cpu_reference_arm(packed_host, n_samples, Q, Y, mask, ydy, scale, dof, block_variants, n_blocks, warm=1):
     """Times oracle/linreg_oracle.block_stats (= _linear_regression_inner, lin_reg.py:226-249, incl.
     the np.column_stack transpose) on `n_blocks` blocks of `block_variants` variants; BLAS uses every
     host core.  Decode + mean substitution (JVM side in the reference) are NOT timed."""
     from oracle import linreg_oracle as orc
+    use_all_host_cores()
     st = orc.OracleState(Q, mask, scale, dof, ['y0'], orc.OracleYState(Y, ydy), None, None)
     times = []
     for b in range(warm + n_blocks):
@@ -189,6 +200,7 @@ def run_reference_impl(args):
     if rank != 0:
         return
     n = args.samples
+    use_all_host_cores()
     Q, Y, mask, ydy, scale, dof = host_state(n)
     bv = args.cpu_block_variants
     rg = np.random.default_rng(SEED)

@@ -60,7 +60,7 @@ struct DevBuf {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
-  DevBuf geno, out, s_part, s_red, sxx_part, sxx, v1, d_part, d_red;
+  DevBuf geno, out, s_part, s_red, sxx_part, sxx, v1, d_part, d_red, xx;
   bool busy = false;
   bool has_masked = false, has_prepass = false;
   int launches = 0;
@@ -68,10 +68,7 @@ struct Lane {
 };
 
 int pick_mt(int n_mtiles) {
-  const int opts[] = {1, 2, 3, 4, 6, 8};
-  for (int o : opts)
-    if (n_mtiles <= o) return o;
-  return 8;
+  return n_mtiles < 1 ? 1 : (n_mtiles > 8 ? 8 : n_mtiles);
 }
 int pick_mt_masked(int n_mtiles) {
   const int opts[] = {1, 2, 4, 8};
@@ -107,7 +104,7 @@ struct glr_state {
   PvalConst pc{};
   std::vector<Lane> lanes;
   int sm_count = 148;
-  int force_split = 0, force_warps = 0;
+  int force_split = 0;
 };
 
 extern "C" {
@@ -151,7 +148,7 @@ int glr_state_destroy(glr_state* st) {
     if (l.stream) cudaStreamSynchronize(l.stream);
     for (auto& e : l.ev)
       if (e) cudaEventDestroy(e);
-    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.sxx_part, &l.sxx, &l.v1, &l.d_part, &l.d_red})
+    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.sxx_part, &l.sxx, &l.v1, &l.d_part, &l.d_red, &l.xx})
       b->release();
     if (l.stream) cudaStreamDestroy(l.stream);
   }
@@ -199,7 +196,6 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   st->n_chunks = ceil_div(st->Ng, kChunk);
   CU(cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, d->device));
   if (const char* e = getenv("GLR_SPLIT")) st->force_split = atoi(e);
-  if (const char* e = getenv("GLR_WARPS")) st->force_warps = atoi(e);
 
   const int64_t N = st->N, Ng = st->Ng;
   const int K = st->K, P = st->P, C = st->C;
@@ -444,8 +440,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
 
   // ---- plan ----
   const int nt = 2;
-  int warps = 8;
-  if (b->format == GLR_FMT_PLINK2 && st->force_warps != 8) warps = 16;
+  const int warps = (b->format == GLR_FMT_PLINK2 && st->MT <= 4) ? 16 : 8;
   const int tile = gram_tile_variants(nt, warps);
   const int64_t ldS = round_up(G, 256);
   const int64_t ctas = ceil_div(G, tile) * st->n_groups;
@@ -471,6 +466,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
     if (int rc = L.s_part.ensure((size_t)n_split * Mpad * ldS * 8)) return rc;
   if (int rc = L.sxx.ensure((size_t)ldS * 8)) return rc;
   if (int rc = L.v1.ensure((size_t)ldS * 8)) return rc;
+  if (int rc = L.xx.ensure((size_t)ldS * 8)) return rc;
   if (float_fmt && n_split > 1)
     if (int rc = L.sxx_part.ensure((size_t)n_split * ldS * 8)) return rc;
   const int n_out = st->verbose ? 7 : 4;
@@ -590,8 +586,8 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   ep.n = st->verbose ? d_outs[4] : nullptr;
   ep.sum_x = st->verbose ? d_outs[5] : nullptr;
   ep.ytx = st->verbose ? d_outs[6] : nullptr;
-  launch_epilogue(ep, s);
-  ++L.launches;
+  launch_epilogue(ep, L.xx.as<double>(), s);
+  L.launches += 2;
   CU(cudaEventRecord(L.ev[4], s));
   CU(cudaGetLastError());
   if (o->memspace == GLR_MEM_HOST) {

@@ -142,46 +142,70 @@ void launch_reduce_splits(const double* part, double* out, int64_t rows, int64_t
 // epilogue: lin_reg.py:241-249 per (phenotype, variant); variants on x (coalesced), phenotypes
 // strided over y.  HBM-bound on the 4 x 8 B result writes.
 // ------------------------------------------------------------------------------------------------
-constexpr int kEpiThreads = 128;
-constexpr int kEpiPhenoPerBlock = 8;
+constexpr int kEpiThreads = 256;
 
-__global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpilogueParams p) {
+// xx_full[v] = sum x^2 - |Q^T x|^2  (= |x - Q Q^T x|^2, the fully observed XdotX)
+__global__ void __launch_bounds__(kEpiThreads) xx_full_kernel(const double* S, const double* sxx, int K, int G,
+                                                               int64_t ldS, double* xx) {
   const int v = blockIdx.x * kEpiThreads + threadIdx.x;
-  if (v >= p.G) return;
-  // XdotX for fully observed phenotypes: sum x^2 - |Q^T x|^2  (= |x - Q Q^T x|^2)
+  if (v >= G) return;
   double a2 = 0.0;
-  for (int k = 0; k < p.K; ++k) {
-    const double a = p.S[(int64_t)k * p.ldS + v];
+  for (int k = 0; k < K; ++k) {
+    const double a = S[(int64_t)k * ldS + v];
     a2 = fma(a, a, a2);
   }
-  const double xx_full = p.sxx[v] - a2;
-  const int p0 = blockIdx.y * kEpiPhenoPerBlock;
-  const int p1 = min(p.P, p0 + kEpiPhenoPerBlock);
-  for (int ph = p0; ph < p1; ++ph) {
-    const int mid = p.mask_id[ph];
-    const double XdotX = mid < 0 ? xx_full : p.D[(int64_t)mid * p.ldS + v];
-    const double XdotY = p.S[(int64_t)(p.K + ph) * p.ldS + v];
-    const double recip = 1.0 / XdotX;                                             // lin_reg.py:241
-    const double beta = XdotY * recip;                                            // :242
-    const double se = sqrt((p.YdotY[ph] * recip - beta * beta) / p.dof);          // :243
-    const double T = beta / se;                                                   // :244
-    const double pv = t_two_sided_pvalue(T, p.pc);                                // :245
-    const int64_t o = (int64_t)ph * p.G + v;
-    p.effect[o] = beta * p.Y_scale[ph];                                           // :247-248
-    p.stderror[o] = se * p.Y_scale[ph];                                           // :249
-    p.tvalue[o] = T;
-    p.pvalue[o] = pv;
-    if (p.verbose) {                                                              // :234-237
-      p.n[o] = p.n_obs[ph];
-      p.sum_x[o] = p.S[(int64_t)(p.K + p.P + ph) * p.ldS + v];
-      p.ytx[o] = p.S[(int64_t)(p.K + 2 * p.P + ph) * p.ldS + v];
-    }
+  xx[v] = sxx[v] - a2;
+}
+
+// one thread per (phenotype, variant) test: the p-value loops are latency bound, so parallelism
+// across tests (not work per thread) is what hides them
+__global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpilogueParams p, const double* xx_full) {
+  const int v = blockIdx.x * kEpiThreads + threadIdx.x;
+  const int ph = blockIdx.y;
+  if (v >= p.G) return;
+  const int mid = p.mask_id[ph];
+  const double XdotX = mid < 0 ? xx_full[v] : p.D[(int64_t)mid * p.ldS + v];
+  const double XdotY = p.S[(int64_t)(p.K + ph) * p.ldS + v];
+  const double recip = 1.0 / XdotX;                                             // lin_reg.py:241
+  const double beta = XdotY * recip;                                            // :242
+  const double se = sqrt((p.YdotY[ph] * recip - beta * beta) / p.dof);          // :243
+  const double T = beta / se;                                                   // :244
+  const double pv = t_two_sided_pvalue(T, p.pc);                                // :245
+  const int64_t o = (int64_t)ph * p.G + v;
+  p.effect[o] = beta * p.Y_scale[ph];                                           // :247-248
+  p.stderror[o] = se * p.Y_scale[ph];                                           // :249
+  p.tvalue[o] = T;
+  p.pvalue[o] = pv;
+  if (p.verbose) {                                                              // :234-237
+    p.n[o] = p.n_obs[ph];
+    p.sum_x[o] = p.S[(int64_t)(p.K + p.P + ph) * p.ldS + v];
+    p.ytx[o] = p.S[(int64_t)(p.K + 2 * p.P + ph) * p.ldS + v];
   }
 }
-void launch_epilogue(const EpilogueParams& p, cudaStream_t st) {
+void launch_epilogue(const EpilogueParams& p, double* xx_scratch, cudaStream_t st) {
   if (p.G <= 0 || p.P <= 0) return;
-  dim3 grid((unsigned)ceil_div(p.G, kEpiThreads), (unsigned)ceil_div(p.P, kEpiPhenoPerBlock));
-  epilogue_kernel<<<grid, kEpiThreads, 0, st>>>(p);
+  const unsigned gx = (unsigned)ceil_div(p.G, kEpiThreads);
+  xx_full_kernel<<<gx, kEpiThreads, 0, st>>>(p.S, p.sxx, p.K, p.G, p.ldS, xx_scratch);
+  for (int p0 = 0; p0 < p.P; p0 += 65535) {  // gridDim.y limit
+    EpilogueParams q = p;
+    const int np = p.P - p0 < 65535 ? p.P - p0 : 65535;
+    q.P = p.P;
+    q.mask_id += p0;
+    q.YdotY += p0;
+    q.Y_scale += p0;
+    q.n_obs += p0;
+    q.effect += (int64_t)p0 * p.G;
+    q.stderror += (int64_t)p0 * p.G;
+    q.tvalue += (int64_t)p0 * p.G;
+    q.pvalue += (int64_t)p0 * p.G;
+    if (p.verbose) {
+      q.n += (int64_t)p0 * p.G;
+      q.sum_x += (int64_t)p0 * p.G;
+      q.ytx += (int64_t)p0 * p.G;
+    }
+    q.S = p.S + (int64_t)p0 * p.ldS;  // rows K+ph, K+P+ph, K+2P+ph all shift by p0
+    epilogue_kernel<<<dim3(gx, (unsigned)np), kEpiThreads, 0, st>>>(q, xx_scratch);
+  }
 }
 
 __global__ void pvalues_kernel(const double* t, int64_t n, PvalConst pc, double* out) {

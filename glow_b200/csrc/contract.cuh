@@ -35,25 +35,42 @@ constexpr int kBarBytes = 128;  // full[4] + empty[4] mbarriers, padded
 template <int FMT, int NT>
 struct XLoader;
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// PLINK 2-bit.  Decode = table lookup: every variant of the warp has a 4-entry table
+// {code 00 -> 2, 01 -> missing substitute, 10 -> 1, 11 -> 0} in shared memory
+// (PlinkRowToInternalRowConverter.scala:40-47 + genotype_states + mean_substitute); a lane fetches its two
+// values of a sample group with two 8-byte LDS.  Lanes 0-15 / 16-31 of an LDS.64 touch 4 variants
+// x 4 entries = 16 distinct 8-byte bank pairs (or broadcast the same entry): always conflict free.
 template <int NT>
 struct XLoader<GLR_FMT_PLINK2, NT> {
   static constexpr int UG = 8;  // one 64-sample chunk = 16 bytes per variant
+  static constexpr int kLutDoublesPerWarp = NT * 8 * 4;
   const uint8_t* row[NT];
-  double v1[NT];
+  uint32_t lut[NT];  // shared-space byte address of this lane's variant table
   uint32_t cur[NT][5], nxt[NT][5];
   uint32_t sh_cur[NT], sh_nxt[NT];
   int64_t row_bytes;
   int nib_shift;
 
-  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j) {
+  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j, double* lut_warp, int lane) {
     row_bytes = (x.n_geno + 3) >> 2;
     nib_shift = 4 * j;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      int v = min(v0 + nt * 8 + r, x.n_variants - 1);
+      const int v = min(v0 + nt * 8 + r, x.n_variants - 1);
       row[nt] = x.base + (int64_t)v * x.stride;
-      v1[nt] = x.v1[v];
+      // lane 4*r' + c writes entry c of variant r' of this n-tile
+      const int c = lane & 3;
+      const int vv = min(v0 + nt * 8 + (lane >> 2), x.n_variants - 1);
+      lut_warp[(nt * 8 + (lane >> 2)) * 4 + c] = dec((uint32_t)c, x.v1[vv]);
+      lut[nt] = smem_u32(lut_warp + (nt * 8 + r) * 4);
     }
+    __syncwarp();
   }
   __device__ __forceinline__ void load(int64_t s0) {
     const int64_t b0 = s0 >> 2;
@@ -95,7 +112,6 @@ struct XLoader<GLR_FMT_PLINK2, NT> {
     }
   }
   static __device__ __forceinline__ double dec(uint32_t code, double miss) {
-    // 00 -> 2, 01 -> missing, 10 -> 1, 11 -> 0  (PlinkRowToInternalRowConverter.scala:40-47 + genotype_states)
     const int hi = (code == 0u) ? 0x40000000 : ((code == 2u) ? 0x3FF00000 : 0);
     const double v = __hiloint2double(hi, 0);
     return (code == 1u) ? miss : v;
@@ -103,9 +119,9 @@ struct XLoader<GLR_FMT_PLINK2, NT> {
   __device__ __forceinline__ void get(int g, int nt, double& xa, double& xb) const {
     const int i = g >> 1;
     const uint32_t w = __funnelshift_r(cur[nt][i], cur[nt][i + 1], sh_cur[nt]);
-    const uint32_t nib = (w >> (16 * (g & 1) + nib_shift)) & 15u;
-    xa = dec(nib & 3u, v1[nt]);
-    xb = dec(nib >> 2, v1[nt]);
+    const uint32_t nib = w >> (16 * (g & 1) + nib_shift);
+    xa = lds_f64(lut[nt] + ((nib & 3u) << 3));
+    xb = lds_f64(lut[nt] + ((nib & 12u) << 1));
   }
 };
 
@@ -120,7 +136,8 @@ struct XLoaderFloat {
   int joff;
   bool vec;
 
-  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j) {
+  static constexpr int kLutDoublesPerWarp = 0;
+  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j, double*, int) {
     n = x.n_geno;
     joff = 2 * j;
     vec = ((reinterpret_cast<uintptr_t>(x.base) | (uintptr_t)x.stride) & (2 * sizeof(T) - 1)) == 0;
@@ -132,6 +149,16 @@ struct XLoaderFloat {
   }
   __device__ __forceinline__ void load(int64_t s0) {
     const bool fast = s0 + UG * 8 <= n;
+    // pull the lines two more units ahead into L2 (no registers held): one lane per 128-byte line
+    if (joff == 0) {
+      const int64_t sp = s0 + 2 * UG * 8;
+      constexpr int kPerLine = 128 / (int)sizeof(T);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < UG * 8; e += kPerLine)
+          if (sp + e < n) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row[nt] + sp + e));
+    }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
@@ -178,7 +205,8 @@ struct XLoader<GLR_FMT_I8, NT> {
   int64_t n;
   int joff;
 
-  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j) {
+  static constexpr int kLutDoublesPerWarp = 0;
+  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j, double*, int) {
     n = x.n_geno;
     joff = 2 * j;
 #pragma unroll
@@ -276,7 +304,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
   const int r = lane >> 2, j = lane & 3;
   const int v_warp = blockIdx.x * (WARPS * NT * 8) + warp * (NT * 8);
   Loader ld;
-  ld.init(p.x, v_warp, r, j);
+  ld.init(p.x, v_warp, r, j, wst + (int64_t)kStages * kStageDoubles + warp * Loader::kLutDoublesPerWarp, lane);
 
   double acc[MT][NT][2];
 #pragma unroll
@@ -318,6 +346,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
       ld.advance();
       const int64_t t = it * UPC + u + 1;
       if (t < t_total) ld.load(s_begin + t * (UG * kGroup));
+      // genotype values are decoded one sample group ahead of their DMMAs as well
+      double xa_n[NT], xb_n[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) ld.get(0, nt, xa_n[nt], xb_n[nt]);
 #pragma unroll
       for (int g = 0; g < UG; ++g) {
         const int gg = u * UG + g;
@@ -327,6 +359,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
         for (int mt = 0; mt < MT; ++mt) a[mt] = a_nxt[mt];
 #pragma unroll
         for (int t2 = 0; t2 < (TAIL > 0 ? TAIL : 1); ++t2) w[t2] = w_nxt[t2];
+        double xa[NT], xb[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          xa[nt] = xa_n[nt];
+          xb[nt] = xb_n[nt];
+        }
         if (gg + 1 < kChunkGroups) {
           const double2* ap = reinterpret_cast<const double2*>(st + (int64_t)(gg + 1) * MT * kAtomDoubles) + lane;
 #pragma unroll
@@ -338,9 +376,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
             for (int t2 = 0; t2 < TAIL; ++t2) w_nxt[t2] = tp[t2 * 4];
           }
         }
-        double xa[NT], xb[NT];
+        if (g + 1 < UG) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) ld.get(g, nt, xa[nt], xb[nt]);
+          for (int nt = 0; nt < NT; ++nt) ld.get(g + 1, nt, xa_n[nt], xb_n[nt]);
+        }
         if (FMT == GLR_FMT_F64 || FMT == GLR_FMT_F32) {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) sq[nt] = fma(xa[nt], xa[nt], fma(xb[nt], xb[nt], sq[nt]));
@@ -448,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) masked_kernel(const MaskedParams 
   const int r = lane >> 2, j = lane & 3;
   const int v_warp = blockIdx.x * (kWarps * NT * 8) + warp * (NT * 8);
   Loader ld;
-  ld.init(p.x, v_warp, r, j);
+  ld.init(p.x, v_warp, r, j, negA_s + (int64_t)kWarps * NT * 2 * KT2 * 32 + warp * Loader::kLutDoublesPerWarp, lane);
 
   // A operand of the residual product: lane (r, j) holds -a[4*kk + j][variant r] for k-step kk
   double* negA = negA_s + (int64_t)warp * NT * 2 * KT2 * 32;
@@ -537,7 +576,8 @@ template <int FMT, int MT, int NT, int TAIL, int WARPS = kWarps>
 void launch_gram_inst(const GramParams& p, cudaStream_t st) {
   const int tile = WARPS * NT * 8;
   dim3 grid((unsigned)ceil_div(p.x.n_variants, tile), (unsigned)p.n_groups, (unsigned)p.n_split);
-  const size_t smem = kBarBytes + (size_t)kStages * kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup) * 8;
+  const size_t smem = kBarBytes + (size_t)kStages * kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup) * 8 +
+                      (size_t)WARPS * XLoader<FMT, NT>::kLutDoublesPerWarp * 8;
   auto kern = gram_kernel<FMT, MT, NT, TAIL, WARPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<grid, (WARPS + 1) * 32, smem, st>>>(p);
@@ -557,16 +597,25 @@ void launch_gram_tail(const GramParams& p, cudaStream_t st) {
   launch_gram_inst<FMT, MT, NT, 0, WARPS>(p, st);
 }
 
-template <int FMT, int NT, bool TAILS, int WARPS = kWarps>
+// MT_LO..MT_HI: which m-tile counts this (NT, WARPS) shape is instantiated for
+template <int FMT, int NT, bool TAILS, int WARPS = kWarps, int MT_LO = 1, int MT_HI = 8>
 void launch_gram_mt(const GramParams& p, cudaStream_t st) {
+#define GLR_MT_CASE(M)                                                                         \
+  case M:                                                                                      \
+    if constexpr (M >= MT_LO && M <= MT_HI) launch_gram_tail<FMT, M, NT, TAILS, WARPS>(p, st); \
+    break;
   switch (p.MT) {
-    case 1: launch_gram_tail<FMT, 1, NT, TAILS, WARPS>(p, st); break;
-    case 2: launch_gram_tail<FMT, 2, NT, TAILS, WARPS>(p, st); break;
-    case 3: launch_gram_tail<FMT, 3, NT, TAILS, WARPS>(p, st); break;
-    case 4: launch_gram_tail<FMT, 4, NT, TAILS, WARPS>(p, st); break;
-    case 6: launch_gram_tail<FMT, 6, NT, TAILS, WARPS>(p, st); break;
-    default: launch_gram_tail<FMT, 8, NT, TAILS, WARPS>(p, st); break;
+    GLR_MT_CASE(1)
+    GLR_MT_CASE(2)
+    GLR_MT_CASE(3)
+    GLR_MT_CASE(4)
+    GLR_MT_CASE(5)
+    GLR_MT_CASE(6)
+    GLR_MT_CASE(7)
+    GLR_MT_CASE(8)
+    default: break;
   }
+#undef GLR_MT_CASE
 }
 
 template <int FMT, int MT>
@@ -574,7 +623,8 @@ void launch_masked_inst(const MaskedParams& p, cudaStream_t st) {
   const int tile = kWarps * kMaskedNT * 8;
   dim3 grid((unsigned)ceil_div(p.x.n_variants, tile), (unsigned)p.n_groups, (unsigned)p.n_split);
   const size_t stage = (size_t)kChunkGroups * (MT + p.KT2) * kAtomDoubles * 8;
-  const size_t smem = kBarBytes + kStages * stage + (size_t)kWarps * kMaskedNT * 2 * p.KT2 * 32 * 8;
+  const size_t smem = kBarBytes + kStages * stage + (size_t)kWarps * kMaskedNT * 2 * p.KT2 * 32 * 8 +
+                      (size_t)kWarps * XLoader<FMT, kMaskedNT>::kLutDoublesPerWarp * 8;
   auto kern = masked_kernel<FMT, MT>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<grid, kThreads, smem, st>>>(p);

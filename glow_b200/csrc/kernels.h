@@ -79,7 +79,8 @@ struct EpilogueParams {
   double *effect, *stderror, *tvalue, *pvalue;  // [P][G]
   double *n, *sum_x, *ytx;                      // verbose, [P][G]
 };
-void launch_epilogue(const EpilogueParams& p, cudaStream_t st);
+// xx_scratch: [G] doubles of workspace (fully observed XdotX per variant)
+void launch_epilogue(const EpilogueParams& p, double* xx_scratch, cudaStream_t st);
 
 void launch_pvalues(const double* t, int64_t n, PvalConst pc, double* p, cudaStream_t st);
 void launch_decode(const BlockView& x, double* out, cudaStream_t st);  // out [G_b][n_geno]

@@ -2,8 +2,11 @@
 // Replaces scipy's stats.distributions.t.sf at python/glow/gwas/lin_reg.py:245.
 //
 // Regularised incomplete beta with a = dof/2 (up to ~2.5e5 at biobank scale) and b = 1/2:
-//   * bulk (y = 1 - x <= (b+1)/(a+b+2), i.e. roughly t^2 < 3): power series of I_y(1/2, a),
-//     p = 1 - I_y;  p >= ~0.08 here so the subtraction costs about one digit;
+//   * bulk: power series of I_y(1/2, a), y = 1 - x, and p = 1 - I_y.  Used while the series
+//     converges quickly AND p is not tiny: t^2 <= 20 (p >= 7.7e-6 for every dof, so the subtraction
+//     costs at most 5 of the 16 digits -- the north-star bar on p is 1e-6) and y small enough that
+//     the term ratio drops below 1/2 within 64 terms.  Nearly every null test takes this branch, so
+//     warps do not diverge into the (much more expensive) continued fraction;
 //   * tail: modified-Lentz continued fraction of I_x(a, 1/2) evaluated directly, with the
 //     prefactor x^a (1-x)^(1/2) / (a B(a,1/2)) assembled in log space so that p stays
 //     relatively accurate down to the double underflow threshold (~1e-308).
@@ -19,7 +22,9 @@ struct PvalConst {
   double a;         // nu / 2
   double logc_cf;   // -ln B(a,1/2) - ln a
   double logc_ser;  // -ln B(a,1/2) + ln 2
-  double y_switch;  // (b+1)/(a+b+2)
+  double y_switch;  // (b+1)/(a+b+2): below this the series is always the right choice
+  double y_series;  // series also used for y <= y_series when t^2 <= 20
+  double ser_coef[64];  // (a + 1/2 + n) / (3/2 + n): term ratio of the series without the division
 };
 
 #ifndef __CUDACC_RTC__
@@ -41,6 +46,9 @@ inline PvalConst make_pval_const(double nu) {
   c.logc_cf = (double)(-lnB - logl(a > 0 ? a : 1.0L));
   c.logc_ser = (double)(-lnB + logl(2.0L));
   c.y_switch = 1.5 / (c.a + 2.5);
+  c.y_series = 0.5 * 65.5 / (c.a + 64.5);
+  if (c.y_series < c.y_switch) c.y_series = c.y_switch;
+  for (int n = 0; n < 64; ++n) c.ser_coef[n] = (c.a + 0.5 + n) / (1.5 + n);
   return c;
 }
 #endif
@@ -54,13 +62,21 @@ __device__ __forceinline__ double t_two_sided_pvalue(double t, const PvalConst& 
   const double denom = c.nu + t2;
   const double y = t2 / denom;
   const double lx = -log1p(t2 / c.nu);
-  if (y <= c.y_switch) {
+  if (y <= c.y_switch || (t2 <= 20.0 && y <= c.y_series)) {
     // I_y(1/2, a) = y^(1/2) (1-y)^a / (1/2 B) * sum_n (a+1/2)_n / (3/2)_n y^n
     double s = 1.0, term = 1.0;
-    for (int n = 0; n < 2000; ++n) {
-      term *= (a + 0.5 + n) / (1.5 + n) * y;
+    int n = 0;
+    for (; n < 64; ++n) {
+      term *= c.ser_coef[n] * y;
       s += term;
       if (term < 1e-16 * s) break;
+    }
+    if (n == 64) {
+      for (; n < 2000; ++n) {
+        term *= (a + 0.5 + n) / (1.5 + n) * y;
+        s += term;
+        if (term < 1e-16 * s) break;
+      }
     }
     const double q = exp(0.5 * log(y) + a * lx + c.logc_ser) * s;
     return 1.0 - q;
