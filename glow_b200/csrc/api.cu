@@ -1,5 +1,6 @@
 // C ABI (include/glow_b200.h): state packing, lanes (streams + staging), block execution.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -60,7 +61,7 @@ struct DevBuf {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
-  DevBuf geno, out, s_part, s_red, sxx_part, sxx, v1, d_part, d_red, xx;
+  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx;
   bool busy = false;
   bool has_masked = false, has_prepass = false;
   int launches = 0;
@@ -88,6 +89,9 @@ struct glr_state {
   // pass-1 operand
   int Mcols = 0, MT = 1, n_groups = 1, tail = 0;
   int64_t s_rows = 0;  // rows of the S workspace
+  // intercept column of Q handled outside the GEMM: Q^T x for a constant column q0 is q0 * sum(x)
+  int has_icpt = 0;
+  double icpt_q0 = 0.0;
   int64_t w_contig_doubles = 0;
   double* wpk = nullptr;  // [C][n_groups][n_chunks][8][MT][64]
   // masked pass
@@ -148,7 +152,7 @@ int glr_state_destroy(glr_state* st) {
     if (l.stream) cudaStreamSynchronize(l.stream);
     for (auto& e : l.ev)
       if (e) cudaEventDestroy(e);
-    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.sxx_part, &l.sxx, &l.v1, &l.d_part, &l.d_red, &l.xx})
+    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.mom_part, &l.mom, &l.v1, &l.d_part, &l.d_red, &l.xx})
       b->release();
     if (l.stream) cudaStreamDestroy(l.stream);
   }
@@ -309,8 +313,26 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     CU(cudaMemcpy(dYraw, d->Y_raw, (size_t)N * P * sizeof(double), in_kind));
   }
 
+  // ---- intercept column: np.linalg.qr of [1 | covariates] (lin_reg.py:142-147) gives a constant
+  // first column +-1/sqrt(N); its product with x is q0 * sum(x), which the pre-pass already has ----
+  if (K > 0 && !getenv("GLR_KEEP_INTERCEPT")) {
+    std::vector<double> col0(N);
+    CU(cudaMemcpy2D(col0.data(), sizeof(double), dQ, (size_t)K * sizeof(double), sizeof(double), N,
+                    cudaMemcpyDeviceToHost));
+    long double sum = 0;
+    for (int64_t i = 0; i < N; ++i) sum += col0[i];
+    const double q0 = (double)(sum / N);
+    double dev = 0;
+    for (int64_t i = 0; i < N; ++i) dev = std::max(dev, std::fabs(col0[i] - q0));
+    if (q0 != 0.0 && dev <= 1e-13 * std::fabs(q0)) {
+      st->has_icpt = 1;
+      st->icpt_q0 = q0;
+    }
+  }
+  const int Kg = K - st->has_icpt;  // Q columns that go through the GEMM
+
   // ---- pass-1 operand W_c = [Q | Ytilde_c | mask | Yraw], Ytilde_c = (I - Q Q^T) Y_c ----
-  st->Mcols = K + P * (st->verbose ? 3 : 1);
+  st->Mcols = Kg + P * (st->verbose ? 3 : 1);
   const int n_mtiles = (int)ceil_div(st->Mcols, 8);
   const int full_tiles = st->Mcols / 8, rem_cols = st->Mcols % 8;
   const bool no_tail = getenv("GLR_NO_TAIL") != nullptr;
@@ -326,7 +348,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     st->MT = kMaxMT;
     st->n_groups = (int)ceil_div(n_mtiles, kMaxMT);
   }
-  st->s_rows = (int64_t)st->n_groups * st->MT * 8 + (st->tail ? 8 : 0);
+  st->s_rows = st->has_icpt + (int64_t)st->n_groups * st->MT * 8 + (st->tail ? 8 : 0);
   st->w_contig_doubles =
       (int64_t)st->n_groups * st->n_chunks * kChunkGroups * (st->MT * kAtomDoubles + st->tail * kGroup);
   const size_t w_bytes = (size_t)C * st->w_contig_doubles * sizeof(double);
@@ -338,12 +360,13 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     if (K > 0) {
       launch_qty(dQ, dY, N, K, P, dT, s0);
       launch_residualize(dQ, dT, dY, N, K, P, s0);
-      launch_pack_a(dQ, N, K, 0, K, d_g2r, Ng, dst, 0, st->MT, st->tail, st->n_chunks, s0);
+      if (Kg > 0)
+        launch_pack_a(dQ, N, K, st->has_icpt, Kg, d_g2r, Ng, dst, 0, st->MT, st->tail, st->n_chunks, s0);
     }
-    launch_pack_a(dY, N, P, 0, P, d_g2r, Ng, dst, K, st->MT, st->tail, st->n_chunks, s0);
+    launch_pack_a(dY, N, P, 0, P, d_g2r, Ng, dst, Kg, st->MT, st->tail, st->n_chunks, s0);
     if (st->verbose) {
-      launch_pack_a(dM, N, P, 0, P, d_g2r, Ng, dst, K + P, st->MT, st->tail, st->n_chunks, s0);
-      launch_pack_a(dYraw, N, P, 0, P, d_g2r, Ng, dst, K + 2 * P, st->MT, st->tail, st->n_chunks, s0);
+      launch_pack_a(dM, N, P, 0, P, d_g2r, Ng, dst, Kg + P, st->MT, st->tail, st->n_chunks, s0);
+      launch_pack_a(dYraw, N, P, 0, P, d_g2r, Ng, dst, Kg + 2 * P, st->MT, st->tail, st->n_chunks, s0);
     }
   }
   CU(cudaGetLastError());
@@ -464,11 +487,11 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   if (int rc = L.s_red.ensure((size_t)Mpad * ldS * 8)) return rc;
   if (n_split > 1)
     if (int rc = L.s_part.ensure((size_t)n_split * Mpad * ldS * 8)) return rc;
-  if (int rc = L.sxx.ensure((size_t)ldS * 8)) return rc;
+  if (int rc = L.mom.ensure((size_t)2 * ldS * 8)) return rc;
   if (int rc = L.v1.ensure((size_t)ldS * 8)) return rc;
   if (int rc = L.xx.ensure((size_t)ldS * 8)) return rc;
   if (float_fmt && n_split > 1)
-    if (int rc = L.sxx_part.ensure((size_t)n_split * ldS * 8)) return rc;
+    if (int rc = L.mom_part.ensure((size_t)n_split * 2 * ldS * 8)) return rc;
   const int n_out = st->verbose ? 7 : 4;
   double* outs[7] = {o->effect, o->stderror, o->tvalue, o->pvalue, o->n, o->sum_x, o->y_transpose_x};
   double* d_outs[7];
@@ -491,7 +514,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   CU(cudaEventRecord(L.ev[0], s));
   // ---- pre-pass (A0): missing substitute + sum of squares from integer counts ----
   if (!float_fmt) {
-    launch_prepass(x, b->missing_policy, L.v1.as<double>(), L.sxx.as<double>(), s);
+    launch_prepass(x, b->missing_policy, L.v1.as<double>(), L.mom.as<double>(), ldS, s);
     L.has_prepass = true;
     ++L.launches;
   }
@@ -508,20 +531,26 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   gp.nt = nt;
   gp.warps = warps;
   gp.ldS = ldS;
-  gp.S = n_split > 1 ? L.s_part.as<double>() : L.s_red.as<double>();
-  gp.sxx_part = (float_fmt && n_split > 1) ? L.sxx_part.as<double>() : L.sxx.as<double>();
+  // GEMM rows start below the intercept row (row 0 of S) when the intercept is handled outside
+  gp.S = (n_split > 1 ? L.s_part.as<double>() : L.s_red.as<double>()) + (int64_t)st->has_icpt * ldS;
+  gp.s_slab = Mpad * ldS;
+  gp.mom_part = (float_fmt && n_split > 1) ? L.mom_part.as<double>() : L.mom.as<double>();
   launch_gram(gp, s);
   ++L.launches;
   if (n_split > 1) {
     launch_reduce_splits(L.s_part.as<double>(), L.s_red.as<double>(), Mpad, ldS, n_split, s);
     ++L.launches;
     if (float_fmt) {
-      launch_reduce_splits(L.sxx_part.as<double>(), L.sxx.as<double>(), 1, ldS, n_split, s);
+      launch_reduce_splits(L.mom_part.as<double>(), L.mom.as<double>(), 2, ldS, n_split, s);
       ++L.launches;
     }
   }
   if (st->n_drop > 0) {
-    launch_dropped_sumsq(x, st->drop_idx, st->n_drop, L.sxx.as<double>(), s);
+    launch_dropped_moments(x, st->drop_idx, st->n_drop, L.mom.as<double>(), ldS, s);
+    ++L.launches;
+  }
+  if (st->has_icpt) {
+    launch_intercept_row(L.mom.as<double>() + ldS, st->icpt_q0, L.s_red.as<double>(), G, s);
     ++L.launches;
   }
   CU(cudaEventRecord(L.ev[2], s));
@@ -566,7 +595,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   // ---- epilogue (A5-A7) ----
   EpilogueParams ep;
   ep.S = L.s_red.as<double>();
-  ep.sxx = L.sxx.as<double>();
+  ep.sxx = L.mom.as<double>();
   ep.D = d_D;
   ep.mask_id = st->mask_id;
   ep.YdotY = st->YdotY + (int64_t)b->contig * P;
@@ -680,7 +709,7 @@ int glr_decode_block(int device, const glr_block_desc* b, int64_t n_geno, double
   double *dv1 = nullptr, *dsxx = nullptr, *dout = nullptr;
   CU(cudaMalloc(&dg, bytes + 64));
   CU(cudaMalloc(&dv1, G * sizeof(double)));
-  CU(cudaMalloc(&dsxx, G * sizeof(double)));
+  CU(cudaMalloc(&dsxx, 2 * G * sizeof(double)));
   CU(cudaMalloc(&dout, (size_t)G * n_geno * sizeof(double)));
   CU(cudaMemcpy(dg, b->genotypes, bytes, cudaMemcpyHostToDevice));
   BlockView x;
@@ -690,7 +719,8 @@ int glr_decode_block(int device, const glr_block_desc* b, int64_t n_geno, double
   x.format = b->format;
   x.n_geno = n_geno;
   x.v1 = dv1;
-  if (b->format == GLR_FMT_I8 || b->format == GLR_FMT_PLINK2) launch_prepass(x, b->missing_policy, dv1, dsxx, nullptr);
+  if (b->format == GLR_FMT_I8 || b->format == GLR_FMT_PLINK2)
+    launch_prepass(x, b->missing_policy, dv1, dsxx, G, nullptr);
   launch_decode(x, dout, nullptr);
   cudaError_t e = cudaMemcpy(out_values, dout, (size_t)G * n_geno * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(dg);

@@ -41,7 +41,8 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long* sh) {
   return t;
 }
 
-__global__ void __launch_bounds__(kPreThreads) prepass_kernel(BlockView x, int policy, double* v1, double* sxx) {
+__global__ void __launch_bounds__(kPreThreads) prepass_kernel(BlockView x, int policy, double* v1, double* mom,
+                                                              int64_t ld) {
   __shared__ long long sh[kPreThreads / 32];
   const int g = blockIdx.x;
   const uint8_t* row = x.base + (int64_t)g * x.stride;
@@ -115,13 +116,14 @@ __global__ void __launch_bounds__(kPreThreads) prepass_kernel(BlockView x, int p
     double m = -1.0;
     if (policy == GLR_MISSING_MEAN && c_miss < n) m = (double)s1 / (double)(n - c_miss);  // MeanSubstitute.scala:57-84
     v1[g] = m;
-    sxx[g] = (double)s2 + (m * m) * (double)c_miss;
+    mom[g] = (double)s2 + (m * m) * (double)c_miss;
+    mom[ld + g] = (double)s1 + m * (double)c_miss;
   }
 }
 
-void launch_prepass(const BlockView& x, int missing_policy, double* v1, double* sxx, cudaStream_t st) {
+void launch_prepass(const BlockView& x, int missing_policy, double* v1, double* mom, int64_t ld, cudaStream_t st) {
   if (x.n_variants <= 0) return;
-  prepass_kernel<<<x.n_variants, kPreThreads, 0, st>>>(x, missing_policy, v1, sxx);
+  prepass_kernel<<<x.n_variants, kPreThreads, 0, st>>>(x, missing_policy, v1, mom, ld);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -230,21 +232,33 @@ void launch_decode(const BlockView& x, double* out, cudaStream_t st) {
   decode_kernel<<<grid, 256, 0, st>>>(x, out);
 }
 
-__global__ void dropped_sumsq_kernel(BlockView x, const int64_t* drop_idx, int64_t n_drop, double* sxx) {
+__global__ void dropped_moments_kernel(BlockView x, const int64_t* drop_idx, int64_t n_drop, double* mom, int64_t ld) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= x.n_variants) return;
   const uint8_t* row = x.base + (int64_t)g * x.stride;
   const double miss = (x.format == GLR_FMT_I8 || x.format == GLR_FMT_PLINK2) ? x.v1[g] : 0.0;
-  double s = 0.0;
+  double s2 = 0.0, s1 = 0.0;
   for (int64_t i = 0; i < n_drop; ++i) {
     const double v = decode_elem(x, row, drop_idx[i], miss);
-    s = fma(v, v, s);
+    s2 = fma(v, v, s2);
+    s1 += v;
   }
-  sxx[g] -= s;
+  mom[g] -= s2;
+  mom[ld + g] -= s1;
 }
-void launch_dropped_sumsq(const BlockView& x, const int64_t* drop_idx, int64_t n_drop, double* sxx, cudaStream_t st) {
+void launch_dropped_moments(const BlockView& x, const int64_t* drop_idx, int64_t n_drop, double* mom, int64_t ld,
+                            cudaStream_t st) {
   if (x.n_variants <= 0 || n_drop <= 0) return;
-  dropped_sumsq_kernel<<<(unsigned)ceil_div(x.n_variants, 128), 128, 0, st>>>(x, drop_idx, n_drop, sxx);
+  dropped_moments_kernel<<<(unsigned)ceil_div(x.n_variants, 128), 128, 0, st>>>(x, drop_idx, n_drop, mom, ld);
+}
+
+__global__ void intercept_row_kernel(const double* sum_x, double q0, double* row0, int G) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < G) row0[v] = q0 * sum_x[v];
+}
+void launch_intercept_row(const double* sum_x, double q0, double* row0, int G, cudaStream_t st) {
+  if (G <= 0) return;
+  intercept_row_kernel<<<(unsigned)ceil_div(G, 256), 256, 0, st>>>(sum_x, q0, row0, G);
 }
 
 // ------------------------------------------------------------------------------------------------

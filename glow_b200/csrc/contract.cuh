@@ -311,9 +311,9 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-  double sq[NT];
+  double sq[NT], sx[NT];
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) sq[nt] = 0.0;
+  for (int nt = 0; nt < NT; ++nt) sq[nt] = sx[nt] = 0.0;
   double tacc[TAIL > 0 ? TAIL : 1][NT];
 #pragma unroll
   for (int t = 0; t < (TAIL > 0 ? TAIL : 1); ++t)
@@ -382,7 +382,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
         }
         if (FMT == GLR_FMT_F64 || FMT == GLR_FMT_F32) {
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) sq[nt] = fma(xa[nt], xa[nt], fma(xb[nt], xb[nt], sq[nt]));
+          for (int nt = 0; nt < NT; ++nt) {
+            sq[nt] = fma(xa[nt], xa[nt], fma(xb[nt], xb[nt], sq[nt]));
+            sx[nt] += xa[nt] + xb[nt];
+          }
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -405,8 +408,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
   }
 
   // C fragment: lane (r, j) holds rows r of each m-tile, variants 2j, 2j+1 of each n-tile
-  const int64_t rows = (int64_t)p.n_groups * MT * 8 + (TAIL > 0 ? 8 : 0);
-  double* Sz = p.S + (int64_t)blockIdx.z * rows * p.ldS;
+  double* Sz = p.S + (int64_t)blockIdx.z * p.s_slab;
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -429,10 +431,15 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
   if (want_sq) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      double v = sq[nt];
+      double v = sq[nt], u = sx[nt];
       v += __shfl_xor_sync(0xffffffffu, v, 1);
+      u += __shfl_xor_sync(0xffffffffu, u, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (j == 0) p.sxx_part[(int64_t)blockIdx.z * p.ldS + v_warp + nt * 8 + r] = v;
+      u += __shfl_xor_sync(0xffffffffu, u, 2);
+      if (j == 0) {
+        p.mom_part[((int64_t)blockIdx.z * 2 + 0) * p.ldS + v_warp + nt * 8 + r] = v;
+        p.mom_part[((int64_t)blockIdx.z * 2 + 1) * p.ldS + v_warp + nt * 8 + r] = u;
+      }
     }
   }
 }

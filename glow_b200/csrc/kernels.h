@@ -19,9 +19,9 @@ struct BlockView {
 };
 
 // ---- pre-pass: per-variant missing substitute and sum of squares (I8 / PLINK2) ------------------
-// v1[g]  = mean of non-missing (policy MEAN; -1 if all missing) or -1
-// sxx[g] = sum_s x^2 with missing replaced by v1[g]
-void launch_prepass(const BlockView& x, int missing_policy, double* v1, double* sxx, cudaStream_t st);
+// v1[g]     = mean of non-missing (policy MEAN; -1 if all missing) or -1
+// mom[0][g] = sum_s x^2, mom[1][g] = sum_s x, missing replaced by v1[g]   (mom is [2][ld])
+void launch_prepass(const BlockView& x, int missing_policy, double* v1, double* mom, int64_t ld, cudaStream_t st);
 
 // ---- pass 1: S = W^T X on FP64 tensor cores ----------------------------------------------------
 struct GramParams {
@@ -34,8 +34,9 @@ struct GramParams {
   int32_t n_split;     // split of the sample range across CTAs (deterministic 2-stage reduce)
   int32_t nt;          // n-tiles (8 variants) per warp: 2 or 4
   int32_t warps;       // consumer warps per CTA: 8, or 16 (PLINK2 with nt == 2 only)
-  double* S;           // [n_split][n_groups*MT*8 (+8 if tail)][ldS]
-  double* sxx_part;    // [n_split][ldS]   (F64 / F32 only, written by column group 0)
+  double* S;           // first row this kernel writes; split z starts at S + z * s_slab
+  int64_t s_slab;      // elements between the per-split slabs of S
+  double* mom_part;    // [n_split][2][ldS]: sum x^2, sum x (F64 / F32 only, written by column group 0)
   int64_t ldS;         // >= G_b rounded up to the CTA tile
 };
 int gram_tile_variants(int nt, int warps = 8);  // variants per CTA
@@ -84,8 +85,11 @@ void launch_epilogue(const EpilogueParams& p, double* xx_scratch, cudaStream_t s
 
 void launch_pvalues(const double* t, int64_t n, PvalConst pc, double* p, cudaStream_t st);
 void launch_decode(const BlockView& x, double* out, cudaStream_t st);  // out [G_b][n_geno]
-// sum over the listed (dropped) samples of x^2, subtracted from sxx when rows are dropped
-void launch_dropped_sumsq(const BlockView& x, const int64_t* drop_idx, int64_t n_drop, double* sxx, cudaStream_t st);
+// sums over the listed (dropped) samples of x^2 and x, subtracted from mom[0] / mom[1] when rows are dropped
+void launch_dropped_moments(const BlockView& x, const int64_t* drop_idx, int64_t n_drop, double* mom, int64_t ld,
+                            cudaStream_t st);
+// S row of an intercept column that is not in the GEMM: row0[v] = q0 * sum_x[v]
+void launch_intercept_row(const double* sum_x, double q0, double* row0, int G, cudaStream_t st);
 
 // ---- state packing (once per call of linear_regression) -----------------------------------------
 struct PackDims {
