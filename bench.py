@@ -44,7 +44,7 @@ SEED = 20261019
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--variants-per-step', type=int, default=148 * 256)
@@ -451,7 +451,11 @@ def main():
             'peak': fp64_peak,
             'unit': 'TFLOP/s',
             'frac': achieved / fp64_peak,
-            'traffic': None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at the default shape,
+            # from the ncu --set full capture in profiles/r01_gram_full.txt (4.812 GB + 6 MB; algorithmic
+            # bytes are 4.736 GB of packed genotypes + 68 MB of packed state): no re-reads
+            'traffic': 4.818e9 if (n == N_SAMPLES and G == 148 * 256) else None,
+            'algorithmic_bytes_per_launch': float(G) * row_bytes + 8.0 * n * cols,
             'peak_source': 'cuBLAS DGEMM 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json has no fp64 entry)',
             'flops_per_launch_algorithmic': flops_alg,
             'issued_tflops_incl_padding': flops_issued / gram_s / 1e12,

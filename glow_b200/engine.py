@@ -30,6 +30,30 @@ class GenotypeBlock:
     missing: str = 'minus_one'  # 'minus_one' (genotype_states) | 'mean' (mean_substitute)
 
 
+def _arrow_list_to_matrix(col):
+    """pyarrow (Chunked)Array of list<T> / large_list<T> / fixed_size_list<T> with equal lengths ->
+    [G, N] numpy view of the flat child buffer (zero copy for primitive, null-free data)."""
+    import pyarrow as pa
+    if isinstance(col, pa.ChunkedArray):
+        col = col.combine_chunks() if col.num_chunks != 1 else col.chunk(0)
+    if col.null_count:
+        raise ValueError('the values column contains null arrays')
+    t = col.type
+    G = len(col)
+    if pa.types.is_fixed_size_list(t):
+        n = t.list_size
+    elif pa.types.is_list(t) or pa.types.is_large_list(t):
+        lens = np.diff(col.offsets.to_numpy(zero_copy_only=False))
+        n = int(lens[0]) if G else 0
+        if G and not (lens == n).all():
+            raise ValueError('all genotype arrays of a block must have the same length')
+    else:
+        raise ValueError(f'the values column must be an Arrow list type, got {t}')
+    flat = col.flatten()
+    arr = flat.to_numpy(zero_copy_only=False)  # nulls inside an array become NaN (one copy)
+    return arr.reshape(G, n)
+
+
 def as_block(values, dt=np.float64) -> GenotypeBlock:
     """Turns the `_glow_regression_values` column of a pandas block (a sequence of per-variant
     arrays, lin_reg.py:226) into one contiguous variant-major matrix.  No transpose: the device
@@ -37,6 +61,12 @@ def as_block(values, dt=np.float64) -> GenotypeBlock:
     if isinstance(values, GenotypeBlock):
         return values
     arr = values if isinstance(values, np.ndarray) and values.ndim == 2 else None
+    if arr is None and type(values).__module__.startswith('pyarrow'):
+        arr = _arrow_list_to_matrix(values)
+    elif arr is None and hasattr(values, 'dtype') and type(values.dtype).__name__ == 'ArrowDtype':
+        import pyarrow as pa
+        arr = _arrow_list_to_matrix(pa.chunked_array(values.array._pa_array) if hasattr(values, 'array') else
+                                    values._pa_array)
     if arr is None:
         seq = list(values)
         if len(seq) == 0:

@@ -174,18 +174,20 @@ def _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output, gt_in
 
 def _assemble(genotype_pdf: pd.DataFrame, res: Dict[str, np.ndarray], phenotype_names, verbose_output, out_dt):
     """Result frame of one block (lin_reg.py:231-252): pass-through columns replicated once per
-    phenotype, statistics raveled phenotype-major."""
+    phenotype (``pd.concat([genotype_pdf] * P)``), statistics raveled phenotype-major
+    (``np.ravel`` of the P x G_b matrices).  Built column-wise with numpy instead of concatenating
+    P frames and converting every matrix to a Python list."""
     num_genotypes = genotype_pdf.shape[0]
     P = res['effect'].shape[0]
-    out_df = pd.concat([genotype_pdf] * P) if P else genotype_pdf.iloc[0:0]
+    cols = {c: np.tile(genotype_pdf[c].to_numpy(), P) for c in genotype_pdf.columns}
     if verbose_output:
-        out_df['n'] = np.ravel(res['n']).astype(np.int32)
-        out_df['sum_x'] = np.ravel(res['sum_x']).astype(out_dt, copy=False)
-        out_df['y_transpose_x'] = np.ravel(res['y_transpose_x']).astype(out_dt, copy=False)
+        cols['n'] = np.ravel(res['n']).astype(np.int32)
+        cols['sum_x'] = np.ravel(res['sum_x']).astype(out_dt, copy=False)
+        cols['y_transpose_x'] = np.ravel(res['y_transpose_x']).astype(out_dt, copy=False)
     for k in STAT_NAMES:
-        out_df[k] = np.ravel(res[k]).astype(out_dt, copy=False)
-    out_df['phenotype'] = np.repeat(np.asarray(list(phenotype_names), dtype=object), num_genotypes)
-    return out_df
+        cols[k] = np.ravel(res[k]).astype(out_dt, copy=False)
+    cols['phenotype'] = np.repeat(np.asarray(list(phenotype_names), dtype=object), num_genotypes)
+    return pd.DataFrame(cols, index=np.tile(genotype_pdf.index.to_numpy(), P), copy=False)
 
 
 def _linear_regression_inner(genotype_pdf: pd.DataFrame, Y_state: YState, Y_mask, Y_scale, Q, dof: int,
@@ -237,6 +239,8 @@ def _generate_linreg_output(genotype_df, np_dt, values_column, Y_state, Y_mask, 
     from ..sources import GenotypeSource
     if isinstance(genotype_df, GenotypeSource):
         return _run_source(genotype_df, Y_state, phenotype_names, verbose_output, np_dt)
+    if _is_arrow_input(genotype_df):
+        return _run_arrow(genotype_df, values_column, Y_state, phenotype_names, verbose_output, np_dt)
 
     blocks = [genotype_df] if isinstance(genotype_df, pd.DataFrame) else genotype_df
     prepared = (gwas_fx._prepare_genotype_pdf(pdf, values_column, np_dt) for pdf in blocks)
@@ -282,6 +286,85 @@ def _run_source(source, Y_state, phenotype_names, verbose_output, np_dt) -> pd.D
     out = pd.concat(parts)
     passthrough = [c for c in out.columns if c not in STAT_NAMES + VERBOSE_NAMES + ('phenotype', )]
     return out[passthrough + list(STAT_NAMES) + ['phenotype'] + (list(VERBOSE_NAMES) if verbose_output else [])]
+
+
+def _is_arrow_input(obj) -> bool:
+    mod = type(obj).__module__ or ''
+    return mod.startswith('pyarrow') and type(obj).__name__ in ('Table', 'RecordBatch', 'RecordBatchReader',
+                                                                'RecordBatchFileReader')
+
+
+def _run_arrow(data, values_column, Y_state, phenotype_names, verbose_output, np_dt):
+    """Arrow-native intake: record batches whose values column is a
+    list<double|float|int8> go to the device straight from the Arrow child buffer -- no pandas
+    objects, no np.column_stack (lin_reg.py:226-227), no per-row Python lists on the way out
+    (lin_reg.py:248-252).  Returns a pyarrow Table with the reference's column order."""
+    import pyarrow as pa
+    if not isinstance(values_column, str):
+        raise ValueError('values_column must be a column name for Arrow input')
+    if values_column == gwas_fx._GENOTYPES_COLUMN_NAME:
+        raise ValueError(f'The values column should not be called "{gwas_fx._GENOTYPES_COLUMN_NAME}"')
+    if isinstance(data, pa.Table):
+        batches = data.to_batches()
+        schema = data.schema
+    elif isinstance(data, pa.RecordBatch):
+        batches, schema = [data], data.schema
+    else:
+        batches, schema = data, data.schema
+    if values_column not in schema.names:
+        raise ValueError(f'genotype_df has no column named "{values_column}"')
+    is_loco = isinstance(Y_state, dict)
+    engine = (next(iter(Y_state.values())) if is_loco else Y_state)._engine
+    keep_cols = [n for n in schema.names if n not in (values_column, gwas_fx._GENOTYPES_COLUMN_NAME)]
+    P = len(phenotype_names)
+    names = np.asarray(list(phenotype_names), dtype=object)
+    pending = []
+
+    def work():
+        for batch in batches:
+            if batch.num_rows == 0:
+                continue
+            X = as_block(batch.column(schema.get_field_index(values_column)), np_dt)
+            meta = batch.select(keep_cols)
+            if is_loco:
+                contig = batch.column(schema.get_field_index('contigName')).to_numpy(zero_copy_only=False)
+                for c in pd.unique(contig):
+                    sel = np.flatnonzero(contig == c)
+                    sub = GenotypeBlock(np.ascontiguousarray(X.data[sel]), X.format, X.missing)
+                    pending.append(meta.take(pa.array(sel)))
+                    yield sub, Y_state[c]._contig_index
+            else:
+                pending.append(meta)
+                yield X, 0
+
+    out_batches = []
+    for res in engine.run_pipelined(work()):
+        meta = pending.pop(0)
+        G = meta.num_rows
+        idx = pa.array(np.tile(np.arange(G, dtype=np.int64), P))
+        cols = [meta.column(i).take(idx) for i in range(meta.num_columns)]
+        fields = [meta.schema.field(i) for i in range(meta.num_columns)]
+        pa_dt = pa.float32() if np_dt == np.float32 else pa.float64()
+        for k in STAT_NAMES:
+            cols.append(pa.array(np.ravel(res[k]).astype(np_dt, copy=False)))
+            fields.append(pa.field(k, pa_dt))
+        cols.append(pa.array(np.repeat(names, G), type=pa.string()))
+        fields.append(pa.field('phenotype', pa.string()))
+        if verbose_output:
+            cols.append(pa.array(np.ravel(res['n']).astype(np.int32)))
+            fields.append(pa.field('n', pa.int32()))
+            for k in ('sum_x', 'y_transpose_x'):
+                cols.append(pa.array(np.ravel(res[k]).astype(np_dt, copy=False)))
+                fields.append(pa.field(k, pa_dt))
+        out_batches.append(pa.RecordBatch.from_arrays(cols, schema=pa.schema(fields)))
+    if not out_batches:
+        pa_dt = pa.float32() if np_dt == np.float32 else pa.float64()
+        fields = [schema.field(n) for n in keep_cols] + [pa.field(k, pa_dt) for k in STAT_NAMES]
+        fields.append(pa.field('phenotype', pa.string()))
+        if verbose_output:
+            fields += [pa.field('n', pa.int32()), pa.field('sum_x', pa_dt), pa.field('y_transpose_x', pa_dt)]
+        return pa.schema(fields).empty_table()
+    return pa.Table.from_batches(out_batches)
 
 
 def _spark_map(genotype_df, np_dt, values_column, map_func, verbose_output):

@@ -221,3 +221,41 @@ def test_plink_source_and_block_checks(golden_dir):
         glow_b200.PlinkBedSource(b'\x00\x00\x00' + d['bed'][3:].tobytes(), 5)
     with pytest.raises(ValueError):
         glow_b200.PlinkBedSource(d['bed'].tobytes(), 9)  # 10 payload bytes are not a multiple of ceil(9/4) = 3
+
+
+def test_arrow_list_columns_become_blocks_without_copy():
+    import pyarrow as pa
+    from glow_b200.engine import as_block
+    X = np.random.default_rng(3).random((6, 9))
+    col = pa.array(list(X), type=pa.list_(pa.float64()))
+    blk = as_block(col)
+    assert blk.format == 'f64' and np.array_equal(blk.data, X)
+    # zero copy: the block aliases the Arrow child buffer
+    assert blk.data.ctypes.data == col.flatten().buffers()[1].address
+    fixed = pa.FixedSizeListArray.from_arrays(pa.array(X.ravel()), 9)
+    assert np.array_equal(as_block(fixed).data, X)
+    assert np.array_equal(as_block(pa.table({'v': col})['v']).data, X)
+    i8 = as_block(pa.array([[0, 1, -1], [2, 2, 0]], type=pa.list_(pa.int8())))
+    assert i8.format == 'i8' and i8.data.tolist() == [[0, 1, -1], [2, 2, 0]]
+    assert as_block(pa.array(list(X.astype(np.float32)), type=pa.list_(pa.float32())), np.float32).format == 'f32'
+    with pytest.raises(ValueError):
+        as_block(pa.array([[1.0], [1.0, 2.0]]))
+    with pytest.raises(ValueError):
+        as_block(pa.array([[1.0], None], type=pa.list_(pa.float64())))
+    # pandas Series backed by Arrow
+    s = pd.Series(pd.arrays.ArrowExtensionArray(pa.chunked_array([col])))
+    assert np.array_equal(as_block(s).data, X)
+
+
+def test_assemble_matches_reference_layout():
+    # lin_reg.py:231-252: pass-through columns replicated per phenotype, statistics raveled phenotype-major
+    from glow_b200.gwas.lin_reg import _assemble
+    pdf = pd.DataFrame({'contigName': ['1', '1', '2'], 'start': [5, 6, 7]}, index=[10, 11, 12])
+    res = {k: np.arange(6, dtype=np.float64).reshape(2, 3) + i for i, k in enumerate(('effect', 'stderror', 'tvalue', 'pvalue'))}
+    out = _assemble(pdf, res, ['a', 'b'], False, np.float64)
+    ref = pd.concat([pdf] * 2)
+    for i, k in enumerate(('effect', 'stderror', 'tvalue', 'pvalue')):
+        ref[k] = list(np.ravel(res[k]))
+    ref['phenotype'] = pd.Series(['a', 'b']).repeat(3).tolist()
+    pd.testing.assert_frame_equal(out, ref, check_dtype=False)
+    assert out.index.tolist() == [10, 11, 12, 10, 11, 12]
