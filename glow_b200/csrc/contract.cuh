@@ -293,7 +293,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
       const double* src = p.wpk + ((int64_t)blockIdx.y * p.n_chunks + c_begin) * kStageDoubles;
       for (int64_t it = 0; it < n_it; ++it) {
         const int s = (int)(it % kStages);
-        if (it >= kStages) mbar_wait(&ring.empty[s], (uint32_t)((it / kStages) & 1) ^ 1u);
+        if (it >= kStages) mbar_wait_backoff(&ring.empty[s], (uint32_t)((it / kStages) & 1) ^ 1u);
         mbar_expect_tx(&ring.full[s], kStageBytes);
         bulk_g2s(wst + (int64_t)s * kStageDoubles, src + it * kStageDoubles, kStageBytes, &ring.full[s]);
       }
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) masked_kernel(const MaskedParams 
       const double* qsrc = p.qb + c_begin * qStageDoubles;
       for (int64_t it = 0; it < n_it; ++it) {
         const int s = (int)(it % kStages);
-        if (it >= kStages) mbar_wait(&ring.empty[s], (uint32_t)((it / kStages) & 1) ^ 1u);
+        if (it >= kStages) mbar_wait_backoff(&ring.empty[s], (uint32_t)((it / kStages) & 1) ^ 1u);
         mbar_expect_tx(&ring.full[s], stageBytes);
         double* dst = stage0 + (int64_t)s * stageDoubles;
         bulk_g2s(dst, msrc + it * mStageDoubles, (uint32_t)mStageDoubles * 8, &ring.full[s]);

@@ -1,0 +1,179 @@
+"""Edge cases of the CUDA path through the C ABI: tiny and ragged shapes, strides and alignment,
+device-resident buffers, asynchronous lanes, error codes."""
+import ctypes as C
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from gpu_utils import pack_plink
+from helpers import STATS, assert_stats_close
+from oracle import linreg_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _state(phe, cov, **kw):
+    from glow_b200.engine import DeviceState
+    st = orc.prepare_state(phe, cov, **kw)
+    ys = list(st.y_state.values()) if isinstance(st.y_state, dict) else [st.y_state]
+    eng = DeviceState(Q=st.Q, Y=np.stack([y.Y for y in ys]), Y_mask=st.Y_mask, YdotY=np.stack([y.YdotY for y in ys]),
+                      Y_scale=st.Y_scale, dof=st.dof)
+    return eng, st
+
+
+def _data(rg, N, G, P, K):
+    X = rg.integers(0, 3, (G, N)).astype(np.float64)
+    X[:, 0] = [g % 3 for g in range(G)]  # no constant rows even for tiny N
+    X[:, -1] = [(g + 1) % 3 for g in range(G)]
+    cov = pd.DataFrame(rg.standard_normal((N, K))) if K else None
+    phe = pd.DataFrame(rg.standard_normal((N, P)))
+    return X, phe, cov
+
+
+@pytest.mark.parametrize('N', [5, 7, 8, 9, 31, 63, 64, 65, 127, 129])
+def test_tiny_and_ragged_sample_counts(rg, N):
+    from glow_b200.engine import GenotypeBlock
+    G, P, K = 11, 2, 1
+    X, phe, cov = _data(rg, N, G, P, K)
+    eng, st = _state(phe, cov)
+    ref = orc.block_stats(X, st)
+    for blk in (GenotypeBlock(X, 'f64'), GenotypeBlock(X.astype(np.float32), 'f32'), GenotypeBlock(X.astype(np.int8), 'i8'),
+                GenotypeBlock(pack_plink(X.astype(np.int64)), 'plink2')):
+        got = eng.run(blk)
+        assert_stats_close({k: got[k] for k in STATS}, ref, label=f'N={N} {blk.format}')
+    eng.close()
+
+
+@pytest.mark.parametrize('G', [1, 2, 7, 8, 9, 127, 128, 129, 255, 257, 1000])
+def test_ragged_variant_counts(rg, G):
+    from glow_b200.engine import GenotypeBlock
+    N, P, K = 200, 3, 2
+    X, phe, cov = _data(rg, N, G, P, K)
+    eng, st = _state(phe, cov)
+    ref = orc.block_stats(X, st)
+    assert_stats_close(eng.run(GenotypeBlock(X, 'f64')), ref, label=f'G={G} f64')
+    assert_stats_close(eng.run(GenotypeBlock(pack_plink(X.astype(np.int64)), 'plink2')), ref, label=f'G={G} plink')
+    eng.close()
+
+
+@pytest.mark.parametrize('K,P', [(0, 1), (1, 1), (3, 5), (7, 1), (8, 8), (15, 1), (16, 1), (17, 1), (30, 40), (40, 100)])
+def test_column_count_shapes(rg, K, P):
+    """Every packing shape: fewer than one m-tile, exact multiples of 8, 1-3 tail columns, several column groups."""
+    from glow_b200.engine import GenotypeBlock
+    N, G = 300, 40
+    X, phe, cov = _data(rg, N, G, P, K)
+    eng, st = _state(phe, cov)
+    ref = orc.block_stats(X, st)
+    assert_stats_close(eng.run(GenotypeBlock(X, 'f64')), ref, label=f'K={K} P={P} f64')
+    assert_stats_close(eng.run(GenotypeBlock(pack_plink(X.astype(np.int64)), 'plink2')), ref, label=f'K={K} P={P} p2')
+    eng.close()
+
+
+def test_no_intercept_and_no_covariates(rg):
+    # add_intercept=False with covariates, and no covariates at all (Q has zero columns)
+    import glow_b200
+    N, G, P = 120, 9, 2
+    X, phe, cov = _data(rg, N, G, P, 3)
+    out = glow_b200.gwas.linear_regression(pd.DataFrame({'values': list(X)}), phe, cov, add_intercept=False)
+    ref = orc.block_stats(X, orc.prepare_state(phe, cov, add_intercept_col=False))
+    assert_stats_close({k: out[k].to_numpy().reshape(P, G) for k in STATS}, ref, label='no intercept')
+    # covariate matrix whose constant column is not the first one: no intercept shortcut, still exact
+    cov2 = cov.copy()
+    cov2[3] = 1.0
+    out2 = glow_b200.gwas.linear_regression(pd.DataFrame({'values': list(X)}), phe, cov2, add_intercept=False)
+    ref2 = orc.block_stats(X, orc.prepare_state(phe, cov2, add_intercept_col=False))
+    assert_stats_close({k: out2[k].to_numpy().reshape(P, G) for k in STATS}, ref2, label='constant last')
+
+
+def test_masked_pass_covariate_limit(rg):
+    from glow_b200.engine import DeviceState
+    N, P, K = 200, 2, 33
+    Q = np.linalg.qr(rg.standard_normal((N, K)))[0]
+    Y = rg.standard_normal((N, P))
+    mask = np.ones((N, P))
+    mask[3, 0] = 0
+    with pytest.raises(ValueError, match='at most 32 covariates'):
+        DeviceState(Q=Q, Y=Y * mask, Y_mask=mask, YdotY=np.sum((Y * mask)**2, axis=0), Y_scale=np.ones(P), dof=N - K - 1)
+    # fully observed phenotypes have no such limit
+    eng = DeviceState(Q=Q, Y=Y, Y_mask=np.ones((N, P)), YdotY=np.sum(Y**2, axis=0), Y_scale=np.ones(P), dof=N - K - 1)
+    eng.close()
+
+
+def test_strided_and_unaligned_rows(rg):
+    """row_stride larger than a row, and rows that start at odd addresses (PLINK) / 8-byte-only aligned (f64, odd N)."""
+    from glow_b200 import _capi
+    from glow_b200.engine import GenotypeBlock
+    N, G, P, K = 131, 37, 2, 2  # odd N: f64 rows alternate 16-byte alignment
+    X, phe, cov = _data(rg, N, G, P, K)
+    eng, st = _state(phe, cov)
+    ref = orc.block_stats(X, st)
+    assert_stats_close(eng.run(GenotypeBlock(X, 'f64')), ref, label='odd N f64')
+    lib = _capi.load()
+    # strided f64: a [G, N + 5] buffer of which the first N entries of every row are the block
+    wide = np.full((G, N + 5), np.nan)
+    wide[:, :N] = X
+    out = {k: np.empty((P, G)) for k in STATS}
+    bd = _capi.BlockDesc(format=_capi.FMT_F64, memspace=_capi.MEM_HOST, genotypes=wide.ctypes.data,
+                         row_stride_bytes=wide.strides[0], n_variants=G, contig=0, missing_policy=0)
+    bo = _capi.BlockOut(memspace=_capi.MEM_HOST, **{k: out[k].ctypes.data for k in STATS})
+    _capi.check(lib.glr_run_block(eng._handle, C.byref(bd), C.byref(bo)))
+    assert_stats_close(out, ref, label='strided f64')
+    # PLINK rows at every byte alignment: 33-byte rows inside a buffer offset by 1..3 bytes
+    packed = pack_plink(X.astype(np.int64))
+    rb = packed.shape[1]
+    for shift in (1, 2, 3):
+        buf = np.zeros(G * (rb + 3) + 8, dtype=np.uint8)
+        view = np.lib.stride_tricks.as_strided(buf[shift:], shape=(G, rb), strides=(rb + 3, 1))
+        view[:] = packed
+        bd = _capi.BlockDesc(format=_capi.FMT_PLINK2, memspace=_capi.MEM_HOST, genotypes=buf.ctypes.data + shift,
+                             row_stride_bytes=rb + 3, n_variants=G, contig=0, missing_policy=0)
+        _capi.check(lib.glr_run_block(eng._handle, C.byref(bd), C.byref(bo)))
+        assert_stats_close(out, ref, label=f'plink shift {shift}')
+    eng.close()
+
+
+def test_device_resident_buffers_and_async_lanes(rg):
+    import torch
+    from glow_b200.engine import GenotypeBlock
+    N, G, P, K = 1000, 300, 3, 4
+    X, phe, cov = _data(rg, N, G, P, K)
+    eng, st = _state(phe, cov)
+    ref = orc.block_stats(X, st)
+    packed = pack_plink(X.astype(np.int64))
+    d_in = torch.from_numpy(packed).cuda()
+    d_out = {k: torch.empty((P, G), dtype=torch.float64, device='cuda') for k in STATS}
+    eng.run_device('plink2', d_in.data_ptr(), packed.shape[1], G, {k: v.data_ptr() for k, v in d_out.items()},
+                   missing='minus_one')
+    assert_stats_close({k: v.cpu().numpy() for k, v in d_out.items()}, ref, label='device buffers')
+    t = eng.timing(0)
+    assert t['kernel_launches'] >= 3 and t['gram_ms'] > 0
+    # two lanes in flight, results in submission order
+    blocks = [(GenotypeBlock(packed[i:i + 64], 'plink2'), 0) for i in range(0, G, 64)]
+    outs = list(eng.run_pipelined(iter(blocks)))
+    for k in STATS:
+        np.testing.assert_allclose(np.concatenate([o[k] for o in outs], axis=1), ref[k], rtol=1e-9, atol=1e-12)
+    eng.close()
+
+
+def test_error_codes(rg):
+    from glow_b200 import _capi
+    from glow_b200.engine import GenotypeBlock
+    N, G, P, K = 64, 4, 1, 1
+    X, phe, cov = _data(rg, N, G, P, K)
+    eng, _ = _state(phe, cov)
+    with pytest.raises(ValueError):  # wrong row length
+        eng.run(GenotypeBlock(X[:, :-1].copy(), 'f64'))
+    with pytest.raises(ValueError):  # contig out of range
+        eng.run(GenotypeBlock(X, 'f64'), contig=3)
+    lib = _capi.load()
+    assert lib.glr_block_wait(eng._handle, 0) == _capi.ERR_STATE  # nothing in flight
+    assert b'no block in flight' in lib.glr_last_error()
+    with pytest.raises(ValueError):  # lane out of range
+        eng.submit(9, GenotypeBlock(X, 'f64'))
+    eng.close()
+
+
+def test_smoke_entry_point():
+    import __graft_entry__ as ge
+    ge.smoke()
