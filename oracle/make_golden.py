@@ -265,8 +265,92 @@ def golden_random():
     print('random_cases:', sorted(meta))
 
 
+def golden_regenie():
+    """G4: python/glow/gwas/tests/test_lin_reg.py:632-666 + tests/functions.py:47-102 -- regenie 1.0.6.7
+    outputs for the first 100 SNPs, Glow hard calls from the BGEN fixtures, LOCO offsets from the
+    regenie step-1 .loco files.  The reference's own comparison (rtol 1e-2, atol 1e-3) is asserted
+    here against the UNMODIFIED reference kernel before the fixture is written."""
+    from oracle.bgen import read_bgen_states
+    d = os.path.join(REF, 'test-data/regenie')
+
+    def fid_iid(df):
+        df['FID_IID'] = df['FID'].astype(str) + '_' + df['IID'].astype(str)
+        return df.sort_values(by=['FID', 'IID']).drop(columns=['FID', 'IID']).set_index(['FID_IID'])
+
+    def read_offset(file, trait):
+        df = pd.melt(pd.read_table(file, sep=r'\s+'), id_vars=['FID_IID']) \
+            .rename(columns={'FID_IID': 'contigName', 'variable': 'FID_IID', 'value': trait}) \
+            .astype({'FID_IID': 'str', 'contigName': 'str'})
+        df[['FID', 'IID']] = df.FID_IID.str.split('_', expand=True).astype(int)
+        return df.sort_values(by=['FID', 'IID']).drop(columns=['FID', 'IID']).set_index(['FID_IID', 'contigName'])
+
+    cases = {
+        'lin': dict(bgen='example.bgen', loco=('fit_lin_out_1.loco', 'fit_lin_out_2.loco'), prefix='test_lin_out_',
+                    missing=[]),
+        'lin_missing': dict(bgen='example.bgen', loco=('fit_lin_out_1.loco', 'fit_lin_out_2.loco'),
+                            prefix='test_lin_out_missing_',
+                            missing=['35_35', '136_136', '77_77', '100_100', '204_204', '474_474']),
+        'lin_3chr': dict(bgen='example_3chr.bgen', loco=('fit_lin_out_3chr_1.loco', 'fit_lin_out_3chr_2.loco'),
+                         prefix='test_lin_out_3chr_', missing=[]),
+    }
+    arrays = {}
+    for name, c in cases.items():
+        contigs, pos, rsids, states = read_bgen_states(os.path.join(d, c['bgen']))
+        sel = (pos - 1) < 100  # .filter('start < 100'), start = position - 1
+        contigs = [x for x, k in zip(contigs, sel) if k]
+        rsids = [x for x, k in zip(rsids, sel) if k]
+        states = states[sel]
+        phe = fid_iid(pd.read_table(os.path.join(d, 'phenotype.txt'), sep=r'\s+'))
+        phe.loc[c['missing'], :] = np.nan
+        cov = fid_iid(pd.read_table(os.path.join(d, 'covariates.txt'), sep=r'\s+'))
+        off = pd.merge(read_offset(os.path.join(d, c['loco'][0]), 'Y1'), read_offset(os.path.join(d, c['loco'][1]), 'Y2'),
+                       left_index=True, right_index=True)
+        assert list(phe.index[:3]) == ['1_1', '2_2', '3_3']
+        pdf = pd.DataFrame({'contigName': contigs, 'names': rsids, 'values': list(states.astype(np.float64))})
+        out = refshim.reference_linear_regression(pdf, phe, cov, off)
+        reg = pd.concat([
+            pd.read_table(os.path.join(d, c['prefix'] + t + '.regenie'), sep=r'\s+').astype({'ID': 'str'}).assign(phenotype=t)
+            for t in ('Y1', 'Y2')
+        ], ignore_index=True)
+        reg = reg[reg['GENPOS'] <= 100]
+        reg['pvalue'] = np.power(10, -reg['LOG10P'])
+        ours = out.rename(columns={'effect': 'BETA', 'stderror': 'SE', 'names': 'ID'})
+        if name == 'lin_3chr':
+            reg['key'] = reg['CHROM'].astype(str) + ':' + reg['ID']
+            ours['key'] = ours['contigName'].astype(str) + ':' + ours['ID']
+        else:
+            reg['key'], ours['key'] = reg['ID'], ours['ID']
+        reg = reg.set_index(['key', 'phenotype'])
+        ours = ours.set_index(['key', 'phenotype']).reindex(reg.index)
+        cols = ['BETA', 'SE', 'pvalue']
+        ok = np.isclose(ours[cols].to_numpy(), reg[cols].to_numpy(), rtol=1e-2, atol=1e-3)
+        assert ok.all(), (name, (~ok).sum())
+        G = states.shape[0]
+        contig_levels = list(dict.fromkeys(off.index.get_level_values(1)))
+        arrays.update({
+            f'{name}/states': states,
+            f'{name}/contigs': np.array(contigs),
+            f'{name}/rsids': np.array(rsids),
+            f'{name}/phenotypes': phe.to_numpy(np.float64),
+            f'{name}/covariates': cov.to_numpy(np.float64),
+            f'{name}/sample_ids': np.array(phe.index).astype(str),
+            f'{name}/offset_contigs': np.array(contig_levels),
+            # offsets as [contig][sample][trait] in phenotype row order
+            f'{name}/offsets': np.stack([off.xs(cn, level=1).reindex(phe.index).to_numpy(np.float64) for cn in contig_levels]),
+            f'{name}/regenie_key': np.array([f'{k}|{t}' for k, t in reg.index]),
+            f'{name}/regenie': reg[cols].to_numpy(np.float64),
+        })
+        for k in STATS:
+            arrays[f'{name}/ref_{k}'] = out[k].to_numpy(np.float64)
+        arrays[f'{name}/ref_key'] = np.array([f'{a}|{b}' for a, b in zip(
+            (out['contigName'].astype(str) + ':' + out['names']) if name == 'lin_3chr' else out['names'], out['phenotype'])])
+        print(f'regenie {name}: reference within rtol 1e-2 / atol 1e-3 of regenie on {ok.size} values')
+    np.savez_compressed(os.path.join(OUT, 'regenie.npz'), **arrays)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    golden_regenie()
     golden_docs()
     golden_doctest()
     golden_cars()

@@ -91,3 +91,28 @@ def assert_stats_close(got, ref, rtol_stat=RTOL_STAT, rtol_p=RTOL_P, label=''):
             i = np.argmax(err / np.maximum(tol, 1e-320))
             raise AssertionError(f'{label} {k}: {bad.sum()} of {ok.sum()} outside tolerance; worst got={g[ok][i]!r} '
                                  f'ref={r[ok][i]!r} rel={err[i] / max(abs(r[ok][i]), 1e-320):.3e}')
+
+
+def load_regenie_case(name):
+    """Inputs + regenie 1.0.6.7 outputs of one case of tests/golden/regenie.npz (oracle/make_golden.py::golden_regenie)."""
+    d = np.load(os.path.join(GOLDEN, 'regenie.npz'))
+    c = {k.split('/', 1)[1]: d[k] for k in d.files if k.startswith(name + '/')}
+    samples = [str(s) for s in c['sample_ids']]
+    phe = pd.DataFrame(c['phenotypes'], index=samples, columns=['Y1', 'Y2'])
+    cov = pd.DataFrame(c['covariates'], index=samples, columns=['V1', 'V2', 'V3'])
+    contigs = [str(x) for x in c['offset_contigs']]
+    off = pd.concat([pd.DataFrame(c['offsets'][i], index=pd.MultiIndex.from_product([samples, [cn]]), columns=['Y1', 'Y2'])
+                     for i, cn in enumerate(contigs)])
+    pdf = pd.DataFrame({'contigName': [str(x) for x in c['contigs']], 'names': [str(x) for x in c['rsids']],
+                        'values': list(c['states'].astype(np.float64))})
+    return c, pdf, phe, cov, off
+
+
+def regenie_compare(c, out, three_chr):
+    """The reference's comparison (python/glow/gwas/tests/functions.py:81-102): BETA, SE, p within
+    rtol 1e-2 / atol 1e-3 of regenie on the first 100 SNPs."""
+    key = (out['contigName'].astype(str) + ':' + out['names']) if three_chr else out['names']
+    ours = pd.DataFrame({'k': [f'{a}|{b}' for a, b in zip(key, out['phenotype'])], 'BETA': out['effect'].to_numpy(),
+                         'SE': out['stderror'].to_numpy(), 'pvalue': out['pvalue'].to_numpy()}).set_index('k')
+    ours = ours.reindex([str(k) for k in c['regenie_key']])
+    assert np.isclose(ours[['BETA', 'SE', 'pvalue']].to_numpy(), c['regenie'], rtol=1e-2, atol=1e-3).all()
