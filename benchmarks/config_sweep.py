@@ -82,11 +82,12 @@ def run(name, N, K_cov, P, G, fmt, missing=0.0, n_contigs=1, steps=3, warmup=2):
     st.close()
 
 
+import os as _os
 CONFIGS = {
     # configs[1]: dense fp64 dosages, 10k x 100k x 10 phenotypes x 10 covariates (whole config in one block)
     'cfg2': dict(N=10_000, K_cov=10, P=10, G=100_000, fmt='f64'),
     # configs[2]: bench.py's workload, here for one-stop comparison
-    'cfg3': dict(N=500_000, K_cov=16, P=1, G=37_888, fmt='plink2'),
+    'cfg3': dict(N=500_000, K_cov=16, P=1, G=int(_os.environ.get('SWEEP_G', 37_888)), fmt='plink2'),
     # configs[3]: 50k samples x 2 000 phenotypes with 10 % missing each (distinct masks), 2-bit; G scaled to one block
     'cfg4': dict(N=50_000, K_cov=10, P=2_000, G=8_192, fmt='plink2', missing=0.1),
     # configs[4]: 200k samples x 20 phenotypes, LOCO (2 of 22 contig states built here), 2-bit

@@ -22,7 +22,8 @@ namespace glr {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = (kWarps + 1) * 32;
-constexpr int kStages = 4;
+constexpr int kStages = 4;     // masked pass / large stages
+constexpr int kMaxStages = 8;  // gram pass with small stages (MT <= 4): deeper ring, warps drift further apart
 constexpr int kBarBytes = 128;  // full[4] + empty[4] mbarriers, padded
 
 // ------------------------------------------------------------------------------------------------
@@ -248,12 +249,11 @@ struct XLoader<GLR_FMT_I8, NT> {
 struct Ring {
   uint64_t* full;
   uint64_t* empty;
-  __device__ __forceinline__ void init(unsigned char* smem, int tid, int n_consumer_warps) {
+  __device__ __forceinline__ void init(unsigned char* smem, int tid, int n_consumer_warps, int n_stages = kStages) {
     full = reinterpret_cast<uint64_t*>(smem);
-    empty = full + kStages;
+    empty = full + kMaxStages;
     if (tid == 0) {
-#pragma unroll
-      for (int s = 0; s < kStages; ++s) {
+      for (int s = 0; s < n_stages; ++s) {
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], n_consumer_warps);
       }
@@ -280,7 +280,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Ring ring;
-  ring.init(smem, tid, WARPS);
+  constexpr int kStagesG = MT <= 4 ? kMaxStages : kStages;
+  ring.init(smem, tid, WARPS, kStagesG);
   double* wst = reinterpret_cast<double*>(smem + kBarBytes);
 
   const int64_t cps = ceil_div(p.n_chunks, p.n_split);
@@ -292,8 +293,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
     if (lane == 0) {
       const double* src = p.wpk + ((int64_t)blockIdx.y * p.n_chunks + c_begin) * kStageDoubles;
       for (int64_t it = 0; it < n_it; ++it) {
-        const int s = (int)(it % kStages);
-        if (it >= kStages) mbar_wait_backoff(&ring.empty[s], (uint32_t)((it / kStages) & 1) ^ 1u);
+        const int s = (int)(it % kStagesG);
+        if (it >= kStagesG) mbar_wait_backoff(&ring.empty[s], (uint32_t)((it / kStagesG) & 1) ^ 1u);
         mbar_expect_tx(&ring.full[s], kStageBytes);
         bulk_g2s(wst + (int64_t)s * kStageDoubles, src + it * kStageDoubles, kStageBytes, &ring.full[s]);
       }
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
   const int r = lane >> 2, j = lane & 3;
   const int v_warp = blockIdx.x * (WARPS * NT * 8) + warp * (NT * 8);
   Loader ld;
-  ld.init(p.x, v_warp, r, j, wst + (int64_t)kStages * kStageDoubles + warp * Loader::kLutDoublesPerWarp, lane);
+  ld.init(p.x, v_warp, r, j, wst + (int64_t)kStagesG * kStageDoubles + warp * Loader::kLutDoublesPerWarp, lane);
 
   double acc[MT][NT][2];
 #pragma unroll
@@ -325,8 +326,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
   const int64_t s_begin = c_begin * kChunk;
   if (t_total > 0) ld.load(s_begin);
   for (int64_t it = 0; it < n_it; ++it) {
-    const int s = (int)(it % kStages);
-    mbar_wait(&ring.full[s], (uint32_t)((it / kStages) & 1));
+    const int s = (int)(it % kStagesG);
+    mbar_wait(&ring.full[s], (uint32_t)((it / kStagesG) & 1));
     const double* st = wst + (int64_t)s * kStageDoubles;
     // A fragments (and tail weights) are fetched one sample group ahead of their DMMAs
     double2 a_nxt[MT];
@@ -583,7 +584,7 @@ template <int FMT, int MT, int NT, int TAIL, int WARPS = kWarps>
 void launch_gram_inst(const GramParams& p, cudaStream_t st) {
   const int tile = WARPS * NT * 8;
   dim3 grid((unsigned)ceil_div(p.x.n_variants, tile), (unsigned)p.n_groups, (unsigned)p.n_split);
-  const size_t smem = kBarBytes + (size_t)kStages * kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup) * 8 +
+  const size_t smem = kBarBytes + (size_t)(MT <= 4 ? kMaxStages : kStages) * kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup) * 8 +
                       (size_t)WARPS * XLoader<FMT, NT>::kLutDoublesPerWarp * 8;
   auto kern = gram_kernel<FMT, MT, NT, TAIL, WARPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
