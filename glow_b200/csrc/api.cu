@@ -94,6 +94,12 @@ struct glr_state {
   double icpt_q0 = 0.0;
   int64_t w_contig_doubles = 0;
   double* wpk = nullptr;  // [C][n_groups][n_chunks][8][MT][64]
+  // integer tensor-core variant of pass 1 (PLINK2 blocks): digits of W, see split8.cu
+  int split8 = 0;  // 0 = off, 1 = built
+  int s8_cols = 0, s8_NB = 0;
+  int64_t s8_stages = 0, s8_contig_bytes = 0;
+  int8_t* w8 = nullptr;       // [C][stage][NB][128]
+  double* s8_scale = nullptr; // [C][s8_cols]
   // masked pass
   int U = 0, MT2 = 1, n_groups2 = 0, KT2 = 0;
   double* qb = nullptr;
@@ -157,7 +163,7 @@ int glr_state_destroy(glr_state* st) {
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   for (void* p : {(void*)st->wpk, (void*)st->qb, (void*)st->mpk, (void*)st->mask_id, (void*)st->YdotY,
-                  (void*)st->Y_scale, (void*)st->n_obs, (void*)st->drop_idx})
+                  (void*)st->Y_scale, (void*)st->n_obs, (void*)st->drop_idx, (void*)st->w8, (void*)st->s8_scale})
     if (p) cudaFree(p);
   delete st;
   return 0;
@@ -354,6 +360,21 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   const size_t w_bytes = (size_t)C * st->w_contig_doubles * sizeof(double);
   CU(cudaMalloc(&st->wpk, w_bytes));
   CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
+  // opt-in integer tensor-core operand (GLR_SPLIT8=1): non-verbose states with at most 32 GEMM columns
+  double* d_colmax = nullptr;
+  if (getenv("GLR_SPLIT8") && atoi(getenv("GLR_SPLIT8")) > 0 && !st->verbose && st->Mcols <= 32 && st->Mcols > 0 &&
+      Ng < (int64_t)16000000) {
+    st->split8 = atoi(getenv("GLR_SPLIT8"));  // 1 = large blocks only, 2 = every PLINK2 block
+    st->s8_cols = st->Mcols;
+    st->s8_NB = (int)round_up(8 * st->Mcols, 16);
+    st->s8_stages = ceil_div(Ng, 128);
+    st->s8_contig_bytes = st->s8_stages * (int64_t)st->s8_NB * 128;
+    CU(cudaMalloc(&st->w8, (size_t)C * st->s8_contig_bytes));
+    CU(cudaMemsetAsync(st->w8, 0, (size_t)C * st->s8_contig_bytes, s0));
+    CU(cudaMalloc(&st->s8_scale, (size_t)C * st->s8_cols * sizeof(double)));
+    CU(cudaMalloc(&d_colmax, (size_t)st->s8_cols * sizeof(double)));
+    tmp.v.push_back(d_colmax);
+  }
   for (int c = 0; c < C; ++c) {
     double* dst = st->wpk + (int64_t)c * st->w_contig_doubles;
     CU(cudaMemcpyAsync(dY, d->Y + (int64_t)c * N * P, (size_t)N * P * sizeof(double), in_kind, s0));
@@ -364,6 +385,14 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
         launch_pack_a(dQ, N, K, st->has_icpt, Kg, d_g2r, Ng, dst, 0, st->MT, st->tail, st->n_chunks, s0);
     }
     launch_pack_a(dY, N, P, 0, P, d_g2r, Ng, dst, Kg, st->MT, st->tail, st->n_chunks, s0);
+    if (st->split8) {
+      int8_t* d8 = st->w8 + (int64_t)c * st->s8_contig_bytes;
+      if (Kg > 0)
+        launch_pack_split8(dQ, N, K, st->has_icpt, Kg, d_colmax, d_g2r, Ng, d8, 0, st->s8_NB, st->s8_stages, s0);
+      launch_pack_split8(dY, N, P, 0, P, d_colmax + Kg, d_g2r, Ng, d8, Kg, st->s8_NB, st->s8_stages, s0);
+      CU(cudaMemcpyAsync(st->s8_scale + (int64_t)c * st->s8_cols, d_colmax, (size_t)st->s8_cols * sizeof(double),
+                         cudaMemcpyDeviceToDevice, s0));
+    }
     if (st->verbose) {
       launch_pack_a(dM, N, P, 0, P, d_g2r, Ng, dst, Kg + P, st->MT, st->tail, st->n_chunks, s0);
       launch_pack_a(dYraw, N, P, 0, P, d_g2r, Ng, dst, Kg + 2 * P, st->MT, st->tail, st->n_chunks, s0);
@@ -407,6 +436,12 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   }
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
+  if (st->split8) {  // scale_c = max|w_c| * 2^-54
+    std::vector<double> sc((size_t)C * st->s8_cols);
+    CU(cudaMemcpy(sc.data(), st->s8_scale, sc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (auto& v : sc) v = std::ldexp(v, -54);
+    CU(cudaMemcpy(st->s8_scale, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
 
   // ---- lanes ----
   int n_lanes = d->n_lanes > 0 ? d->n_lanes : 2;
@@ -536,9 +571,24 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   gp.S = (n_split > 1 ? L.s_part.as<double>() : L.s_red.as<double>()) + (int64_t)st->has_icpt * ldS;
   gp.s_slab = Mpad * ldS;
   gp.mom_part = (float_fmt && n_split > 1) ? L.mom_part.as<double>() : L.mom.as<double>();
-  launch_gram(gp, s);
+  const bool use_split8 =
+      st->split8 && b->format == GLR_FMT_PLINK2 && (st->split8 >= 2 || ceil_div(G, 128) * 2 >= st->sm_count);
+  if (use_split8) {
+    Split8Params sp;
+    sp.x = x;
+    sp.w8 = st->w8 + (int64_t)b->contig * st->s8_contig_bytes;
+    sp.scale = st->s8_scale + (int64_t)b->contig * st->s8_cols;
+    sp.n_cols = st->s8_cols;
+    sp.NB = st->s8_NB;
+    sp.n_stages = st->s8_stages;
+    sp.S = L.s_red.as<double>() + (int64_t)st->has_icpt * ldS;
+    sp.ldS = ldS;
+    launch_split8(sp, st->sm_count, s);
+  } else {
+    launch_gram(gp, s);
+  }
   ++L.launches;
-  if (n_split > 1) {
+  if (n_split > 1 && !use_split8) {
     launch_reduce_splits(L.s_part.as<double>(), L.s_red.as<double>(), Mpad, ldS, n_split, s);
     ++L.launches;
     if (float_fmt) {

@@ -42,6 +42,22 @@ struct GramParams {
 int gram_tile_variants(int nt, int warps = 8);  // variants per CTA
 void launch_gram(const GramParams& p, cudaStream_t st);
 
+// ---- pass 1, integer tensor-core variant (PLINK 2-bit only): exact digit-split GEMM on tcgen05 ----
+struct Split8Params {
+  BlockView x;          // PLINK2 block; x.v1 = missing substitute per variant
+  const int8_t* w8;     // packed digits of this contig: [stage][NB rows][128 B], 128-byte swizzled
+  const double* scale;  // [n_cols] column scale = max|w_c| * 2^-54
+  int32_t n_cols;       // columns of W in the GEMM
+  int32_t NB;           // digit rows = round_up(8 * n_cols, 16) <= 256
+  int64_t n_stages;     // 128-sample stages
+  double* S;            // first GEMM row of the S workspace, [n_cols][ldS]
+  int64_t ldS;
+};
+void launch_split8(const Split8Params& p, int sm_count, cudaStream_t st);
+void launch_pack_split8(const double* src, int64_t N, int64_t ld, int c0, int ncols, double* colmax_scratch,
+                        const int64_t* geno_to_row, int64_t Ng, int8_t* dst, int dst_col0, int NB, int64_t n_stages,
+                        cudaStream_t st);
+
 // ---- pass 2 (only when some phenotype has missing samples): D = Mu^T (X - Q A)^2 ----------------
 struct MaskedParams {
   BlockView x;
