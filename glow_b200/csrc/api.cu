@@ -61,7 +61,7 @@ struct DevBuf {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
-  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx;
+  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx, s8_scratch;
   bool busy = false;
   bool has_masked = false, has_prepass = false;
   int launches = 0;
@@ -96,7 +96,7 @@ struct glr_state {
   double* wpk = nullptr;  // [C][n_groups][n_chunks][8][MT][64]
   // integer tensor-core variant of pass 1 (PLINK2 blocks): digits of W, see split8.cu
   int split8 = 0;  // 0 = off, 1 = built
-  int s8_cols = 0, s8_NB = 0;
+  int s8_cols = 0, s8_MB = 0;
   int64_t s8_stages = 0, s8_contig_bytes = 0;
   int8_t* w8 = nullptr;       // [C][stage][NB][128]
   double* s8_scale = nullptr; // [C][s8_cols]
@@ -158,7 +158,7 @@ int glr_state_destroy(glr_state* st) {
     if (l.stream) cudaStreamSynchronize(l.stream);
     for (auto& e : l.ev)
       if (e) cudaEventDestroy(e);
-    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.mom_part, &l.mom, &l.v1, &l.d_part, &l.d_red, &l.xx})
+    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.mom_part, &l.mom, &l.v1, &l.d_part, &l.d_red, &l.xx, &l.s8_scratch})
       b->release();
     if (l.stream) cudaStreamDestroy(l.stream);
   }
@@ -362,13 +362,13 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
   // opt-in integer tensor-core operand (GLR_SPLIT8=1): non-verbose states with at most 32 GEMM columns
   double* d_colmax = nullptr;
-  if (getenv("GLR_SPLIT8") && atoi(getenv("GLR_SPLIT8")) > 0 && !st->verbose && st->Mcols <= 32 && st->Mcols > 0 &&
-      Ng < (int64_t)16000000) {
+  if (getenv("GLR_SPLIT8") && atoi(getenv("GLR_SPLIT8")) > 0 && !st->verbose && st->Mcols <= 36 && st->Mcols > 0 &&
+      Ng < (int64_t)8000000) {
     st->split8 = atoi(getenv("GLR_SPLIT8"));  // 1 = large blocks only, 2 = every PLINK2 block
     st->s8_cols = st->Mcols;
-    st->s8_NB = (int)round_up(8 * st->Mcols, 16);
+    st->s8_MB = st->Mcols <= 18 ? 1 : 2;
     st->s8_stages = ceil_div(Ng, 128);
-    st->s8_contig_bytes = st->s8_stages * (int64_t)st->s8_NB * 128;
+    st->s8_contig_bytes = st->s8_stages * (int64_t)st->s8_MB * 128 * 128;
     CU(cudaMalloc(&st->w8, (size_t)C * st->s8_contig_bytes));
     CU(cudaMemsetAsync(st->w8, 0, (size_t)C * st->s8_contig_bytes, s0));
     CU(cudaMalloc(&st->s8_scale, (size_t)C * st->s8_cols * sizeof(double)));
@@ -388,8 +388,8 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     if (st->split8) {
       int8_t* d8 = st->w8 + (int64_t)c * st->s8_contig_bytes;
       if (Kg > 0)
-        launch_pack_split8(dQ, N, K, st->has_icpt, Kg, d_colmax, d_g2r, Ng, d8, 0, st->s8_NB, st->s8_stages, s0);
-      launch_pack_split8(dY, N, P, 0, P, d_colmax + Kg, d_g2r, Ng, d8, Kg, st->s8_NB, st->s8_stages, s0);
+        launch_pack_split8(dQ, N, K, st->has_icpt, Kg, d_colmax, d_g2r, Ng, d8, 0, st->s8_MB, st->s8_stages, s0);
+      launch_pack_split8(dY, N, P, 0, P, d_colmax + Kg, d_g2r, Ng, d8, Kg, st->s8_MB, st->s8_stages, s0);
       CU(cudaMemcpyAsync(st->s8_scale + (int64_t)c * st->s8_cols, d_colmax, (size_t)st->s8_cols * sizeof(double),
                          cudaMemcpyDeviceToDevice, s0));
     }
@@ -547,9 +547,14 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   x.n_geno = st->Ng;
   x.v1 = L.v1.as<double>();
 
+  const bool use_split8 =
+      st->split8 && b->format == GLR_FMT_PLINK2 && (st->split8 >= 2 || ceil_div(G, 128) * 2 >= st->sm_count);
+  const bool fused_counts = use_split8 && st->n_drop == 0;
+  if (use_split8)
+    if (int rc = L.s8_scratch.ensure(split8_scratch_bytes(st->s8_MB, st->sm_count))) return rc;
   CU(cudaEventRecord(L.ev[0], s));
   // ---- pre-pass (A0): missing substitute + sum of squares from integer counts ----
-  if (!float_fmt) {
+  if (!float_fmt && !fused_counts) {
     launch_prepass(x, b->missing_policy, L.v1.as<double>(), L.mom.as<double>(), ldS, s);
     L.has_prepass = true;
     ++L.launches;
@@ -571,18 +576,23 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   gp.S = (n_split > 1 ? L.s_part.as<double>() : L.s_red.as<double>()) + (int64_t)st->has_icpt * ldS;
   gp.s_slab = Mpad * ldS;
   gp.mom_part = (float_fmt && n_split > 1) ? L.mom_part.as<double>() : L.mom.as<double>();
-  const bool use_split8 =
-      st->split8 && b->format == GLR_FMT_PLINK2 && (st->split8 >= 2 || ceil_div(G, 128) * 2 >= st->sm_count);
   if (use_split8) {
     Split8Params sp;
     sp.x = x;
     sp.w8 = st->w8 + (int64_t)b->contig * st->s8_contig_bytes;
     sp.scale = st->s8_scale + (int64_t)b->contig * st->s8_cols;
     sp.n_cols = st->s8_cols;
-    sp.NB = st->s8_NB;
+    sp.MB = st->s8_MB;
+    sp.n_stage_bufs = 0;
+    sp.n_x_bufs = 0;
+    sp.fused_counts = fused_counts ? 1 : 0;
+    sp.missing_policy = b->missing_policy;
     sp.n_stages = st->s8_stages;
     sp.S = L.s_red.as<double>() + (int64_t)st->has_icpt * ldS;
     sp.ldS = ldS;
+    sp.scratch = L.s8_scratch.as<int32_t>();
+    sp.v1_out = L.v1.as<double>();
+    sp.mom_out = L.mom.as<double>();
     launch_split8(sp, st->sm_count, s);
   } else {
     launch_gram(gp, s);

@@ -78,7 +78,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(256);
+    __nanosleep(64);
   }
 }
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0, 16-B aligned).
