@@ -342,9 +342,9 @@ size_t split8_scratch_bytes(int MB, int sm_count) { return (size_t)sm_count * MB
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;
   const int n_tiles = (p.x.n_variants + kS8TileV - 1) / kS8TileV;
-  // 192 KB of operand buffers: MB = 1 -> 6 x 16 KB digits + 3 x 32 KB genotypes; MB = 2 -> 3 x 32 KB + 3 x 32 KB
-  p.n_stage_bufs = p.MB == 1 ? 6 : 3;
-  p.n_x_bufs = 3;
+  // 192 KB of operand buffers: MB = 1 -> 4 x 16 KB digits + 4 x 32 KB genotypes; MB = 2 -> 3 x 32 KB + 3 x 32 KB
+  p.n_stage_bufs = p.MB == 1 ? 4 : 3;
+  p.n_x_bufs = p.MB == 1 ? 4 : 3;
   const size_t smem = (size_t)p.n_stage_bufs * p.MB * kS8M * kS8K + (size_t)p.n_x_bufs * kS8N * kS8K + sizeof(Split8Smem) + 64;
   cudaFuncSetAttribute(split8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   split8_kernel<<<std::min(n_tiles, sm_count), kS8Threads, smem, st>>>(p);
