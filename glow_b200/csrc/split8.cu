@@ -139,13 +139,21 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
   if (warp == 0) {
     // ---- digit-operand producer ----
     if (lane == 0) {
-      int64_t it = 0;
+      // ring slot and phase are carried incrementally: a 64-bit modulo by a run-time ring depth costs
+      // hundreds of cycles per stage on the issuing thread
+      int s = 0;
+      uint32_t ph = 0;
+      bool wrapped = false;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int64_t k = 0; k < n_st; ++k, ++it) {
-          const int s = (int)(it % DW);
-          if (it >= DW) mbar_wait_backoff(&sm->empty_w[s], (uint32_t)((it / DW) & 1) ^ 1u);
+        for (int64_t k = 0; k < n_st; ++k) {
+          if (wrapped) mbar_wait_backoff(&sm->empty_w[s], ph ^ 1u);
           mbar_expect_tx(&sm->full_w[s], w_bytes);
           bulk_g2s(w_ring + (size_t)s * w_bytes, p.w8 + k * w_bytes, w_bytes, &sm->full_w[s]);
+          if (++s == DW) {
+            s = 0;
+            ph ^= 1u;
+            wrapped = true;
+          }
         }
       }
     }
@@ -153,16 +161,17 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     // ---- MMA issuer ----
     // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kS8N >> 3) << 17) | ((uint32_t)(kS8M >> 4) << 24);
-    int64_t it = 0;
+    int sw = 0;  // DW == DX: the two rings advance together
+    uint32_t ph = 0;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       // the epilogue of the previous tile must have drained the accumulators
       if (tcount > 0) mbar_wait(&sm->tmem_empty, (uint32_t)((tcount - 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      for (int64_t k = 0; k < n_st; ++k, ++it) {
-        const int sw = (int)(it % DW), sx = (int)(it % DX);
-        mbar_wait(&sm->full_w[sw], (uint32_t)((it / DW) & 1));
-        mbar_wait(&sm->full_x[sx], (uint32_t)((it / DX) & 1));
+      for (int64_t k = 0; k < n_st; ++k) {
+        const int sx = sw;
+        mbar_wait(&sm->full_w[sw], ph);
+        mbar_wait(&sm->full_x[sx], ph);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         if (lane == 0) {
           const uint32_t w_addr = smem_u32(w_ring + (size_t)sw * w_bytes);
@@ -174,11 +183,15 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
             for (int mb = 0; mb < MB; ++mb)
               s8_mma(tmem + mb * kS8N, s8_desc(w_addr + mb * (kS8M * kS8K) + kk * 32), db, idesc, acc);
           }
-          s8_commit(&sm->empty_w[sw]);                   // both buffers are free once these MMAs retire
-          s8_commit(&sm->empty_x[sx]);
+          s8_commit(&sm->empty_w[sw]);                   // ONE commit per stage (each costs the issuing thread
+                                                         // several hundred cycles): frees both buffers of the stage
           if (k == n_st - 1) s8_commit(&sm->tmem_full);  // accumulators of the tile are complete
         }
         __syncwarp();
+        if (++sw == DW) {
+          sw = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp >= kS8FirstDecodeWarp) {
@@ -188,7 +201,9 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     const int64_t n_geno = p.x.n_geno;
     const int64_t row_bytes = (n_geno + 3) >> 2;
     const int64_t full_bytes = n_geno >> 2;
-    int64_t it = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    bool wrapped = false;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int v = min(tile * kS8TileV + vloc, p.x.n_variants - 1);
@@ -233,15 +248,14 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           if ((int64_t)l * 128 < row_bytes) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + l * 128));
       }
       load(0);
-      for (int64_t k = 0; k < n_st; ++k, ++it) {
+      for (int64_t k = 0; k < n_st; ++k) {
         uint32_t w[kS8Words];
 #pragma unroll
         for (int i = 0; i < kS8Words; ++i) w[i] = __funnelshift_r(nxt[i], nxt[i + 1], sh_nxt);
         if (k + 1 < n_st) load(k + 1);
         if (half == 0 && (k & 3) == 0 && (k + 16) * 32 < row_bytes)
           asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (k + 16) * 32));
-        const int s = (int)(it % DX);
-        if (it >= DX) mbar_wait(&sm->empty_x[s], (uint32_t)((it / DX) & 1) ^ 1u);
+        if (wrapped) mbar_wait(&sm->empty_w[s], ph ^ 1u);
         unsigned char* xrow = x_ring + (size_t)s * x_bytes + vloc * kS8K;
         unsigned char* erow = xrow + kS8TileV * kS8K;
 #pragma unroll
@@ -264,6 +278,11 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes -> async proxy (MMA reads)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->full_x[s]);
+        if (++s == DX) {
+          s = 0;
+          ph ^= 1u;
+          wrapped = true;
+        }
       }
       // per-variant code counts: the two lanes of a variant are neighbours
       n00 += __shfl_xor_sync(0xffffffffu, n00, 1);
@@ -343,8 +362,8 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;
   const int n_tiles = (p.x.n_variants + kS8TileV - 1) / kS8TileV;
   // 192 KB of operand buffers: MB = 1 -> 4 x 16 KB digits + 4 x 32 KB genotypes; MB = 2 -> 3 x 32 KB + 3 x 32 KB
-  p.n_stage_bufs = p.MB == 1 ? 4 : 3;
-  p.n_x_bufs = p.MB == 1 ? 4 : 3;
+  p.n_stage_bufs = p.MB == 1 ? 4 : 3;  // the two rings advance together (one completion barrier per stage)
+  p.n_x_bufs = p.n_stage_bufs;
   const size_t smem = (size_t)p.n_stage_bufs * p.MB * kS8M * kS8K + (size_t)p.n_x_bufs * kS8N * kS8K + sizeof(Split8Smem) + 64;
   cudaFuncSetAttribute(split8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   split8_kernel<<<std::min(n_tiles, sm_count), kS8Threads, smem, st>>>(p);
