@@ -44,7 +44,7 @@ SEED = 20261019
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--variants-per-step', type=int, default=148 * 256)
@@ -311,44 +311,61 @@ def main():
     out_addrs = {k: v.data_ptr() for k, v in outs.items()}
     torch.cuda.synchronize()
 
-    lane_stream = torch.cuda.ExternalStream(state.lane_stream(0), device=dev)
-
-    def step_device():
-        state.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=False)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-        state.wait_device(0)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {'prepass_ms': 0.0, 'gram_ms': 0.0, 'masked_ms': 0.0, 'epilogue_ms': 0.0, 'total_ms': 0.0}
-    launches = 0
-    ev0.record(lane_stream)
-    for _ in range(args.steps):
-        step_device()
-        state.wait_device(0)
-        t = state.timing(0)
+    def measure(st, sample_clocks):
+        """W warm-up steps, then K timed steps on the lane stream of `st` (CUDA events, max over ranks)."""
+        lane_stream = torch.cuda.ExternalStream(st.lane_stream(0), device=dev)
+
+        def step_device():
+            st.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=False)
+
+        for _ in range(args.warmup):
+            step_device()
+            st.wait_device(0)
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = {'prepass_ms': 0.0, 'gram_ms': 0.0, 'masked_ms': 0.0, 'epilogue_ms': 0.0, 'total_ms': 0.0}
+        launches = 0
+        ev0.record(lane_stream)
+        for _ in range(args.steps):
+            step_device()
+            st.wait_device(0)
+            t = st.timing(0)
+            for k in stage:
+                stage[k] += t[k]
+            launches += t['kernel_launches']
+        ev1.record(lane_stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms_total = ev0.elapsed_time(ev1)
+        t_max = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        ms_step = float(t_max.item()) / args.steps
         for k in stage:
-            stage[k] += t[k]
-        launches += t['kernel_launches']
-    ev1.record(lane_stream)
-    barrier()
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    t_max = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    ms_step = float(t_max.item()) / args.steps
+            stage[k] /= args.steps
+        return ms_step, stage, launches, clocks
+
+    # primary arm: the library's default path (2-bit genotypes -> exact int8 digit-split GEMM on tcgen05)
+    ms_step, stage, launches, clocks = measure(state, True)
     value = world * G * P / (ms_step / 1e3)
-    for k in stage:
-        stage[k] /= args.steps
+    t_primary = outs['tvalue'].clone()
+
+    # secondary arm in the same run: the FP64 tensor-core (DMMA) path forced for the same batch
+    os.environ['GLR_SPLIT8'] = '0'
+    state_dmma = gdist.device_state_from_flat(flat, header, local_rank, n_lanes=1)
+    os.environ.pop('GLR_SPLIT8', None)
+    ms_dmma, stage_dmma, _, _ = measure(state_dmma, False)
+    paths_agree = bool(torch.allclose(outs['tvalue'], t_primary, rtol=1e-9, atol=1e-12, equal_nan=True))
+    state_dmma.close()
+    state.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=True)
 
     # sanity: results are real numbers for (nearly) all variants
     pv = outs['pvalue']
@@ -407,8 +424,9 @@ def main():
         }
         del host_packed
 
-    # ---- roofline of the dominant kernel (DMMA contraction) ----
+    # ---- rooflines ----
     roof = None
+    dmma = None
     cpu = None
     if rank == 0:
         peaks = {}
@@ -418,57 +436,74 @@ def main():
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         hbm_src = 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
-        # FP64 tensor peak: measured here (cuBLAS DGEMM 8192^3, best of 5), MEASURED_PEAKS.json has none
-        a = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
-        b = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
-        best = 1e9
-        for i in range(0 if args.skip_peak else 7):
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            torch.matmul(a, b)
-            s1.record()
-            torch.cuda.synchronize()
-            if i >= 2:
-                best = min(best, s0.elapsed_time(s1))
-        fp64_peak = 2 * 8192**3 / (best / 1e3) / 1e12 if not args.skip_peak else float('nan')
-        del a, b
-        # executed formulation: S = [Q(:,1:) | Ytilde]^T X.  The intercept column of Q is constant, so its
-        # product with x is q0 * sum(x) and comes from the integer genotype counts of the pre-pass: its
-        # 2N flops per variant are NOT executed and are not counted in `achieved`.
+
+        def best_of(fn, n=7, skip=2):
+            best = 1e9
+            for i in range(n):
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                fn()
+                s1.record()
+                torch.cuda.synchronize()
+                if i >= skip:
+                    best = min(best, s0.elapsed_time(s1))
+            return best
+
+        fp64_peak = float('nan')
+        int8_peak, int8_src = float('nan'), 'not measured'
+        if not args.skip_peak:
+            # FP64 tensor peak: cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json has no fp64 entry)
+            a = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
+            b = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
+            fp64_peak = 2 * 8192**3 / (best_of(lambda: torch.matmul(a, b)) / 1e3) / 1e12
+            del a, b
+            # INT8 tensor peak: cuBLASLt int8 GEMM 8192^3 through torch._int_mm; if that is not available the
+            # rate of back-to-back tcgen05.mma kind::i8 (benchmarks/micro/umma_i8_rate.cu, 4.28 Pop/s) is used
+            try:
+                a8 = torch.randint(-127, 127, (8192, 8192), dtype=torch.int8, device=dev)
+                b8 = torch.randint(-127, 127, (8192, 8192), dtype=torch.int8, device=dev)
+                int8_peak = 2 * 8192**3 / (best_of(lambda: torch._int_mm(a8, b8)) / 1e3) / 1e12
+                int8_src = 'cuBLASLt int8 GEMM 8192^3 via torch._int_mm, best of 5, measured in this run'
+                del a8, b8
+            except Exception as exc:  # noqa: BLE001
+                int8_peak = 4280.0
+                int8_src = f'tcgen05.mma kind::i8 issue-rate microbenchmark (torch._int_mm unavailable: {type(exc).__name__})'
+        # Executed formulation: S = [Q(:,1:) | Ytilde]^T X.  The intercept column of Q is constant, so its product
+        # with x is q0 * sum(x) and comes from the genotype counts: its flops are NOT executed and not counted.
         cols = (K - 1) + P
-        dmma_cols = (cols // 8) * 8 if 1 <= cols % 8 <= 3 and cols // 8 >= 1 else ((cols + 7) // 8) * 8
-        flops_alg = 2.0 * n * cols * G
-        flops_issued = 2.0 * n * max(dmma_cols, cols) * G  # DMMA columns (incl. zero padding) + FMA tail columns
-        flops_ref = float(n) * (4 * K + 4 * P + 2) * G  # reference formulation, SURVEY.md section 8(d)
+        flops_f64_equiv = 2.0 * n * cols * G                      # FP64 flops of the contraction as formulated
+        flops_ref = float(n) * (4 * K + 4 * P + 2) * G            # reference formulation, SURVEY.md section 8(d)
         gram_s = stage['gram_ms'] / 1e3
-        achieved = flops_alg / gram_s / 1e12
+        # int8 digit-split kernel: 7 digit rows per column, two int8 operands (genotype, missing indicator)
+        ops_int8 = 2.0 * n * (7 * cols) * 2 * G
+        mb = 1 if cols <= 18 else 2
+        ops_int8_issued = 2.0 * (-(-n // 128) * 128) * (128 * mb) * 256 * (-(-G // 128))
+        achieved = ops_int8 / gram_s / 1e12
         roof = {
-            'kernel': 'gram_kernel<PLINK2, MT=2, NT=2, TAIL=1, WARPS=16> (mma.sync.m8n8k4.f64 DMMA for the 16 covariate '
-                      'columns, FP64 FMA for the phenotype column, intercept column from genotype counts, fused '
-                      '2-bit decode)',
+            'kernel': 'split8_kernel (tcgen05.mma kind::i8 M128 N256 K32, accumulators in TMEM; exact 7-digit radix-256 '
+                      'split of the FP64 operand, 2-bit decode + genotype counts fused, FP64 recombination in the epilogue)',
             'bound': 'tensor',
             'achieved': achieved,
-            'peak': fp64_peak,
+            'peak': int8_peak,
             'unit': 'TFLOP/s',
-            'frac': achieved / fp64_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at the default shape,
-            # from the ncu --set full capture in profiles/r01_gram_full.txt (4.812 GB + 6 MB; algorithmic
-            # bytes are 4.736 GB of packed genotypes + 68 MB of packed state): no re-reads
-            'traffic': 4.818e9 if (n == N_SAMPLES and G == 148 * 256) else None,
-            'algorithmic_bytes_per_launch': float(G) * row_bytes + 8.0 * n * cols,
-            'peak_source': 'cuBLAS DGEMM 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json has no fp64 entry)',
-            'flops_per_launch_algorithmic': flops_alg,
-            'issued_tflops_incl_padding': flops_issued / gram_s / 1e12,
+            'op_type': 'int8 tensor-core operations (2 per multiply-accumulate), algorithmic = digit rows actually needed',
+            'frac': achieved / int8_peak,
+            'traffic': None,
+            'peak_source': int8_src,
+            'ops_per_launch_algorithmic': ops_int8,
+            'issued_tops_incl_padding': ops_int8_issued / gram_s / 1e12,
+            'fp64_equivalent_tflops': flops_f64_equiv / gram_s / 1e12,
             'reference_equivalent_tflops': flops_ref / gram_s / 1e12,
+            'algorithmic_bytes_per_launch': float(G) * row_bytes + 7.0 * n * cols,
             'avg_launch_ms': stage['gram_ms'],
             'share_of_step': stage['gram_ms'] / max(stage['total_ms'], 1e-9),
             'stages': {
-                'prepass': {
+                'genotype_read_inside_kernel': {
                     'bound': 'hbm',
-                    'achieved_gbs': G * row_bytes / max(stage['prepass_ms'], 1e-9) / 1e6,
+                    'achieved_gbs': G * row_bytes / max(stage['gram_ms'], 1e-9) / 1e6,
                     'peak_gbs': hbm_peak,
                     'peak_source': hbm_src,
-                    'ms': stage['prepass_ms']
+                    'note': 'decode, counts and mean imputation are fused into the contraction kernel: no pre-pass'
                 },
                 'epilogue': {
                     'bound': 'hbm',
@@ -476,6 +511,35 @@ def main():
                     'peak_gbs': hbm_peak,
                     'ms': stage['epilogue_ms']
                 }
+            }
+        }
+        dmma_cols = (cols // 8) * 8 if 1 <= cols % 8 <= 3 and cols // 8 >= 1 else ((cols + 7) // 8) * 8
+        d_s = stage_dmma['gram_ms'] / 1e3
+        dmma = {
+            'note': 'same batch through the FP64 tensor-core path (GLR_SPLIT8=0): what float / dosage input, more than '
+                    '36 columns or small blocks use',
+            'value': world * G * P / (ms_dmma / 1e3),
+            'unit': 'tests/s',
+            'ms_per_step': ms_dmma,
+            'stage_ms': stage_dmma,
+            'agrees_with_primary_path_rel_1e-9': paths_agree,
+            'roofline': {
+                'kernel': 'gram_kernel<PLINK2, MT=2, NT=2, TAIL=1, WARPS=16> (mma.sync.m8n8k4.f64 DMMA for the 16 covariate '
+                          'columns, FP64 FMA for the phenotype column, fused 2-bit decode)',
+                'bound': 'tensor',
+                'achieved': flops_f64_equiv / d_s / 1e12,
+                'peak': fp64_peak,
+                'unit': 'TFLOP/s',
+                'frac': flops_f64_equiv / d_s / 1e12 / fp64_peak,
+                # dram bytes of one launch at the default shape, ncu --set full, profiles/r01_gram_full.txt
+                'traffic': 4.818e9 if (n == N_SAMPLES and G == 148 * 256) else None,
+                'algorithmic_bytes_per_launch': float(G) * row_bytes + 8.0 * n * cols,
+                'peak_source': 'cuBLAS DGEMM 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json has no fp64 entry)',
+                'issued_tflops_incl_padding': 2.0 * n * max(dmma_cols, cols) * G / d_s / 1e12,
+                'reference_equivalent_tflops': flops_ref / d_s / 1e12,
+                'avg_launch_ms': stage_dmma['gram_ms'],
+                'prepass_gbs': G * row_bytes / max(stage_dmma['prepass_ms'], 1e-9) / 1e6,
+                'hbm_peak_gbs': hbm_peak
             }
         }
         if not args.skip_cpu_baseline:
@@ -516,6 +580,7 @@ def main():
             'e2e': e2e,
             'gpu_launches': launches,
             'roofline': roof,
+            'dmma_f64_path': dmma,
             'cpu_baseline': cpu,
             'stage_ms': stage,
             'finite_fraction': frac_finite

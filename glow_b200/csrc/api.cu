@@ -360,11 +360,12 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   const size_t w_bytes = (size_t)C * st->w_contig_doubles * sizeof(double);
   CU(cudaMalloc(&st->wpk, w_bytes));
   CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
-  // opt-in integer tensor-core operand (GLR_SPLIT8=1): non-verbose states with at most 32 GEMM columns
+  // integer tensor-core operand (split8.cu): non-verbose states with at most 36 GEMM columns
   double* d_colmax = nullptr;
-  if (getenv("GLR_SPLIT8") && atoi(getenv("GLR_SPLIT8")) > 0 && !st->verbose && st->Mcols <= 36 && st->Mcols > 0 &&
-      Ng < (int64_t)8000000) {
-    st->split8 = atoi(getenv("GLR_SPLIT8"));  // 1 = large blocks only, 2 = every PLINK2 block
+  // GLR_SPLIT8: 0 = never, 1 (default) = PLINK2 blocks that fill at least half the SMs, 2 = every PLINK2 block
+  const int split8_mode = getenv("GLR_SPLIT8") ? atoi(getenv("GLR_SPLIT8")) : 1;
+  if (split8_mode > 0 && !st->verbose && st->Mcols <= 36 && st->Mcols > 0 && Ng < (int64_t)8000000) {
+    st->split8 = split8_mode;
     st->s8_cols = st->Mcols;
     st->s8_MB = st->Mcols <= 18 ? 1 : 2;
     st->s8_stages = ceil_div(Ng, 128);

@@ -177,3 +177,69 @@ def test_error_codes(rg):
 def test_smoke_entry_point():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+@pytest.mark.parametrize('N,G,P,K', [(1000, 300, 1, 16), (515, 129, 2, 3), (4099, 1000, 20, 16), (127, 64, 1, 0), (130, 5, 3, 30)])
+def test_int8_split_path_matches_dmma_path_and_oracle(rg, N, G, P, K, monkeypatch):
+    """The tcgen05 int8 digit-split contraction (split8.cu) against the FP64 DMMA path and the oracle:
+    ragged sample / variant counts, unaligned rows, both imputation policies, one and two digit blocks."""
+    from glow_b200 import _capi
+    from glow_b200.engine import GenotypeBlock
+    X = rg.integers(0, 3, (G, N)).astype(np.float64)
+    X[:, 0] = [g % 3 for g in range(G)]
+    X[:, -1] = [(g + 1) % 3 for g in range(G)]
+    states = X.astype(np.int64)
+    states[rg.random((G, N)) < 0.03] = -1
+    states[1, :] = np.where(states[1] == -1, 0, states[1])
+    cov = pd.DataFrame(rg.standard_normal((N, K))) if K else None
+    phe = pd.DataFrame(rg.standard_normal((N, P)))
+    packed = pack_plink(states)
+    monkeypatch.setenv('GLR_SPLIT8', '2')
+    eng8, st = _state(phe, cov)
+    monkeypatch.setenv('GLR_SPLIT8', '0')
+    engd, _ = _state(phe, cov)
+    for policy in ('mean', 'minus_one'):
+        Xo = orc.mean_substitute(states.astype(np.float64)) if policy == 'mean' else states.astype(np.float64)
+        ref = orc.block_stats(Xo, st)
+        r8 = eng8.run(GenotypeBlock(packed, 'plink2', policy))
+        rd = engd.run(GenotypeBlock(packed, 'plink2', policy))
+        assert_stats_close(r8, ref, label=f'split8 {policy}')
+        assert_stats_close(rd, ref, label=f'dmma {policy}')
+        assert_stats_close(r8, rd, label=f'split8 vs dmma {policy}')
+    # rows at an odd byte offset with a padded stride
+    rb = packed.shape[1]
+    buf = np.zeros(G * (rb + 5) + 8, dtype=np.uint8)
+    view = np.lib.stride_tricks.as_strided(buf[3:], shape=(G, rb), strides=(rb + 5, 1))
+    view[:] = packed
+    out = {k: np.empty((P, G)) for k in STATS}
+    bd = _capi.BlockDesc(format=_capi.FMT_PLINK2, memspace=_capi.MEM_HOST, genotypes=buf.ctypes.data + 3,
+                         row_stride_bytes=rb + 5, n_variants=G, contig=0, missing_policy=_capi.MISSING_MEAN)
+    bo = _capi.BlockOut(memspace=_capi.MEM_HOST, **{k: out[k].ctypes.data for k in STATS})
+    _capi.check(_capi.load().glr_run_block(eng8._handle, C.byref(bd), C.byref(bo)))
+    assert_stats_close(out, orc.block_stats(orc.mean_substitute(states.astype(np.float64)), st), label='split8 unaligned')
+    eng8.close()
+    engd.close()
+
+
+def test_int8_split_path_with_dropped_samples_and_loco(rg, monkeypatch):
+    import glow_b200
+    monkeypatch.setenv('GLR_SPLIT8', '2')
+    N, G, P, K = 260, 40, 2, 4
+    samples = [f's{i}' for i in range(N)]
+    states = rg.integers(-1, 3, (G, N))
+    states[:, :3] = [0, 1, 2]
+    keep = [i for i in range(N) if i % 11 != 5]
+    phe = pd.DataFrame(rg.standard_normal((N, P)), index=samples).iloc[keep]
+    cov = pd.DataFrame(rg.standard_normal((N, K)), index=samples)
+    contigs = ['1', '2']
+    off = pd.DataFrame(0.1 * rg.standard_normal((len(keep) * 2, P)), index=pd.MultiIndex.from_product([phe.index, contigs]))
+    meta = pd.DataFrame({'contigName': [contigs[g % 2] for g in range(G)], 'idx': np.arange(G)})
+    src = glow_b200.PlinkBedSource(bytes([0x6c, 0x1b, 0x01]) + pack_plink(states).tobytes(), N, meta, mean_substitute=True)
+    out = glow_b200.gwas.linear_regression(src, phe, cov, off, intersect_samples=True, genotype_sample_ids=samples)
+    X = orc.mean_substitute(states.astype(np.float64))
+    st = orc.prepare_state(phe, cov, off, intersect_samples=True, genotype_sample_ids=samples)
+    pdf = meta.copy()
+    pdf['values'] = list(X)
+    ref = orc.block_frame(pdf, 'values', st)
+    assert out['idx'].tolist() == ref['idx'].tolist()
+    assert_stats_close({k: out[k].to_numpy() for k in STATS}, {k: ref[k].to_numpy() for k in STATS}, label='split8 drop+loco')
