@@ -499,8 +499,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
 
   // ---- plan ----
   const int nt = 2;
-  int warps = (b->format == GLR_FMT_PLINK2 && st->MT <= 4) ? 16 : 8;
-  if (warps == 16 && getenv("GLR_WARPS15")) warps = 15;
+  const int warps = (b->format == GLR_FMT_PLINK2 && st->MT <= 4) ? 16 : 8;
   const int tile = gram_tile_variants(nt, warps);
   const int64_t ldS = std::max(round_up(round_up(G, tile), 8), round_up(G, 256));
   const int64_t ctas = ceil_div(G, tile) * st->n_groups;

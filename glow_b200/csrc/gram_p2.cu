@@ -10,10 +10,6 @@ void launch_gram_p2(const GramParams& p, cudaStream_t st) {
     launch_gram_mt<GLR_FMT_PLINK2, 2, true, 16, 1, 4>(p, st);
     return;
   }
-  if (p.warps == 15) {  // 15 consumers + producer = 512 threads: 128 registers per thread instead of 96
-    launch_gram_mt<GLR_FMT_PLINK2, 2, true, 15, 1, 4>(p, st);
-    return;
-  }
   launch_gram_mt<GLR_FMT_PLINK2, 2, true, 8, 5, 8>(p, st);
 }
 void launch_masked_p2(const MaskedParams& p, cudaStream_t st) { launch_masked_mt<GLR_FMT_PLINK2>(p, st); }

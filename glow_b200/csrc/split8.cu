@@ -6,7 +6,7 @@
 // integers, so the product can be computed EXACTLY with integer tensor-core MMAs (Ozaki-style
 // error-free splitting of the FP64 operand):
 //   * every column of W = [Q(:,1:) | Ytilde] is scaled by its max |w| and rounded to a signed 55-bit
-//     integer (quantum 2^-54 of the column maximum), then written as 7 balanced radix-256 digits
+//     integer (quantum 2^-54 of the column maximum, i.e. an operand error of about one FP64 ulp of the largest entries), then written as 7 balanced radix-256 digits
 //     d_i in [-128, 127]  (int8);
 //   * a genotype row is x = xi + mu * e with xi in {0,1,2} (missing -> 0) and e the missing-call
 //     indicator, both int8;

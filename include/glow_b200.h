@@ -84,6 +84,10 @@ typedef struct glr_state_desc {
   int64_t dof;             /* N - K - 1, lin_reg.py:159 */
   int32_t max_block_variants; /* hint for workspace sizing (grown on demand) */
   int32_t n_lanes;         /* independent in-flight blocks (streams); 0 -> default 2 */
+  /* Environment knobs read at state creation: GLR_SPLIT8 = 0 | 1 (default) | 2 selects the exact int8
+   * tensor-core contraction for PLINK2 blocks never | for blocks filling >= half the SMs | always;
+   * GLR_KEEP_INTERCEPT keeps a constant first column of Q inside the GEMM; GLR_NO_TAIL pads the
+   * column count to a multiple of 8 instead of using FP64-FMA tail columns. */
   int32_t memspace;        /* glr_memspace of Q, Y, Y_mask, YdotY, Y_scale, Y_raw (keep_idx is always
                               host): GLR_MEM_DEVICE lets ranks != 0 build their replica straight
                               from the buffer an NCCL broadcast filled, without a host round trip */
@@ -118,8 +122,8 @@ typedef struct glr_block_out {
 
 typedef struct glr_timing {
   float total_ms;    /* first kernel start -> last kernel end of the block (CUDA events) */
-  float prepass_ms;  /* count / impute pre-pass */
-  float gram_ms;     /* DMMA contraction kernel(s) */
+  float prepass_ms;  /* count / impute pre-pass (0 when the int8 tensor-core kernel counts on the fly) */
+  float gram_ms;     /* contraction kernel(s): FP64 DMMA, or the exact int8 digit-split kernel (2-bit blocks) */
   float masked_ms;   /* masked sum-of-squares kernel (0 when every phenotype is fully observed) */
   float epilogue_ms; /* statistics + p-values */
   int32_t kernel_launches;
