@@ -158,24 +158,24 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer ----
-    // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kS8N >> 3) << 17) | ((uint32_t)(kS8M >> 4) << 24);
-    int sw = 0;  // DW == DX: the two rings advance together
-    uint32_t ph = 0;
-    int tcount = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      // the epilogue of the previous tile must have drained the accumulators
-      if (tcount > 0) mbar_wait(&sm->tmem_empty, (uint32_t)((tcount - 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      for (int64_t k = 0; k < n_st; ++k) {
-        const int sx = sw;
-        mbar_wait(&sm->full_w[sw], ph);
-        mbar_wait(&sm->full_x[sx], ph);
+    // ---- MMA issuer: a single thread runs the whole loop (waits, fences, MMAs, commits); keeping the
+    // other 31 lanes out of it saves a warp re-convergence per stage on the critical issue path ----
+    if (lane == 0) {
+      // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kS8N >> 3) << 17) | ((uint32_t)(kS8M >> 4) << 24);
+      int sw = 0;  // DW == DX: the two rings advance together
+      uint32_t ph = 0;
+      int tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        // the epilogue of the previous tile must have drained the accumulators
+        if (tcount > 0) mbar_wait(&sm->tmem_empty, (uint32_t)((tcount - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        if (lane == 0) {
+        for (int64_t k = 0; k < n_st; ++k) {
+          mbar_wait(&sm->full_w[sw], ph);
+          mbar_wait(&sm->full_x[sw], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint32_t w_addr = smem_u32(w_ring + (size_t)sw * w_bytes);
-          const uint32_t x_addr = smem_u32(x_ring + (size_t)sx * x_bytes);
+          const uint32_t x_addr = smem_u32(x_ring + (size_t)sw * x_bytes);
 #pragma unroll
           for (int kk = 0; kk < kS8K / 32; ++kk) {
             const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
@@ -184,13 +184,12 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
               s8_mma(tmem + mb * kS8N, s8_desc(w_addr + mb * (kS8M * kS8K) + kk * 32), db, idesc, acc);
           }
           s8_commit(&sm->empty_w[sw]);                   // ONE commit per stage (each costs the issuing thread
-                                                         // several hundred cycles): frees both buffers of the stage
+                                                         // ~100 cycles): frees both buffers of the stage
           if (k == n_st - 1) s8_commit(&sm->tmem_full);  // accumulators of the tile are complete
-        }
-        __syncwarp();
-        if (++sw == DW) {
-          sw = 0;
-          ph ^= 1u;
+          if (++sw == DW) {
+            sw = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
