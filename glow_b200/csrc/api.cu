@@ -364,7 +364,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   double* d_colmax = nullptr;
   // GLR_SPLIT8: 0 = never, 1 (default) = PLINK2 blocks that fill at least half the SMs, 2 = every PLINK2 block
   const int split8_mode = getenv("GLR_SPLIT8") ? atoi(getenv("GLR_SPLIT8")) : 1;
-  if (split8_mode > 0 && !st->verbose && st->Mcols <= 36 && st->Mcols > 0 && Ng < (int64_t)8000000) {
+  if (split8_mode > 0 && !st->verbose && st->Mcols <= 36 && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
     st->split8 = split8_mode;
     st->s8_cols = st->Mcols;
     st->s8_MB = st->Mcols <= 18 ? 1 : 2;

@@ -23,7 +23,8 @@
 //
 // CTA roles (384 threads, 1 CTA/SM, persistent over 128-variant tiles):
 //   warp 0    : lane 0 streams the packed digit operand (pre-swizzled image, one bulk copy per stage)
-//   warp 1    : lane 0 issues tcgen05.mma; tcgen05.commit frees the buffers / publishes the accumulators
+//   warps 1, 3: lane 0 of each issues tcgen05.mma for alternate stages; tcgen05.commit frees the buffers /
+//               publishes the accumulators
 //   warp 2    : TMEM allocation / deallocation
 //   warps 4-11: decode the 2-bit rows of the tile into the int8 B operand (xi, e) directly in the
 //               128-byte-swizzled K-major layout the MMA reads, and count the genotype codes on the way;
@@ -95,6 +96,7 @@ struct Split8Smem {
   uint64_t empty_x[kS8MaxRing];
   uint64_t tmem_full;
   uint64_t tmem_empty;
+  uint64_t tile_started;
   uint32_t tmem_base;
   uint32_t pad;
   int32_t counts[2][kS8TileV][4];  // per tile parity: n00, n01 (missing), n10 per variant
@@ -119,8 +121,9 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       mbar_init(&sm->full_x[s], kS8DecodeWarps);
       mbar_init(&sm->empty_x[s], 1);
     }
-    mbar_init(&sm->tmem_full, 1);
+    mbar_init(&sm->tmem_full, 2);   // both MMA issuer threads commit their last stage of the tile
     mbar_init(&sm->tmem_empty, 4);
+    mbar_init(&sm->tile_started, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -157,20 +160,28 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         }
       }
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer: a single thread runs the whole loop (waits, fences, MMAs, commits); keeping the
-    // other 31 lanes out of it saves a warp re-convergence per stage on the critical issue path ----
+  } else if (warp == 1 || warp == 3) {
+    // ---- MMA issuers: two single threads (warp 1 and warp 3, lane 0) take alternate stages, so that one
+    // is issuing while the other is committing / waiting for the next stage's operands.  Integer
+    // accumulation is order independent; the only ordering needed is that the stage that OVERWRITES the
+    // accumulators (first stage of a tile) is issued before the other thread's first stage of that tile. ----
     if (lane == 0) {
+      const int j = warp == 1 ? 0 : 1;
       // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kS8N >> 3) << 17) | ((uint32_t)(kS8M >> 4) << 24);
-      int sw = 0;  // DW == DX: the two rings advance together
-      uint32_t ph = 0;
+      int sw = j % DW;  // ring slot / phase of this thread's next stage (global stage index j, j+2, ...)
+      uint32_t ph = (uint32_t)(j / DW) & 1u;
+      int base_par = 0;  // parity of the global index of the tile's first stage
       int tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        // the epilogue of the previous tile must have drained the accumulators
-        if (tcount > 0) mbar_wait(&sm->tmem_empty, (uint32_t)((tcount - 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        for (int64_t k = 0; k < n_st; ++k) {
+        const int k0 = (j - base_par + 2) & 1;  // first stage of this thread inside the tile
+        for (int64_t k = k0; k < n_st; k += 2) {
+          if (k == 0) {
+            // the epilogue of the previous tile must have drained the accumulators
+            if (tcount > 0) mbar_wait(&sm->tmem_empty, (uint32_t)((tcount - 1) & 1));
+          } else if (k == 1) {
+            mbar_wait(&sm->tile_started, (uint32_t)(tcount & 1));  // stage 0 (overwrite) has been issued
+          }
           mbar_wait(&sm->full_w[sw], ph);
           mbar_wait(&sm->full_x[sw], ph);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -183,14 +194,16 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
             for (int mb = 0; mb < MB; ++mb)
               s8_mma(tmem + mb * kS8N, s8_desc(w_addr + mb * (kS8M * kS8K) + kk * 32), db, idesc, acc);
           }
-          s8_commit(&sm->empty_w[sw]);                   // ONE commit per stage (each costs the issuing thread
-                                                         // ~100 cycles): frees both buffers of the stage
-          if (k == n_st - 1) s8_commit(&sm->tmem_full);  // accumulators of the tile are complete
-          if (++sw == DW) {
-            sw = 0;
+          if (k == 0) mbar_arrive(&sm->tile_started);
+          s8_commit(&sm->empty_w[sw]);                  // ONE commit per stage: frees both buffers of the stage
+          if (k + 2 >= n_st) s8_commit(&sm->tmem_full);  // this thread's last stage of the tile (barrier count 2)
+          sw += 2;
+          while (sw >= DW) {
+            sw -= DW;
             ph ^= 1u;
           }
         }
+        base_par = (base_par + (int)(n_st & 1)) & 1;
       }
     }
   } else if (warp >= kS8FirstDecodeWarp) {
