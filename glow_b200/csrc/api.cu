@@ -61,7 +61,7 @@ struct DevBuf {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
-  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx, s8_scratch;
+  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx;
   bool busy = false;
   bool has_masked = false, has_prepass = false;
   int launches = 0;
@@ -96,9 +96,9 @@ struct glr_state {
   double* wpk = nullptr;  // [C][n_groups][n_chunks][8][MT][64]
   // integer tensor-core variant of pass 1 (PLINK2 blocks): digits of W, see split8.cu
   int split8 = 0;  // 0 = off, 1 = built
-  int s8_cols = 0, s8_MB = 0;
+  int s8_cols = 0, s8_ncb = 0, s8_cpb = 0, s8_NC = 0;  // column blocks, columns per block, digit rows per block
   int64_t s8_stages = 0, s8_contig_bytes = 0;
-  int8_t* w8 = nullptr;       // [C][stage][NB][128]
+  int8_t* w8 = nullptr;       // [C][column block][stage][NC][128]
   double* s8_scale = nullptr; // [C][s8_cols]
   // masked pass
   int U = 0, MT2 = 1, n_groups2 = 0, KT2 = 0;
@@ -158,7 +158,7 @@ int glr_state_destroy(glr_state* st) {
     if (l.stream) cudaStreamSynchronize(l.stream);
     for (auto& e : l.ev)
       if (e) cudaEventDestroy(e);
-    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.mom_part, &l.mom, &l.v1, &l.d_part, &l.d_red, &l.xx, &l.s8_scratch})
+    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.mom_part, &l.mom, &l.v1, &l.d_part, &l.d_red, &l.xx})
       b->release();
     if (l.stream) cudaStreamDestroy(l.stream);
   }
@@ -367,9 +367,9 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   if (split8_mode > 0 && !st->verbose && st->Mcols <= 36 && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
     st->split8 = split8_mode;
     st->s8_cols = st->Mcols;
-    st->s8_MB = st->Mcols <= 18 ? 1 : 2;
+    split8_geometry(st->s8_cols, &st->s8_ncb, &st->s8_cpb, &st->s8_NC);
     st->s8_stages = ceil_div(Ng, 128);
-    st->s8_contig_bytes = st->s8_stages * (int64_t)st->s8_MB * 128 * 128;
+    st->s8_contig_bytes = (int64_t)st->s8_ncb * st->s8_stages * st->s8_NC * 128;
     CU(cudaMalloc(&st->w8, (size_t)C * st->s8_contig_bytes));
     CU(cudaMemsetAsync(st->w8, 0, (size_t)C * st->s8_contig_bytes, s0));
     CU(cudaMalloc(&st->s8_scale, (size_t)C * st->s8_cols * sizeof(double)));
@@ -389,8 +389,8 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     if (st->split8) {
       int8_t* d8 = st->w8 + (int64_t)c * st->s8_contig_bytes;
       if (Kg > 0)
-        launch_pack_split8(dQ, N, K, st->has_icpt, Kg, d_colmax, d_g2r, Ng, d8, 0, st->s8_MB, st->s8_stages, s0);
-      launch_pack_split8(dY, N, P, 0, P, d_colmax + Kg, d_g2r, Ng, d8, Kg, st->s8_MB, st->s8_stages, s0);
+        launch_pack_split8(dQ, N, K, st->has_icpt, Kg, d_colmax, d_g2r, Ng, d8, 0, st->s8_cpb, st->s8_NC, st->s8_stages, s0);
+      launch_pack_split8(dY, N, P, 0, P, d_colmax + Kg, d_g2r, Ng, d8, Kg, st->s8_cpb, st->s8_NC, st->s8_stages, s0);
       CU(cudaMemcpyAsync(st->s8_scale + (int64_t)c * st->s8_cols, d_colmax, (size_t)st->s8_cols * sizeof(double),
                          cudaMemcpyDeviceToDevice, s0));
     }
@@ -550,8 +550,6 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   const bool use_split8 =
       st->split8 && b->format == GLR_FMT_PLINK2 && (st->split8 >= 2 || ceil_div(G, 128) * 2 >= st->sm_count);
   const bool fused_counts = use_split8 && st->n_drop == 0;
-  if (use_split8)
-    if (int rc = L.s8_scratch.ensure(split8_scratch_bytes(st->s8_MB, st->sm_count))) return rc;
   CU(cudaEventRecord(L.ev[0], s));
   // ---- pre-pass (A0): missing substitute + sum of squares from integer counts ----
   if (!float_fmt && !fused_counts) {
@@ -582,15 +580,14 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
     sp.w8 = st->w8 + (int64_t)b->contig * st->s8_contig_bytes;
     sp.scale = st->s8_scale + (int64_t)b->contig * st->s8_cols;
     sp.n_cols = st->s8_cols;
-    sp.MB = st->s8_MB;
-    sp.n_stage_bufs = 0;
-    sp.n_x_bufs = 0;
+    sp.n_cb = st->s8_ncb;
+    sp.cpb = st->s8_cpb;
+    sp.NC = st->s8_NC;
     sp.fused_counts = fused_counts ? 1 : 0;
     sp.missing_policy = b->missing_policy;
     sp.n_stages = st->s8_stages;
     sp.S = L.s_red.as<double>() + (int64_t)st->has_icpt * ldS;
     sp.ldS = ldS;
-    sp.scratch = L.s8_scratch.as<int32_t>();
     sp.v1_out = L.v1.as<double>();
     sp.mom_out = L.mom.as<double>();
     launch_split8(sp, st->sm_count, s);

@@ -45,26 +45,25 @@ void launch_gram(const GramParams& p, cudaStream_t st);
 // ---- pass 1, integer tensor-core variant (PLINK 2-bit only): exact digit-split GEMM on tcgen05 ----
 struct Split8Params {
   BlockView x;           // PLINK2 block; x.v1 = missing substitute per variant (used when !fused_counts)
-  const int8_t* w8;      // packed digits of this contig: [stage][MB*128 rows][128 B], 128-byte swizzled
+  const int8_t* w8;      // packed digits of this contig: [column block][stage][NC rows][128 B], 128-byte swizzled
   const double* scale;   // [n_cols] column scale = max|w_c| * 2^-54
   int32_t n_cols;        // columns of W in the GEMM (7 digit rows each)
-  int32_t MB;            // 128-row digit blocks: 1 (<= 18 columns) or 2 (<= 36)
-  int32_t n_stage_bufs;  // set by the launcher: depth of the digit-operand ring
-  int32_t n_x_bufs;      // set by the launcher: depth of the decoded-genotype ring
+  int32_t n_cb;          // column blocks (1 for <= 18 columns, 2 for <= 36)
+  int32_t cpb;           // columns per block; digit row 7 * cpb of every block is the row of ones
+  int32_t NC;            // digit rows per block = MMA N (multiple of 16, <= 128)
   int32_t fused_counts;  // 1: the kernel derives v1 / sum x^2 / sum x from the codes it decodes (no pre-pass)
   int32_t missing_policy;
-  int64_t n_stages;      // 128-sample stages
+  int64_t n_stages;      // 128-sample stages (>= 2)
   double* S;             // first GEMM row of the S workspace, [n_cols][ldS]
   int64_t ldS;
-  int32_t* scratch;      // [grid][MB*128][256] int32, L2-resident transpose buffer of the epilogue
   double* v1_out;        // [ldS]      (fused_counts)
   double* mom_out;       // [2][ldS]   (fused_counts): sum x^2, sum x
 };
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st);
-size_t split8_scratch_bytes(int MB, int sm_count);
+void split8_geometry(int n_cols, int* n_cb, int* cpb, int* NC);
 void launch_pack_split8(const double* src, int64_t N, int64_t ld, int c0, int ncols, double* colmax_scratch,
-                        const int64_t* geno_to_row, int64_t Ng, int8_t* dst, int dst_col0, int MB, int64_t n_stages,
-                        cudaStream_t st);
+                        const int64_t* geno_to_row, int64_t Ng, int8_t* dst, int dst_col0, int cpb, int NC,
+                        int64_t n_stages, cudaStream_t st);
 
 // ---- pass 2 (only when some phenotype has missing samples): D = Mu^T (X - Q A)^2 ----------------
 struct MaskedParams {
