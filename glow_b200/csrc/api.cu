@@ -360,16 +360,19 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   const size_t w_bytes = (size_t)C * st->w_contig_doubles * sizeof(double);
   CU(cudaMalloc(&st->wpk, w_bytes));
   CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
-  // integer tensor-core operand (split8.cu): non-verbose states with at most 36 GEMM columns
+  // integer tensor-core operand (split8.cu): non-verbose states, any number of columns (blocks of up to 18)
   double* d_colmax = nullptr;
   // GLR_SPLIT8: 0 = never, 1 (default) = PLINK2 blocks that fill at least half the SMs, 2 = every PLINK2 block
   const int split8_mode = getenv("GLR_SPLIT8") ? atoi(getenv("GLR_SPLIT8")) : 1;
-  if (split8_mode > 0 && !st->verbose && st->Mcols <= 36 && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
-    st->split8 = split8_mode;
+  if (split8_mode > 0 && !st->verbose && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
     st->s8_cols = st->Mcols;
     split8_geometry(st->s8_cols, &st->s8_ncb, &st->s8_cpb, &st->s8_NC);
     st->s8_stages = ceil_div(Ng, 128);
     st->s8_contig_bytes = (int64_t)st->s8_ncb * st->s8_stages * st->s8_NC * 128;
+    // the digit image costs about 7.1 bytes per W entry (the FP64 image costs 8): built while it fits 16 GiB
+    if ((int64_t)C * st->s8_contig_bytes <= ((int64_t)16 << 30)) st->split8 = split8_mode;
+  }
+  if (st->split8) {
     CU(cudaMalloc(&st->w8, (size_t)C * st->s8_contig_bytes));
     CU(cudaMemsetAsync(st->w8, 0, (size_t)C * st->s8_contig_bytes, s0));
     CU(cudaMalloc(&st->s8_scale, (size_t)C * st->s8_cols * sizeof(double)));
@@ -548,7 +551,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   x.v1 = L.v1.as<double>();
 
   const bool use_split8 =
-      st->split8 && b->format == GLR_FMT_PLINK2 && (st->split8 >= 2 || ceil_div(G, 128) * 2 >= st->sm_count);
+      st->split8 && b->format == GLR_FMT_PLINK2 && (st->split8 >= 2 || ceil_div(G, 128) * st->s8_ncb * 2 >= st->sm_count);
   const bool fused_counts = use_split8 && st->n_drop == 0;
   CU(cudaEventRecord(L.ev[0], s));
   // ---- pre-pass (A0): missing substitute + sum of squares from integer counts ----

@@ -28,7 +28,8 @@
 // TMEM lane ends up holding every digit sum of ONE variant, so the epilogue recombines in registers.
 // The row of ones yields sum xi and the number of missing calls per variant for free; the count of
 // homozygous-alternate codes (needed for sum x^2) is a popcount in the decode.
-// States with 19..36 columns are processed as two column blocks (the tile's rows are decoded twice).
+// States with more than 18 columns are processed in column blocks of up to 18 (the tile's rows are decoded once
+// per block; the kernel stays MMA-bound).
 //
 // CTA roles (384 threads, 1 CTA/SM, persistent over (128-variant tile, column block) work items):
 //   warp 0    : lane 0 streams the packed digit operand (pre-swizzled image, one bulk copy per stage)
@@ -75,6 +76,20 @@ __device__ __forceinline__ void s8_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
       "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ uint32_t s8_and(uint32_t a, uint32_t m) {
+  uint32_t r;
+  asm("and.b32 %0, %1, %2;\n" : "=r"(r) : "r"(a), "r"(m));
+  return r;
+}
+// mbarrier wait that names the decoded words as read-write operands: their computation cannot be scheduled after it
+__device__ __forceinline__ void s8_wait_keep(uint64_t* bar, uint32_t parity, uint32_t (&a)[32], uint32_t (&b)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8)
+    asm volatile("" : "+r"(a[i]), "+r"(a[i + 1]), "+r"(a[i + 2]), "+r"(a[i + 3]), "+r"(a[i + 4]), "+r"(a[i + 5]), "+r"(a[i + 6]),
+                 "+r"(a[i + 7]), "+r"(b[i]), "+r"(b[i + 1]), "+r"(b[i + 2]), "+r"(b[i + 3]), "+r"(b[i + 4]), "+r"(b[i + 5]),
+                 "+r"(b[i + 6]), "+r"(b[i + 7]));
+  mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void s8_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
                : "memory");
@@ -104,6 +119,20 @@ struct Split8Smem {
   int32_t n00[2][kS8TileV];  // per stage-parity group: homozygous-alternate (code 00) count per variant
 };
 
+// Work-item order.  A round of concurrently running items should touch few distinct digit blocks (128 N bytes
+// each) AND few distinct genotype tiles (32 N bytes each): column blocks are taken in groups of kS8CbGroup, and
+// inside a group the items run tile-major, so that a wave of 148 CTAs shares ~6 digit blocks and ~25 tiles through L2.
+constexpr int kS8CbGroup = 6;
+__device__ __forceinline__ void s8_item(int item, int n_tiles, int n_cb, int& tile, int& cb) {
+  const int per_group = n_tiles * kS8CbGroup;
+  const int grp = item / per_group, rem = item - grp * per_group;
+  const int gsz = min(kS8CbGroup, n_cb - grp * kS8CbGroup);  // the last group may be smaller
+  tile = rem / gsz;
+  cb = grp * kS8CbGroup + (rem - tile * gsz);
+}
+
+// kAligned: every row starts on a 4-byte boundary (base and stride multiples of 4): no funnel shifts.
+template <bool kAligned>
 __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NC = p.NC;
@@ -144,12 +173,18 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     if (lane == 0) {
       uint32_t g = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int8_t* src = p.w8 + (int64_t)(item % p.n_cb) * n_st * w_bytes;
+        int tile, cb;
+        s8_item(item, n_tiles, p.n_cb, tile, cb);
+        const int8_t* src = p.w8 + (int64_t)cb * n_st * w_bytes;
         for (int64_t k = 0; k < n_st; ++k, ++g) {
           const uint32_t s = g & (kS8WRing - 1);
           if (g >= (uint32_t)kS8WRing) mbar_wait_backoff(&sm->done[s], ((g >> 3) & 1u) ^ 1u);  // stage g - 8 consumed
+#ifdef GLR_S8_DBG_NOW
+          mbar_arrive(&sm->full_w[s]);
+#else
           mbar_expect_tx(&sm->full_w[s], w_bytes);
           bulk_g2s(w_ring + (size_t)s * w_bytes, src + k * w_bytes, w_bytes, &sm->full_w[s]);
+#endif
         }
       }
     }
@@ -205,7 +240,8 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     uint32_t g0 = 0;
     int icount = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
-      const int tile = item / p.n_cb, cb = item - tile * p.n_cb;
+      int tile, cb;
+      s8_item(item, n_tiles, p.n_cb, tile, cb);
       const int v = min(tile * kS8TileV + vloc, p.x.n_variants - 1);
       const uint8_t* row = p.x.base + (int64_t)v * p.x.stride;
       uint32_t nxt[kS8Words + 1];
@@ -214,7 +250,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         const int64_t b0 = k * 32;
         if (b0 + 4 * kS8Words + 3 <= full_bytes) {  // every word touched lies inside the whole bytes of the row
           const uint8_t* q8 = row + b0;
-          const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(q8) & 3);
+          const uint32_t a = kAligned ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(q8) & 3);
           const uint32_t* qw = reinterpret_cast<const uint32_t*>(q8 - a);
 #pragma unroll
           for (int i = 0; i < kS8Words; ++i) nxt[i] = __ldg(qw + i);
@@ -253,41 +289,48 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         const uint32_t g = g0 + (uint32_t)k;
         uint32_t w[kS8Words];
 #pragma unroll
-        for (int i = 0; i < kS8Words; ++i) w[i] = __funnelshift_r(nxt[i], nxt[i + 1], sh_nxt);
+        for (int i = 0; i < kS8Words; ++i) w[i] = kAligned ? nxt[i] : __funnelshift_r(nxt[i], nxt[i + 1], sh_nxt);
         if (k + 2 < n_st) load(k + 2);
         if ((k & 3) == 0 && (k + 16) * 32 < row_bytes)
           asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (k + 16) * 32));
+        // decode into registers first, THEN wait for the TMEM slot: the slot frees up when the MMAs of stage g - 4
+        // complete, and the hand-off back to the issuer must not include the decode arithmetic
+        uint32_t xs[32], es[32];
+#ifdef GLR_S8_DBG_NODECODE
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xs[i] = es[i] = w[0];
+#else
+#pragma unroll
+        for (int i = 0; i < kS8Words; ++i) {
+          const uint32_t ww = w[i];
+          n00 += __popc(~(ww | (ww << 1)) & 0xAAAAAAAAu);  // both bits of a code clear (left shift: FMA pipe, not ALU)
+          // PRMT selectors: nibble n of `ev` = code 2n (bit 2 is a stray bit of the neighbouring code: the table
+          // is passed in both source registers, so it does not matter; bit 3 must be clear), of `od` = code 2n+1.
+          // Sample order inside a 16-sample group is therefore 0,2,4,6 | 8,10,12,14 | 1,3,5,7 | 9,11,13,15;
+          // the digit operand is packed with the same permutation (pack_split8_kernel).
+          // (masks through opaque asm: otherwise the compiler rewrites (w & m) >> 16 into two more mask operations)
+          const uint32_t ev = s8_and(ww, 0x77777777u), od = s8_and(ww >> 2, 0x77777777u);
+          const uint32_t ev_hi = ev >> 16, od_hi = od >> 16;
+          // code 00 -> 2, 01 -> 0 (missing), 10 -> 1, 11 -> 0;  e: code 01 -> 1
+          xs[4 * i + 0] = __byte_perm(0x00010002u, 0x00010002u, ev);
+          xs[4 * i + 1] = __byte_perm(0x00010002u, 0x00010002u, ev_hi);
+          xs[4 * i + 2] = __byte_perm(0x00010002u, 0x00010002u, od);
+          xs[4 * i + 3] = __byte_perm(0x00010002u, 0x00010002u, od_hi);
+          es[4 * i + 0] = __byte_perm(0x00000100u, 0x00000100u, ev);
+          es[4 * i + 1] = __byte_perm(0x00000100u, 0x00000100u, ev_hi);
+          es[4 * i + 2] = __byte_perm(0x00000100u, 0x00000100u, od);
+          es[4 * i + 3] = __byte_perm(0x00000100u, 0x00000100u, od_hi);
+        }
+#endif
         const uint32_t sa = g & (kS8ARing - 1);
         // the MMAs that read this TMEM slot last (stage g - 4) must have completed
-        if (g >= (uint32_t)kS8ARing) mbar_wait(&sm->done[(g - kS8ARing) & (kS8WRing - 1)], ((g - kS8ARing) >> 3) & 1u);
+        if (g >= (uint32_t)kS8ARing) s8_wait_keep(&sm->done[(g - kS8ARing) & (kS8WRing - 1)], ((g - kS8ARing) >> 3) & 1u, xs, es);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t a_x = lane_addr + kS8ColA + sa * 64, a_e = a_x + 32;
-#pragma unroll
-        for (int hw = 0; hw < 2; ++hw) {  // 4 words = 64 samples = 16 + 16 TMEM words at a time
-          uint32_t xs[16], es[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t ww = w[hw * 4 + i];
-            n00 += __popc(~(ww | (ww >> 1)) & 0x55555555u);
-            // PRMT selectors: nibble n of `ev` = code 2n (bit 2 is a stray bit of the neighbouring code: the table
-            // is passed in both source registers, so it does not matter; bit 3 must be clear), of `od` = code 2n+1.
-            // Sample order inside a 16-sample group is therefore 0,2,4,6 | 8,10,12,14 | 1,3,5,7 | 9,11,13,15;
-            // the digit operand is packed with the same permutation (pack_split8_kernel).
-            const uint32_t ev = ww & 0x77777777u, od = (ww >> 2) & 0x77777777u;
-            const uint32_t ev_hi = ev >> 16, od_hi = od >> 16;
-            // code 00 -> 2, 01 -> 0 (missing), 10 -> 1, 11 -> 0;  e: code 01 -> 1
-            xs[4 * i + 0] = __byte_perm(0x00010002u, 0x00010002u, ev);
-            xs[4 * i + 1] = __byte_perm(0x00010002u, 0x00010002u, ev_hi);
-            xs[4 * i + 2] = __byte_perm(0x00010002u, 0x00010002u, od);
-            xs[4 * i + 3] = __byte_perm(0x00010002u, 0x00010002u, od_hi);
-            es[4 * i + 0] = __byte_perm(0x00000100u, 0x00000100u, ev);
-            es[4 * i + 1] = __byte_perm(0x00000100u, 0x00000100u, ev_hi);
-            es[4 * i + 2] = __byte_perm(0x00000100u, 0x00000100u, od);
-            es[4 * i + 3] = __byte_perm(0x00000100u, 0x00000100u, od_hi);
-          }
-          tmem_st16(a_x + hw * 16, xs);
-          tmem_st16(a_e + hw * 16, es);
-        }
+        tmem_st16(a_x, xs);
+        tmem_st16(a_x + 16, xs + 16);
+        tmem_st16(a_e, es);
+        tmem_st16(a_e + 16, es + 16);
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
@@ -355,8 +398,10 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;
   const int n_items = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb;
   const size_t smem = (size_t)kS8WRing * p.NC * kS8K + sizeof(Split8Smem) + 64;
-  cudaFuncSetAttribute(split8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  split8_kernel<<<std::min(n_items, sm_count), kS8Threads, smem, st>>>(p);
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.x.base) & 3) == 0 && (p.x.stride & 3) == 0;
+  auto kern = aligned ? split8_kernel<true> : split8_kernel<false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<std::min(n_items, sm_count), kS8Threads, smem, st>>>(p);
 }
 
 // ------------------------------------------------------------------------------------------------

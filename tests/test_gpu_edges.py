@@ -179,10 +179,11 @@ def test_smoke_entry_point():
     ge.smoke()
 
 
-@pytest.mark.parametrize('N,G,P,K', [(1000, 300, 1, 16), (515, 129, 2, 3), (4099, 1000, 20, 16), (127, 64, 1, 0), (130, 5, 3, 30)])
+@pytest.mark.parametrize('N,G,P,K', [(1000, 300, 1, 16), (515, 129, 2, 3), (4099, 1000, 20, 16), (127, 64, 1, 0), (130, 5, 3, 30),
+                                     (700, 260, 45, 16), (300, 129, 19, 0)])
 def test_int8_split_path_matches_dmma_path_and_oracle(rg, N, G, P, K, monkeypatch):
     """The tcgen05 int8 digit-split contraction (split8.cu) against the FP64 DMMA path and the oracle:
-    ragged sample / variant counts, unaligned rows, both imputation policies, one and two digit blocks."""
+    ragged sample / variant counts, unaligned rows, both imputation policies, one to four column blocks."""
     from glow_b200 import _capi
     from glow_b200.engine import GenotypeBlock
     X = rg.integers(0, 3, (G, N)).astype(np.float64)
