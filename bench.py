@@ -476,20 +476,26 @@ def main():
         gram_s = stage['gram_ms'] / 1e3
         # int8 digit-split kernel: 7 digit rows per column, two int8 operands (genotype, missing indicator)
         ops_int8 = 2.0 * n * (7 * cols) * 2 * G
-        mb = 1 if cols <= 18 else 2
-        ops_int8_issued = 2.0 * (-(-n // 128) * 128) * (128 * mb) * 256 * (-(-G // 128))
+        n_cb = -(-cols // 18)                                     # column blocks of up to 18 columns
+        nc_rows = -(-(7 * -(-cols // n_cb) + 1) // 16) * 16       # digit rows per block incl. the row of ones = MMA N
+        ops_int8_issued = 2.0 * (-(-n // 128) * 128) * nc_rows * n_cb * 2 * (-(-G // 128) * 128)
         achieved = ops_int8 / gram_s / 1e12
         roof = {
-            'kernel': 'split8_kernel (tcgen05.mma kind::i8 M128 N256 K32, accumulators in TMEM; exact 7-digit radix-256 '
-                      'split of the FP64 operand, 2-bit decode + genotype counts fused, FP64 recombination in the epilogue)',
+            'kernel': 'split8_kernel (tcgen05.mma kind::i8, A = decoded genotypes of 128 variants in TMEM, B = digit rows in '
+                      'shared memory, M128 N128 K32, accumulators in TMEM; exact 7-digit radix-256 split of the FP64 operand, '
+                      '2-bit decode + genotype counts fused, FP64 recombination in the epilogue)',
             'bound': 'tensor',
             'achieved': achieved,
             'peak': int8_peak,
             'unit': 'TFLOP/s',
             'op_type': 'int8 tensor-core operations (2 per multiply-accumulate), algorithmic = digit rows actually needed',
             'frac': achieved / int8_peak,
-            'traffic': None,
+            # dram bytes of one launch at the default shape, ncu --set full, profiles/r01_split8_full.txt
+            'traffic': 4.876e9 if (n == N_SAMPLES and G == 148 * 256) else None,
             'peak_source': int8_src,
+            # back-to-back tcgen05.mma kind::i8 from one thread per SM, operands resident (benchmarks/micro/umma_i8_ts.cu):
+            # 64 clk per M128 N128 K32 = 4.34 Pop/s in a 0.6 ms burst; a library GEMM and this kernel both run below it
+            'frac_of_mma_issue_rate': achieved / 4340.0,
             'ops_per_launch_algorithmic': ops_int8,
             'issued_tops_incl_padding': ops_int8_issued / gram_s / 1e12,
             'fp64_equivalent_tflops': flops_f64_equiv / gram_s / 1e12,
@@ -516,8 +522,8 @@ def main():
         dmma_cols = (cols // 8) * 8 if 1 <= cols % 8 <= 3 and cols // 8 >= 1 else ((cols + 7) // 8) * 8
         d_s = stage_dmma['gram_ms'] / 1e3
         dmma = {
-            'note': 'same batch through the FP64 tensor-core path (GLR_SPLIT8=0): what float / dosage input, more than '
-                    '36 columns or small blocks use',
+            'note': 'same batch through the FP64 tensor-core path (GLR_SPLIT8=0): what float / dosage input, verbose '
+                    'states and small blocks use',
             'value': world * G * P / (ms_dmma / 1e3),
             'unit': 'tests/s',
             'ms_per_step': ms_dmma,

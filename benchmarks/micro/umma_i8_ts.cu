@@ -212,8 +212,7 @@ __global__ void __launch_bounds__(384, 1) ts_rate(int iters, int st_mode, long l
 }
 
 template <int N, int NISS>
-void rate(int st_mode) {
-  const int iters = 2000;
+void rate(int st_mode, int iters = 2000) {
   long long* d;
   cudaMalloc(&d, 148 * 8);
   const size_t smem = (size_t)2 * N * 128 + 384 * 16 + 1024;
@@ -232,8 +231,8 @@ void rate(int st_mode) {
   cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
   const int per_it = (2 * N <= 480) ? 8 : 4;
   const double macs = 148.0 * iters * per_it * 128.0 * N * 32;
-  printf("TS rate N=%3d issuers=%d st_mode=%d  %s  %.3f ms  %.0f clk/MMA  %.2f Pop/s\n", N, NISS, st_mode, cudaGetErrorString(e), ms,
-         (double)c / (iters * (double)per_it), 2 * macs / ms / 1e12);
+  printf("TS rate N=%3d issuers=%d st_mode=%d iters=%d  %s  %.3f ms  %.1f clk/MMA  %.2f Pop/s  SM clock %.0f MHz\n", N, NISS, st_mode,
+         iters, cudaGetErrorString(e), ms, (double)c / (iters * (double)per_it), 2 * macs / ms / 1e12, (double)c / ms / 1e3);
   cudaFree(d);
 }
 
@@ -246,5 +245,9 @@ int main() {
   rate<256, 1>(0);
   rate<256, 1>(1);
   rate<64, 1>(0);
+  rate<128, 2>(0, 20000);  // ~6 ms: long enough for the power management to react
+  rate<128, 2>(3, 100000);
+  rate<112, 1>(0);
+  rate<96, 1>(0);
   return bad;
 }

@@ -41,6 +41,7 @@
 //               TMEM words per stage.  All 8 warps run the epilogue (tcgen05.ld of the variant's digit
 //               sums, FP64 recombination, coalesced store of S).
 #include <algorithm>
+#include <cstdio>
 
 #include "../../include/glow_b200.h"
 #include "common.cuh"
@@ -90,6 +91,17 @@ __device__ __forceinline__ void s8_wait_keep(uint64_t* bar, uint32_t parity, uin
                  "+r"(b[i + 6]), "+r"(b[i + 7]));
   mbar_wait(bar, parity);
 }
+__device__ __forceinline__ bool s8_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void s8_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
                : "memory");
@@ -130,6 +142,15 @@ __device__ __forceinline__ void s8_item(int item, int n_tiles, int n_cb, int& ti
   tile = rem / gsz;
   cb = grp * kS8CbGroup + (rem - tile * gsz);
 }
+
+#ifdef GLR_S8_PROFILE
+__device__ long long g_s8_prof[160][3][8];  // [cta][issuer 0 / issuer 1 / decode warp 4][phase] clock64 sums
+#define S8_T(var) const long long var = clock64()
+#define S8_ACC(role, slot, t1, t0) g_s8_prof[blockIdx.x][role][slot] += (t1) - (t0)
+#else
+#define S8_T(var)
+#define S8_ACC(role, slot, t1, t0)
+#endif
 
 // kAligned: every row starts on a 4-byte boundary (base and stride multiples of 4): no funnel shifts.
 template <bool kAligned>
@@ -189,19 +210,24 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       }
     }
   } else if (warp == 1 || warp == 3) {
-    // ---- MMA issuers: two single threads take alternate stages, so that one is issuing while the other is
+    // ---- MMA issuers: two warps take alternate stages, so that one is issuing while the other is
     // committing / waiting for the next stage's operands.  Integer accumulation is order independent; the only
     // ordering needed is that the stage that OVERWRITES the accumulators (first stage of an item) is issued
     // before the other thread's first stage of that item. ----
-    if (lane == 0) {
-      const uint32_t j = warp == 1 ? 0u : 1u;
+    // The whole warp runs the loop CONVERGED (warp-uniform indices, addresses and barrier polls live in uniform
+    // registers); only the tcgen05 instructions themselves are issued by one elected lane.
+    {
+      const uint32_t j = __shfl_sync(0xffffffffu, warp, 0) == 1 ? 0u : 1u;
       // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(kS8TileV >> 4) << 24);
+      const uint32_t w_ring_addr = smem_u32(w_ring);
+      const int n_st32 = (int)n_st;
       uint32_t g0 = 0;  // global index of the item's first stage
       int icount = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
-        for (int64_t k = (j ^ g0) & 1u; k < n_st; k += kS8Issuers) {
+        for (int k = (int)((j ^ g0) & 1u); k < n_st32; k += kS8Issuers) {
           const uint32_t g = g0 + (uint32_t)k;
+          S8_T(t0);
           if (k == 0) {
             // the epilogue of the previous item must have drained the accumulators
             if (icount > 0) mbar_wait(&sm->tmem_empty, (uint32_t)((icount - 1) & 1));
@@ -209,23 +235,38 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
             mbar_wait(&sm->tile_started, (uint32_t)(icount & 1));  // stage 0 (overwrite) has been issued
           }
           const uint32_t sw = g & (kS8WRing - 1), sa = g & (kS8ARing - 1);
+          S8_T(t1);
           mbar_wait(&sm->full_w[sw], (g >> 3) & 1u);
+          S8_T(t2);
           mbar_wait(&sm->full_a[sa], (g >> 2) & 1u);
+          S8_T(t3);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t w_addr = smem_u32(w_ring + (size_t)sw * w_bytes);
+          // descriptor of the stage's digit rows: only the start-address field changes (units of 16 bytes)
+          const uint64_t db0 = s8_desc(w_ring_addr + sw * w_bytes);
           const uint32_t a_x = tmem + kS8ColA + sa * 64, a_e = a_x + 32;
+          if (s8_elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kS8K / 32; ++kk) {
-            const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
-            const uint64_t db = s8_desc(w_addr + kk * 32);
-            s8_mma_ts(tmem, a_x + kk * 8, db, idesc, acc);
-            s8_mma_ts(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
+            for (int kk = 0; kk < kS8K / 32; ++kk) {
+              const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+              const uint64_t db = db0 + (uint64_t)(kk * 2);
+              s8_mma_ts(tmem, a_x + kk * 8, db, idesc, acc);
+              s8_mma_ts(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
+            }
+            if (k == 0) mbar_arrive(&sm->tile_started);
+            S8_T(t4);
+            s8_commit(&sm->done[sw]);                                 // ONE commit per stage: frees both operands of the stage
+            if (k + kS8Issuers >= n_st32) s8_commit(&sm->tmem_full);  // this warp's last stage of the item
+            S8_T(t5);
+            S8_ACC(j, 0, t1, t0);
+            S8_ACC(j, 1, t2, t1);
+            S8_ACC(j, 2, t3, t2);
+            S8_ACC(j, 3, t4, t3);
+            S8_ACC(j, 4, t5, t4);
+            S8_ACC(j, 5, 1, 0);
           }
-          if (k == 0) mbar_arrive(&sm->tile_started);
-          s8_commit(&sm->done[sw]);                               // ONE commit per stage: frees both operands of the stage
-          if (k + kS8Issuers >= n_st) s8_commit(&sm->tmem_full);  // this thread's last stage of the item
+          __syncwarp();
         }
-        g0 += (uint32_t)n_st;
+        g0 += (uint32_t)n_st32;
       }
     }
   } else if (warp >= kS8FirstDecodeWarp) {
@@ -287,6 +328,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       load(k_first);
       for (int64_t k = k_first; k < n_st; k += 2) {
         const uint32_t g = g0 + (uint32_t)k;
+        S8_T(d0);
         uint32_t w[kS8Words];
 #pragma unroll
         for (int i = 0; i < kS8Words; ++i) w[i] = kAligned ? nxt[i] : __funnelshift_r(nxt[i], nxt[i + 1], sh_nxt);
@@ -323,8 +365,10 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         }
 #endif
         const uint32_t sa = g & (kS8ARing - 1);
+        S8_T(d1);
         // the MMAs that read this TMEM slot last (stage g - 4) must have completed
         if (g >= (uint32_t)kS8ARing) s8_wait_keep(&sm->done[(g - kS8ARing) & (kS8WRing - 1)], ((g - kS8ARing) >> 3) & 1u, xs, es);
+        S8_T(d2);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t a_x = lane_addr + kS8ColA + sa * 64, a_e = a_x + 32;
         tmem_st16(a_x, xs);
@@ -335,6 +379,15 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->full_a[sa]);
+#ifdef GLR_S8_PROFILE
+        if (warp == kS8FirstDecodeWarp && lane == 0) {
+          S8_T(d3);
+          S8_ACC(2, 0, d1, d0);
+          S8_ACC(2, 1, d2, d1);
+          S8_ACC(2, 2, d3, d2);
+          S8_ACC(2, 5, 1, 0);
+        }
+#endif
       }
       sm->n00[grp][vloc] = n00;
       asm volatile("bar.sync 1, 256;\n" ::: "memory");  // all decode warps: both groups' counts are in shared memory
@@ -401,7 +454,27 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   const bool aligned = (reinterpret_cast<uintptr_t>(p.x.base) & 3) == 0 && (p.x.stride & 3) == 0;
   auto kern = aligned ? split8_kernel<true> : split8_kernel<false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#ifdef GLR_S8_PROFILE
+  static long long zero[160][3][8];
+  cudaMemcpyToSymbol(g_s8_prof, zero, sizeof(zero));
+#endif
   kern<<<std::min(n_items, sm_count), kS8Threads, smem, st>>>(p);
+#ifdef GLR_S8_PROFILE
+  static long long h[160][3][8];
+  cudaStreamSynchronize(st);
+  cudaMemcpyFromSymbol(h, g_s8_prof, sizeof(h));
+  const int nc = std::min(n_items, sm_count);
+  const char* names[3] = {"issuer0", "issuer1", "decode4"};
+  for (int r = 0; r < 3; ++r) {
+    double a[8] = {0};
+    for (int c = 0; c < nc; ++c)
+      for (int i = 0; i < 8; ++i) a[i] += (double)h[c][r][i];
+    const double n = a[5] > 0 ? a[5] : 1;
+    fprintf(stderr, "[s8 prof] %s stages/cta %.0f  clk/stage:", names[r], a[5] / nc);
+    for (int i = 0; i < 5; ++i) fprintf(stderr, " %.0f", a[i] / n);
+    fprintf(stderr, "\n");
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
