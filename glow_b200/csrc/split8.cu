@@ -42,6 +42,7 @@
 //               sums, FP64 recombination, coalesced store of S).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/glow_b200.h"
 #include "common.cuh"
@@ -91,6 +92,45 @@ __device__ __forceinline__ void s8_wait_keep(uint64_t* bar, uint32_t parity, uin
                  "+r"(b[i + 6]), "+r"(b[i + 7]));
   mbar_wait(bar, parity);
 }
+// ---- CTA-pair (cta_group::2) forms: one MMA drives the tensor cores of both SMs of a TPC; each CTA holds its own 128
+// variants (A, D in its TMEM) and HALF of the digit rows (B) in its shared memory ----
+__device__ __forceinline__ void s8_mma_ts2(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of the pair, signalled on the same barrier offset in BOTH CTAs
+__device__ __forceinline__ void s8_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t s8_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void s8_arrive_cta(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  // default (cta-scope release) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id): a cluster-scope release turns
+  // into a full memory barrier that waits for the decode's prefetch loads in flight (measured: 1400 clk per arrive);
+  // the data handed over lives in TMEM / async-proxy shared memory and is ordered by the tcgen05 fences
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
+}
+// wait on a barrier whose arrivals come from both CTAs of the pair
+__device__ __forceinline__ void s8_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void s8_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ bool s8_elect_one() {
   uint32_t pred;
   asm volatile(
@@ -126,6 +166,7 @@ struct Split8Smem {
   uint64_t tmem_full;
   uint64_t tmem_empty;
   uint64_t tile_started;
+  uint64_t peer_w[kS8WRing];  // pair mode, leader: the peer CTA's half of a digit stage has landed
   uint32_t tmem_base;
   uint32_t pad;
   int32_t n00[2][kS8TileV];  // per stage-parity group: homozygous-alternate (code 00) count per variant
@@ -153,11 +194,17 @@ __device__ long long g_s8_prof[160][3][8];  // [cta][issuer 0 / issuer 1 / decod
 #endif
 
 // kAligned: every row starts on a 4-byte boundary (base and stride multiples of 4): no funnel shifts.
-template <bool kAligned>
+// kPair: CTA pairs (cluster of 2, cta_group::2): a pair works on 256 variants and shares one copy of every digit
+// stage (each CTA loads and holds half of the rows), which halves the shared-memory and L2 traffic of the digit stream.
+// Only the leader (rank 0) issues MMAs; barriers the leader waits on collect arrivals from both CTAs, and the MMA
+// completion is multicast to both.
+template <bool kAligned, bool kPair>
 __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NC = p.NC;
-  const uint32_t w_bytes = (uint32_t)NC * kS8K;
+  const uint32_t rank = kPair ? s8_cta_rank() : 0u;
+  const uint32_t w_stage_bytes = (uint32_t)NC * kS8K;                   // a whole digit stage in the packed image
+  const uint32_t w_bytes = kPair ? w_stage_bytes / 2 : w_stage_bytes;   // what this CTA holds of it
   unsigned char* w_ring = smem_raw;  // 1024-byte aligned operand buffers first, bookkeeping after
   Split8Smem* sm = reinterpret_cast<Split8Smem*>(w_ring + (size_t)kS8WRing * w_bytes);
 
@@ -167,24 +214,35 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       mbar_init(&sm->full_w[s], 1);
       mbar_init(&sm->done[s], 1);
     }
-    for (int s = 0; s < kS8ARing; ++s) mbar_init(&sm->full_a[s], kS8DecodeWarps / 2);
+    for (int s = 0; s < kS8WRing; ++s) mbar_init(&sm->peer_w[s], 1);
+    for (int s = 0; s < kS8ARing; ++s) mbar_init(&sm->full_a[s], (kPair ? 2 : 1) * kS8DecodeWarps / 2);
     mbar_init(&sm->tmem_full, kS8Issuers);  // every MMA issuer thread commits its last stage of the item
-    mbar_init(&sm->tmem_empty, kS8DecodeWarps);
+    mbar_init(&sm->tmem_empty, (kPair ? 2 : 1) * kS8DecodeWarps);
     mbar_init(&sm->tile_started, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm->tmem_base)),
-                 "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm->tmem_base)),
+                   "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm->tmem_base)),
+                   "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
+  if (kPair) s8_cluster_sync(); else __syncthreads();  // barriers of BOTH CTAs are initialised before any remote arrive
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = sm->tmem_base;
 
-  const int n_tiles = (p.x.n_variants + kS8TileV - 1) / kS8TileV;
-  const int n_items = n_tiles * p.n_cb;  // work item = (tile, column block)
+  // a work unit (one CTA, or one CTA pair) takes items first_item, first_item + item_stride, ...
+  const int tile_v = kPair ? 2 * kS8TileV : kS8TileV;
+  const int n_tiles = (p.x.n_variants + tile_v - 1) / tile_v;
+  const int n_items = n_tiles * p.n_cb;  // work item = (tile [pair], column block)
+  const int first_item = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int64_t n_st = p.n_stages;       // 128-sample stages covering the genotype samples (>= 2)
 
   // Every role walks the same sequence of stages; g = running ("global") stage index of this CTA.  Ring slots and
@@ -193,10 +251,10 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     // ---- digit-operand producer ----
     if (lane == 0) {
       uint32_t g = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = first_item; item < n_items; item += item_stride) {
         int tile, cb;
         s8_item(item, n_tiles, p.n_cb, tile, cb);
-        const int8_t* src = p.w8 + (int64_t)cb * n_st * w_bytes;
+        const int8_t* src = p.w8 + (int64_t)cb * n_st * w_stage_bytes + rank * w_bytes;  // pair: rows [rank NC/2, ..)
         for (int64_t k = 0; k < n_st; ++k, ++g) {
           const uint32_t s = g & (kS8WRing - 1);
           if (g >= (uint32_t)kS8WRing) mbar_wait_backoff(&sm->done[s], ((g >> 3) & 1u) ^ 1u);  // stage g - 8 consumed
@@ -204,7 +262,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           mbar_arrive(&sm->full_w[s]);
 #else
           mbar_expect_tx(&sm->full_w[s], w_bytes);
-          bulk_g2s(w_ring + (size_t)s * w_bytes, src + k * w_bytes, w_bytes, &sm->full_w[s]);
+          bulk_g2s(w_ring + (size_t)s * w_bytes, src + k * w_stage_bytes, w_bytes, &sm->full_w[s]);
 #endif
         }
       }
@@ -216,29 +274,50 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     // before the other thread's first stage of that item. ----
     // The whole warp runs the loop CONVERGED (warp-uniform indices, addresses and barrier polls live in uniform
     // registers); only the tcgen05 instructions themselves are issued by one elected lane.
-    {
+    if (kPair && rank != 0) {
+      // peer CTA of a pair: no MMAs to issue; these two warps forward "my half of digit stage g has landed" to the leader
+      const uint32_t j = __shfl_sync(0xffffffffu, warp, 0) == 1 ? 0u : 1u;
+      const int n_st32 = (int)n_st;
+      uint32_t g0 = 0;
+      for (int item = first_item; item < n_items; item += item_stride) {
+        for (int k = (int)((j ^ g0) & 1u); k < n_st32; k += kS8Issuers) {
+          const uint32_t g = g0 + (uint32_t)k;
+          const uint32_t sw = g & (kS8WRing - 1);
+          mbar_wait(&sm->full_w[sw], (g >> 3) & 1u);
+          if (lane == 0) s8_arrive_cta(&sm->peer_w[sw], 0);
+          __syncwarp();
+        }
+        g0 += (uint32_t)n_st32;
+      }
+    } else {
       const uint32_t j = __shfl_sync(0xffffffffu, warp, 0) == 1 ? 0u : 1u;
       // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(kS8TileV >> 4) << 24);
+      const uint32_t idesc =
+          (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)((kPair ? 2 : 1) * kS8TileV >> 4) << 24);
       const uint32_t w_ring_addr = smem_u32(w_ring);
       const int n_st32 = (int)n_st;
       uint32_t g0 = 0;  // global index of the item's first stage
       int icount = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
+      for (int item = first_item; item < n_items; item += item_stride, ++icount) {
         for (int k = (int)((j ^ g0) & 1u); k < n_st32; k += kS8Issuers) {
           const uint32_t g = g0 + (uint32_t)k;
           S8_T(t0);
           if (k == 0) {
             // the epilogue of the previous item must have drained the accumulators
-            if (icount > 0) mbar_wait(&sm->tmem_empty, (uint32_t)((icount - 1) & 1));
+            if (icount > 0) {
+              if (kPair) s8_wait_cluster(&sm->tmem_empty, (uint32_t)((icount - 1) & 1));
+              else mbar_wait(&sm->tmem_empty, (uint32_t)((icount - 1) & 1));
+            }
           } else if (k < kS8Issuers) {
             mbar_wait(&sm->tile_started, (uint32_t)(icount & 1));  // stage 0 (overwrite) has been issued
           }
           const uint32_t sw = g & (kS8WRing - 1), sa = g & (kS8ARing - 1);
           S8_T(t1);
           mbar_wait(&sm->full_w[sw], (g >> 3) & 1u);
+          if (kPair) s8_wait_cluster(&sm->peer_w[sw], (g >> 3) & 1u);
           S8_T(t2);
-          mbar_wait(&sm->full_a[sa], (g >> 2) & 1u);
+          if (kPair) s8_wait_cluster(&sm->full_a[sa], (g >> 2) & 1u);
+          else mbar_wait(&sm->full_a[sa], (g >> 2) & 1u);
           S8_T(t3);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           // descriptor of the stage's digit rows: only the start-address field changes (units of 16 bytes)
@@ -249,13 +328,25 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
             for (int kk = 0; kk < kS8K / 32; ++kk) {
               const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
               const uint64_t db = db0 + (uint64_t)(kk * 2);
-              s8_mma_ts(tmem, a_x + kk * 8, db, idesc, acc);
-              s8_mma_ts(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
+              if (kPair) {
+                s8_mma_ts2(tmem, a_x + kk * 8, db, idesc, acc);
+                s8_mma_ts2(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
+              } else {
+                s8_mma_ts(tmem, a_x + kk * 8, db, idesc, acc);
+                s8_mma_ts(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
+              }
             }
             if (k == 0) mbar_arrive(&sm->tile_started);
             S8_T(t4);
-            s8_commit(&sm->done[sw]);                                 // ONE commit per stage: frees both operands of the stage
-            if (k + kS8Issuers >= n_st32) s8_commit(&sm->tmem_full);  // this warp's last stage of the item
+            // ONE commit per stage frees both operands of the stage; after this warp's last stage of the item a
+            // second one publishes the accumulators (pair mode: both signalled in both CTAs)
+            if (kPair) {
+              s8_commit2(&sm->done[sw]);
+              if (k + kS8Issuers >= n_st32) s8_commit2(&sm->tmem_full);
+            } else {
+              s8_commit(&sm->done[sw]);
+              if (k + kS8Issuers >= n_st32) s8_commit(&sm->tmem_full);
+            }
             S8_T(t5);
             S8_ACC(j, 0, t1, t0);
             S8_ACC(j, 1, t2, t1);
@@ -280,9 +371,10 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     const int64_t full_bytes = n_geno >> 2;
     uint32_t g0 = 0;
     int icount = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++icount) {
+    for (int item = first_item; item < n_items; item += item_stride, ++icount) {
       int tile, cb;
       s8_item(item, n_tiles, p.n_cb, tile, cb);
+      if (kPair) tile = tile * 2 + (int)rank;  // the pair's two 128-variant halves
       const int v = min(tile * kS8TileV + vloc, p.x.n_variants - 1);
       const uint8_t* row = p.x.base + (int64_t)v * p.x.stride;
       uint32_t nxt[kS8Words + 1];
@@ -378,7 +470,10 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm->full_a[sa]);
+        if (lane == 0) {
+          if (kPair) s8_arrive_cta(&sm->full_a[sa], 0);
+          else mbar_arrive(&sm->full_a[sa]);
+        }
 #ifdef GLR_S8_PROFILE
         if (warp == kS8FirstDecodeWarp && lane == 0) {
           S8_T(d3);
@@ -431,14 +526,20 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm->tmem_empty);      // accumulators may be overwritten
+      if (lane == 0) {  // accumulators may be overwritten
+        if (kPair) s8_arrive_cta(&sm->tmem_empty, 0);
+        else mbar_arrive(&sm->tmem_empty);
+      }
       asm volatile("bar.sync 1, 256;\n" ::: "memory");  // n00[] may be rewritten
       g0 += (uint32_t)n_st;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+  if (kPair) s8_cluster_sync(); else __syncthreads();
+  if (warp == 2) {
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+  }
 }
 
 void split8_geometry(int n_cols, int* n_cb, int* cpb, int* NC) {
@@ -449,21 +550,44 @@ void split8_geometry(int n_cols, int* n_cb, int* cpb, int* NC) {
 
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;
-  const int n_items = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb;
-  const size_t smem = (size_t)kS8WRing * p.NC * kS8K + sizeof(Split8Smem) + 64;
   const bool aligned = (reinterpret_cast<uintptr_t>(p.x.base) & 3) == 0 && (p.x.stride & 3) == 0;
-  auto kern = aligned ? split8_kernel<true> : split8_kernel<false>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // CTA pairs (GLR_S8_PAIR=0 turns them off) once the block has enough variants to occupy the pairs
+  static const int pair_mode = getenv("GLR_S8_PAIR") ? atoi(getenv("GLR_S8_PAIR")) : 1;
+  const int n_items1 = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb;
+  const int n_items2 = (p.x.n_variants + 2 * kS8TileV - 1) / (2 * kS8TileV) * p.n_cb;
+  const bool pair = pair_mode > 0 && (pair_mode > 1 || n_items2 * 2 >= sm_count);
 #ifdef GLR_S8_PROFILE
   static long long zero[160][3][8];
   cudaMemcpyToSymbol(g_s8_prof, zero, sizeof(zero));
 #endif
-  kern<<<std::min(n_items, sm_count), kS8Threads, smem, st>>>(p);
+  if (pair) {
+    const size_t smem = (size_t)kS8WRing * (p.NC / 2) * kS8K + sizeof(Split8Smem) + 64;
+    auto kern = aligned ? split8_kernel<true, true> : split8_kernel<false, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * std::min(n_items2, sm_count / 2));
+    cfg.blockDim = dim3(kS8Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, p);
+  } else {
+    const size_t smem = (size_t)kS8WRing * p.NC * kS8K + sizeof(Split8Smem) + 64;
+    auto kern = aligned ? split8_kernel<true, false> : split8_kernel<false, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<std::min(n_items1, sm_count), kS8Threads, smem, st>>>(p);
+  }
 #ifdef GLR_S8_PROFILE
   static long long h[160][3][8];
   cudaStreamSynchronize(st);
   cudaMemcpyFromSymbol(h, g_s8_prof, sizeof(h));
-  const int nc = std::min(n_items, sm_count);
+  const int nc = pair ? 2 * std::min(n_items2, sm_count / 2) : std::min(n_items1, sm_count);
   const char* names[3] = {"issuer0", "issuer1", "decode4"};
   for (int r = 0; r < 3; ++r) {
     double a[8] = {0};
