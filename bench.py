@@ -481,8 +481,9 @@ def main():
         ops_int8_issued = 2.0 * (-(-n // 128) * 128) * nc_rows * n_cb * 2 * (-(-G // 128) * 128)
         achieved = ops_int8 / gram_s / 1e12
         roof = {
-            'kernel': 'split8_kernel (tcgen05.mma kind::i8, A = decoded genotypes of 128 variants in TMEM, B = digit rows in '
-                      'shared memory, M128 N128 K32, accumulators in TMEM; exact 7-digit radix-256 split of the FP64 operand, '
+            'kernel': 'split8_kernel (tcgen05.mma.cta_group::2 kind::i8 on CTA pairs, A = decoded genotypes of 2 x 128 '
+                      'variants in TMEM, B = digit rows split over the pair\'s shared memory, M256 N128 K32, accumulators in '
+                      'TMEM; exact 7-digit radix-256 split of the FP64 operand, '
                       '2-bit decode + genotype counts fused, FP64 recombination in the epilogue)',
             'bound': 'tensor',
             'achieved': achieved,

@@ -31,10 +31,17 @@
 // States with more than 18 columns are processed in column blocks of up to 18 (the tile's rows are decoded once
 // per block; the kernel stays MMA-bound).
 //
+// CTA pairs.  By default two CTAs of a cluster (the two SMs of a TPC) work as a pair on 256 variants with
+// tcgen05.mma.cta_group::2 (M = 256): each CTA decodes its own 128 variants into its own TMEM, but holds only HALF of
+// the digit rows of a stage in its shared memory — the tensor cores exchange the halves — so the digit stream costs half
+// the L2 and shared-memory traffic.  The leader (rank 0) issues the MMAs; the barriers it waits on collect arrivals from
+// both CTAs (remote mbarrier arrives), and tcgen05.commit multicasts the completions to both.
+//
 // CTA roles (384 threads, 1 CTA/SM, persistent over (128-variant tile, column block) work items):
 //   warp 0    : lane 0 streams the packed digit operand (pre-swizzled image, one bulk copy per stage)
-//   warps 1, 3: lane 0 of each issues tcgen05.mma for alternate stages; one tcgen05.commit per stage
-//               frees the stage's buffers, a second one after the last stage publishes the accumulators
+//   warps 1, 3: issue tcgen05.mma for alternate stages (converged warps, one elected lane); one tcgen05.commit per
+//               stage frees the stage's buffers, a second one after the last stage publishes the accumulators
+//               (in the non-leader CTA of a pair they forward "my half of the digit stage has landed" instead)
 //   warp 2    : TMEM allocation / deallocation
 //   warps 4-11: decode.  Warp w owns TMEM lanes 32 (w % 4) ..; warps 4-7 take the even stages, warps
 //               8-11 the odd ones; a thread turns 32 bytes of its variant's row (128 samples) into 32 + 32
@@ -298,6 +305,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       const int n_st32 = (int)n_st;
       uint32_t g0 = 0;  // global index of the item's first stage
       int icount = 0;
+      S8_T(t_begin);
       for (int item = first_item; item < n_items; item += item_stride, ++icount) {
         for (int k = (int)((j ^ g0) & 1u); k < n_st32; k += kS8Issuers) {
           const uint32_t g = g0 + (uint32_t)k;
@@ -359,6 +367,12 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         }
         g0 += (uint32_t)n_st32;
       }
+#ifdef GLR_S8_PROFILE
+      if (lane == 0) {
+        S8_T(t_end);
+        S8_ACC(j, 6, t_end, t_begin);
+      }
+#endif
     }
   } else if (warp >= kS8FirstDecodeWarp) {
     // ---- decode + count (8 warps), epilogue ----
@@ -552,7 +566,8 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;
   const bool aligned = (reinterpret_cast<uintptr_t>(p.x.base) & 3) == 0 && (p.x.stride & 3) == 0;
   // CTA pairs (GLR_S8_PAIR=0 turns them off) once the block has enough variants to occupy the pairs
-  static const int pair_mode = getenv("GLR_S8_PAIR") ? atoi(getenv("GLR_S8_PAIR")) : 1;
+  const char* pair_env = getenv("GLR_S8_PAIR");  // 0 = never, 1 (default) = when the pairs can be filled, 2 = always
+  const int pair_mode = pair_env ? atoi(pair_env) : 1;
   const int n_items1 = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb;
   const int n_items2 = (p.x.n_variants + 2 * kS8TileV - 1) / (2 * kS8TileV) * p.n_cb;
   const bool pair = pair_mode > 0 && (pair_mode > 1 || n_items2 * 2 >= sm_count);
@@ -596,6 +611,7 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
     const double n = a[5] > 0 ? a[5] : 1;
     fprintf(stderr, "[s8 prof] %s stages/cta %.0f  clk/stage:", names[r], a[5] / nc);
     for (int i = 0; i < 5; ++i) fprintf(stderr, " %.0f", a[i] / n);
+    if (a[6] > 0) fprintf(stderr, "  | loop clk per stage of the CTA: %.0f", a[6] / (2 * n));
     fprintf(stderr, "\n");
   }
 #endif

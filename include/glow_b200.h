@@ -85,7 +85,8 @@ typedef struct glr_state_desc {
   int32_t max_block_variants; /* hint for workspace sizing (grown on demand) */
   int32_t n_lanes;         /* independent in-flight blocks (streams); 0 -> default 2 */
   /* Environment knobs read at state creation: GLR_SPLIT8 = 0 | 1 (default) | 2 selects the exact int8
-   * tensor-core contraction for PLINK2 blocks never | for blocks filling >= half the SMs | always;
+   * tensor-core contraction for PLINK2 blocks never | for blocks filling >= half the SMs | always
+   * (GLR_S8_PAIR = 0 | 1 (default) | 2, read per block: its CTA-pair form never | when the pairs fill | always);
    * GLR_KEEP_INTERCEPT keeps a constant first column of Q inside the GEMM; GLR_NO_TAIL pads the
    * column count to a multiple of 8 instead of using FP64-FMA tail columns. */
   int32_t memspace;        /* glr_memspace of Q, Y, Y_mask, YdotY, Y_scale, Y_raw (keep_idx is always

@@ -181,9 +181,11 @@ def test_smoke_entry_point():
 
 @pytest.mark.parametrize('N,G,P,K', [(1000, 300, 1, 16), (515, 129, 2, 3), (4099, 1000, 20, 16), (127, 64, 1, 0), (130, 5, 3, 30),
                                      (700, 260, 45, 16), (300, 129, 19, 0)])
-def test_int8_split_path_matches_dmma_path_and_oracle(rg, N, G, P, K, monkeypatch):
+@pytest.mark.parametrize('pair', ['0', '2'])
+def test_int8_split_path_matches_dmma_path_and_oracle(rg, N, G, P, K, pair, monkeypatch):
     """The tcgen05 int8 digit-split contraction (split8.cu) against the FP64 DMMA path and the oracle:
-    ragged sample / variant counts, unaligned rows, both imputation policies, one to four column blocks."""
+    ragged sample / variant counts, unaligned rows, both imputation policies, one to four column blocks,
+    single-CTA and CTA-pair kernels."""
     from glow_b200 import _capi
     from glow_b200.engine import GenotypeBlock
     X = rg.integers(0, 3, (G, N)).astype(np.float64)
@@ -195,6 +197,7 @@ def test_int8_split_path_matches_dmma_path_and_oracle(rg, N, G, P, K, monkeypatc
     cov = pd.DataFrame(rg.standard_normal((N, K))) if K else None
     phe = pd.DataFrame(rg.standard_normal((N, P)))
     packed = pack_plink(states)
+    monkeypatch.setenv('GLR_S8_PAIR', pair)  # single-CTA kernel / CTA-pair (cta_group::2) kernel
     monkeypatch.setenv('GLR_SPLIT8', '2')
     eng8, st = _state(phe, cov)
     monkeypatch.setenv('GLR_SPLIT8', '0')
