@@ -265,12 +265,8 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         for (int64_t k = 0; k < n_st; ++k, ++g) {
           const uint32_t s = g & (kS8WRing - 1);
           if (g >= (uint32_t)kS8WRing) mbar_wait_backoff(&sm->done[s], ((g >> 3) & 1u) ^ 1u);  // stage g - 8 consumed
-#ifdef GLR_S8_DBG_NOW
-          mbar_arrive(&sm->full_w[s]);
-#else
           mbar_expect_tx(&sm->full_w[s], w_bytes);
           bulk_g2s(w_ring + (size_t)s * w_bytes, src + k * w_stage_bytes, w_bytes, &sm->full_w[s]);
-#endif
         }
       }
     }
@@ -444,10 +440,6 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         // decode into registers first, THEN wait for the TMEM slot: the slot frees up when the MMAs of stage g - 4
         // complete, and the hand-off back to the issuer must not include the decode arithmetic
         uint32_t xs[32], es[32];
-#ifdef GLR_S8_DBG_NODECODE
-#pragma unroll
-        for (int i = 0; i < 32; ++i) xs[i] = es[i] = w[0];
-#else
 #pragma unroll
         for (int i = 0; i < kS8Words; ++i) {
           const uint32_t ww = w[i];
@@ -469,7 +461,6 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           es[4 * i + 2] = __byte_perm(0x00000100u, 0x00000100u, od);
           es[4 * i + 3] = __byte_perm(0x00000100u, 0x00000100u, od_hi);
         }
-#endif
         const uint32_t sa = g & (kS8ARing - 1);
         S8_T(d1);
         // the MMAs that read this TMEM slot last (stage g - 4) must have completed
