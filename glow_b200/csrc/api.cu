@@ -61,7 +61,7 @@ struct DevBuf {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
-  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx;
+  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx, m8_rmax, m8_z8, m8_Z;
   bool busy = false;
   bool has_masked = false, has_prepass = false;
   int launches = 0;
@@ -104,6 +104,11 @@ struct glr_state {
   int U = 0, MT2 = 1, n_groups2 = 0, KT2 = 0;
   double* qb = nullptr;
   double* mpk = nullptr;
+  // masked pass, integer tensor-core variant (mask8.cu): many distinct masks
+  int mask8 = 0, m8_nmb = 0, m8_NB = 0;
+  int64_t m8_stages = 0;
+  double* qg = nullptr;  // [Ng][K] rows of Q in genotype-sample order
+  int8_t* m8 = nullptr;  // [mask block][stage][NB][128]
   // small per-phenotype arrays
   int32_t* mask_id = nullptr;  // [P]
   double* YdotY = nullptr;     // [C][P]
@@ -158,12 +163,14 @@ int glr_state_destroy(glr_state* st) {
     if (l.stream) cudaStreamSynchronize(l.stream);
     for (auto& e : l.ev)
       if (e) cudaEventDestroy(e);
-    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.mom_part, &l.mom, &l.v1, &l.d_part, &l.d_red, &l.xx})
+    for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.mom_part, &l.mom, &l.v1, &l.d_part, &l.d_red, &l.xx, &l.m8_rmax, &l.m8_z8,
+                       &l.m8_Z})
       b->release();
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   for (void* p : {(void*)st->wpk, (void*)st->qb, (void*)st->mpk, (void*)st->mask_id, (void*)st->YdotY,
-                  (void*)st->Y_scale, (void*)st->n_obs, (void*)st->drop_idx, (void*)st->w8, (void*)st->s8_scale})
+                  (void*)st->Y_scale, (void*)st->n_obs, (void*)st->drop_idx, (void*)st->w8, (void*)st->s8_scale,
+                  (void*)st->qg, (void*)st->m8})
     if (p) cudaFree(p);
   delete st;
   return 0;
@@ -437,6 +444,21 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     tmp.v.push_back(dMu);
     CU(cudaMemcpy(dMu, mu.data(), mu.size() * sizeof(double), cudaMemcpyHostToDevice));
     launch_pack_a(dMu, N, U, 0, U, d_g2r, Ng, st->mpk, 0, st->MT2, 0, st->n_chunks, s0);
+    // GLR_MASK8: 0 = never, 1 (default) = states with at least 64 distinct masks, 2 = whenever there are masks
+    const int mask8_mode = getenv("GLR_MASK8") ? atoi(getenv("GLR_MASK8")) : 1;
+    if (mask8_mode > 0 && (mask8_mode > 1 || U >= 64) && K <= 64 && Ng < (int64_t)16000000) {
+      mask8_geometry(U, &st->m8_nmb, &st->m8_NB);
+      st->m8_stages = ceil_div(Ng, 128);
+      const size_t m8_bytes = (size_t)st->m8_nmb * st->m8_stages * st->m8_NB * 128;
+      if (m8_bytes <= ((size_t)8 << 30)) {
+        st->mask8 = mask8_mode;
+        CU(cudaMalloc(&st->m8, m8_bytes));
+        CU(cudaMemsetAsync(st->m8, 0, m8_bytes, s0));
+        launch_pack_mask8(dMu, N, U, d_g2r, Ng, st->m8_NB, st->m8_stages, st->m8, s0);
+        CU(cudaMalloc(&st->qg, (size_t)std::max<int64_t>(Ng * K, 1) * sizeof(double)));
+        launch_gather_q(dQ, N, K, d_g2r, Ng, st->qg, s0);
+      }
+    }
   }
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
@@ -617,7 +639,41 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   CU(cudaEventRecord(L.ev[2], s));
   // ---- pass 2 (A4 for phenotypes with missing samples): D = Mu^T (X - Q A)^2 ----
   const double* d_D = nullptr;
-  if (st->U > 0) {
+  if (st->U > 0 && st->mask8) {
+    // integer tensor-core form (mask8.cu), in sub-ranges of variants that bound the digit image to 3 GiB
+    const int64_t Upad = (int64_t)st->n_groups2 * st->MT2 * 8;
+    if (int rc = L.d_red.ensure((size_t)Upad * ldS * 8)) return rc;
+    if (int rc = L.m8_rmax.ensure((size_t)ldS * 8)) return rc;
+    const int tv = mask8_tile_variants();
+    const size_t tile_bytes = mask8_tile_bytes(st->m8_stages);
+    int64_t tiles_sub = std::max<int64_t>(2, (int64_t)(((size_t)3 << 30) / tile_bytes) / 2 * 2);
+    tiles_sub = std::min<int64_t>(tiles_sub, round_up(ceil_div(G, tv), 2));
+    if (int rc = L.m8_z8.ensure((size_t)tiles_sub * tile_bytes)) return rc;
+    if (int rc = L.m8_Z.ensure(mask8_z_bytes((int)tiles_sub, st->m8_nmb, st->m8_NB))) return rc;
+    for (int64_t v0 = 0; v0 < G; v0 += tiles_sub * tv) {
+      Mask8Params mp;
+      mp.x = x;
+      mp.qg = st->qg;
+      mp.A = L.s_red.as<double>();
+      mp.ldS = ldS;
+      mp.K = K;
+      mp.v0 = (int)v0;
+      mp.nv = (int)std::min<int64_t>(tiles_sub * tv, G - v0);
+      mp.n_stages = st->m8_stages;
+      mp.rmax_bits = L.m8_rmax.as<unsigned long long>();
+      mp.z8 = L.m8_z8.as<int8_t>();
+      mp.m8 = st->m8;
+      mp.n_mb = st->m8_nmb;
+      mp.NB = st->m8_NB;
+      mp.U = st->U;
+      mp.Z = L.m8_Z.as<int32_t>();
+      mp.D = L.d_red.as<double>();
+      launch_mask8(mp, st->sm_count, s);
+      L.launches += 4;
+    }
+    d_D = L.d_red.as<double>();
+    L.has_masked = true;
+  } else if (st->U > 0) {
     const int64_t Upad = (int64_t)st->n_groups2 * st->MT2 * 8;
     const int tile2 = gram_tile_variants(2);
     const int64_t ctas2 = ceil_div(G, tile2) * st->n_groups2;

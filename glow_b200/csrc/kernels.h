@@ -82,6 +82,31 @@ struct MaskedParams {
 };
 void launch_masked(const MaskedParams& p, cudaStream_t st);
 
+// ---- pass 2, integer tensor-core variant (many distinct masks): see mask8.cu ----
+struct Mask8Params {
+  BlockView x;           // x.v1 = missing substitute per variant
+  const double* qg;      // [n_geno][K] rows of Q in genotype-sample order
+  const double* A;       // coefficients Q^T X: [K][ldS]
+  int64_t ldS;
+  int32_t K;
+  int32_t v0, nv;        // sub-range of variants
+  int64_t n_stages;      // 128-sample stages
+  unsigned long long* rmax_bits;  // [G] scratch: max_s r^2 per variant
+  int8_t* z8;            // digit image of the sub-range: [tile][stage][128][128]
+  const int8_t* m8;      // mask image: [mask block][stage][NB][128]
+  int32_t n_mb, NB, U;
+  int32_t* Z;            // int32 scratch [tile][mask block][128][NB]
+  double* D;             // out: [U][ldS]
+};
+void mask8_geometry(int U, int* n_mb, int* NB);
+size_t mask8_tile_bytes(int64_t n_stages);
+size_t mask8_z_bytes(int n_tiles, int n_mb, int NB);
+int mask8_tile_variants();
+void launch_pack_mask8(const double* mu, int64_t N, int U, const int64_t* geno_to_row, int64_t Ng, int NB, int64_t n_stages,
+                       int8_t* dst, cudaStream_t st);
+void launch_gather_q(const double* Q, int64_t N, int K, const int64_t* geno_to_row, int64_t Ng, double* qg, cudaStream_t st);
+void launch_mask8(const Mask8Params& p, int sm_count, cudaStream_t st);
+
 // sums the n_split partial slabs in fixed order: out[r][v] = sum_z part[z][r][v]
 void launch_reduce_splits(const double* part, double* out, int64_t rows, int64_t ld, int n_split, cudaStream_t st);
 
