@@ -145,6 +145,117 @@ __global__ void __launch_bounds__(kRsqThreads) rsq_kernel(const RsqParams p) {
   if (PASS == 0) atomicMax(p.rmax_bits + v, (unsigned long long)__double_as_longlong(mx_local));
 }
 
+// Fast form for K <= 16: a warp handles ONE variant at a time over the block's 128-sample stage, lane = 4 consecutive
+// samples.  The lane keeps the Q rows of its 4 samples in registers for the whole block (no shared memory at all), the
+// variant's coefficients are warp-uniform loads, the packed genotypes of a variant are one coalesced 32-byte read per
+// warp, and every digit row of the stage is written as one full 128-byte line per warp.
+template <int FMT>
+__device__ __forceinline__ void m8_load4(const uint8_t* row, int64_t s, int64_t n, double miss, double (&x)[4]) {
+  if (FMT == GLR_FMT_PLINK2) {
+    const uint32_t b = s < n ? (uint32_t)__ldg(row + (s >> 2)) : 0xFFu;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = s + j < n ? XLoader<GLR_FMT_PLINK2, 1>::dec((b >> (2 * j)) & 3u, miss) : 0.0;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = s + j < n ? m8_elem<FMT>(row, s + j, miss) : 0.0;
+  }
+}
+
+template <int FMT, int PASS, int KT>
+__global__ void __launch_bounds__(kRsqThreads) rsq4_kernel(const RsqParams p) {
+  // per-block operands of the 256 variants, loaded once (coalesced) so that the variant loop sees shared-memory latency
+  __shared__ double As[KT][kRsqThreads];           // coefficients
+  __shared__ double ms[kRsqThreads];               // missing substitute (PASS 0/1), then 2^54 / max (PASS 1) in invs
+  __shared__ double invs[kRsqThreads];
+  __shared__ __align__(16) uint8_t gb[FMT == GLR_FMT_PLINK2 ? kRsqThreads : 1][32];  // packed genotypes of the stage
+  const int K = p.K;
+  const int64_t stage = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t s = stage * kM8K + 4 * lane;  // this lane's first sample
+  const int64_t n = p.x.n_geno;
+  const int vl0 = blockIdx.y * kRsqThreads;
+  const int nvb = min(kRsqThreads, p.nv - vl0);
+  {
+    const int t = threadIdx.x;
+    if (t < nvb) {
+      const int v = p.v0 + vl0 + t;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) As[k][t] = k < K ? __ldg(p.A + (int64_t)k * p.ldS + v) : 0.0;
+      ms[t] = (FMT == GLR_FMT_I8 || FMT == GLR_FMT_PLINK2) ? __ldg(p.x.v1 + v) : 0.0;
+      if (PASS == 1) {
+        const double mx = __longlong_as_double((long long)__ldg(p.rmax_bits + v));
+        invs[t] = mx > 0.0 ? 18014398509481984.0 /* 2^54 */ / mx : 0.0;
+      }
+      if (FMT == GLR_FMT_PLINK2) {
+        const uint8_t* row = p.x.base + (int64_t)v * p.x.stride;
+        const int64_t b0 = stage * 32, row_bytes = (n + 3) >> 2;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) gb[t][i] = b0 + i < row_bytes ? __ldg(row + b0 + i) : (uint8_t)0xFF;
+      }
+    }
+  }
+  double q[4][KT];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < KT; ++k) q[j][k] = (k < K && s + j < n) ? __ldg(p.qg + (s + j) * K + k) : 0.0;
+  __syncthreads();
+
+  for (int t = warp; t < nvb; t += kRsqThreads / 32) {
+    const int vl = vl0 + t;
+    const int v = p.v0 + vl;
+    const double miss = ms[t];
+    double x[4];
+    if (FMT == GLR_FMT_PLINK2) {
+      const uint32_t b = gb[t][lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = s + j < n ? XLoader<GLR_FMT_PLINK2, 1>::dec((b >> (2 * j)) & 3u, miss) : 0.0;
+    } else {
+      m8_load4<FMT>(p.x.base + (int64_t)v * p.x.stride, s, n, miss, x);
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      if (k < K) {
+        const double ak = As[k][t];  // warp-uniform (broadcast)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = fma(-q[j][k], ak, x[j]);
+      }
+    }
+    if (PASS == 0) {
+      double m = fmax(fmax(x[0] * x[0], x[1] * x[1]), fmax(x[2] * x[2], x[3] * x[3]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) atomicMax(p.rmax_bits + v, (unsigned long long)__double_as_longlong(m));
+    } else {
+      const double inv = invs[t];
+      unsigned long long qq[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qq[j] = (unsigned long long)__double2ll_rn((x[j] * x[j]) * inv) + 0x0080808080808080ull;
+      const int tile = vl / kM8TileV, row0 = (vl - tile * kM8TileV) * kM8Digits;
+      int8_t* img = p.z8 + ((int64_t)tile * p.n_stages + stage) * (kM8Rows * kM8K);
+#pragma unroll
+      for (int i = 0; i < kM8Digits; ++i) {
+        const uint32_t sel = i < 4 ? (uint32_t)(i | ((4 + i) << 4)) : (uint32_t)((i - 4) | (i << 4));
+        const uint32_t lo01 = i < 4 ? __byte_perm((uint32_t)qq[0], (uint32_t)qq[1], sel)
+                                    : __byte_perm((uint32_t)(qq[0] >> 32), (uint32_t)(qq[1] >> 32), sel);
+        const uint32_t lo23 = i < 4 ? __byte_perm((uint32_t)qq[2], (uint32_t)qq[3], sel)
+                                    : __byte_perm((uint32_t)(qq[2] >> 32), (uint32_t)(qq[3] >> 32), sel);
+        const int r = row0 + i;
+        // lane's 4 bytes sit at k = 4 lane: chunk (lane >> 2) ^ (r & 7), offset 4 (lane & 3)
+        *reinterpret_cast<uint32_t*>(img + (int64_t)r * kM8K + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2))) =
+            __byte_perm(lo01, lo23, 0x5410u) ^ 0x80808080u;
+      }
+    }
+  }
+}
+
+template <int FMT, int KT>
+static void launch_rsq4_kt(const RsqParams& p, cudaStream_t st) {
+  const dim3 grid((unsigned)p.n_stages, (unsigned)ceil_div(p.nv, kRsqThreads));
+  rsq4_kernel<FMT, 0, KT><<<grid, kRsqThreads, 0, st>>>(p);
+  rsq4_kernel<FMT, 1, KT><<<grid, kRsqThreads, 0, st>>>(p);
+}
+
 template <int FMT, int KT>
 static void launch_rsq_kt(const RsqParams& p, cudaStream_t st) {
   const dim3 grid((unsigned)p.n_stages, (unsigned)ceil_div(p.nv, kRsqThreads));
@@ -156,7 +267,9 @@ static void launch_rsq_kt(const RsqParams& p, cudaStream_t st) {
 }
 template <int FMT>
 static void launch_rsq_fmt(const RsqParams& p, cudaStream_t st) {
-  if (p.K <= 12) launch_rsq_kt<FMT, 12>(p, st);
+  if (p.K <= 8) launch_rsq4_kt<FMT, 8>(p, st);
+  else if (p.K <= 12) launch_rsq4_kt<FMT, 12>(p, st);
+  else if (p.K <= 16) launch_rsq4_kt<FMT, 16>(p, st);
   else if (p.K <= 24) launch_rsq_kt<FMT, 24>(p, st);
   else launch_rsq_kt<FMT, kRsqMaxK>(p, st);
 }
