@@ -413,12 +413,10 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
 
   // ---- masked-pass operands ----
   if (st->U > 0) {
+    const int U = st->U;
     const int KT = (int)ceil_div(std::max(K, 1), 4);
     st->KT2 = (int)ceil_div(KT, 2);
-    if (2 * st->KT2 > 8)
-      return fail(GLR_ERR_INVALID,
-                  "phenotypes with missing values are supported with at most 32 covariates (incl. intercept)");
-    const int U = st->U;
+    const bool dmma_ok = 2 * st->KT2 <= 8;  // the FP64 DMMA form keeps K <= 32 coefficients per lane
     const int n_mt2 = (int)ceil_div(U, 8);
     if (n_mt2 <= kMaxMT) {
       st->MT2 = pick_mt_masked(n_mt2);
@@ -427,14 +425,6 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
       st->MT2 = kMaxMT;
       st->n_groups2 = (int)ceil_div(n_mt2, kMaxMT);
     }
-    const size_t qb_bytes = (size_t)st->n_chunks * kChunkGroups * st->KT2 * kAtomDoubles * sizeof(double);
-    CU(cudaMalloc(&st->qb, qb_bytes));
-    CU(cudaMemsetAsync(st->qb, 0, qb_bytes, s0));
-    if (K > 0) launch_pack_qb(dQ, N, K, d_g2r, Ng, st->qb, st->KT2, st->n_chunks, s0);
-    const size_t m_bytes =
-        (size_t)st->n_groups2 * st->n_chunks * kChunkGroups * st->MT2 * kAtomDoubles * sizeof(double);
-    CU(cudaMalloc(&st->mpk, m_bytes));
-    CU(cudaMemsetAsync(st->mpk, 0, m_bytes, s0));
     // unique mask columns, row-major [N x U]
     std::vector<double> mu((size_t)N * U);
     for (int64_t s = 0; s < N; ++s)
@@ -443,10 +433,10 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     CU(cudaMalloc(&dMu, mu.size() * sizeof(double)));
     tmp.v.push_back(dMu);
     CU(cudaMemcpy(dMu, mu.data(), mu.size() * sizeof(double), cudaMemcpyHostToDevice));
-    launch_pack_a(dMu, N, U, 0, U, d_g2r, Ng, st->mpk, 0, st->MT2, 0, st->n_chunks, s0);
-    // GLR_MASK8: 0 = never, 1 (default) = states with at least 64 distinct masks, 2 = whenever there are masks
+    // integer tensor-core form (mask8.cu).  GLR_MASK8: 0 = never, 1 (default) = states with at least 64 distinct masks
+    // or more covariates than the DMMA form takes, 2 = whenever there are masks
     const int mask8_mode = getenv("GLR_MASK8") ? atoi(getenv("GLR_MASK8")) : 1;
-    if (mask8_mode > 0 && (mask8_mode > 1 || U >= 64) && K <= 64 && Ng < (int64_t)16000000) {
+    if (mask8_mode > 0 && (mask8_mode > 1 || U >= 64 || !dmma_ok) && K <= 64 && Ng < (int64_t)16000000) {
       mask8_geometry(U, &st->m8_nmb, &st->m8_NB);
       st->m8_stages = ceil_div(Ng, 128);
       const size_t m8_bytes = (size_t)st->m8_nmb * st->m8_stages * st->m8_NB * 128;
@@ -458,6 +448,21 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
         CU(cudaMalloc(&st->qg, (size_t)std::max<int64_t>(Ng * K, 1) * sizeof(double)));
         launch_gather_q(dQ, N, K, d_g2r, Ng, st->qg, s0);
       }
+    }
+    if (!st->mask8) {
+      if (!dmma_ok)
+        return fail(GLR_ERR_INVALID,
+                    "phenotypes with missing values are supported with at most 64 covariates (incl. intercept); "
+                    "at most 32 when the int8 masked pass is disabled");
+      const size_t qb_bytes = (size_t)st->n_chunks * kChunkGroups * st->KT2 * kAtomDoubles * sizeof(double);
+      CU(cudaMalloc(&st->qb, qb_bytes));
+      CU(cudaMemsetAsync(st->qb, 0, qb_bytes, s0));
+      if (K > 0) launch_pack_qb(dQ, N, K, d_g2r, Ng, st->qb, st->KT2, st->n_chunks, s0);
+      const size_t m_bytes =
+          (size_t)st->n_groups2 * st->n_chunks * kChunkGroups * st->MT2 * kAtomDoubles * sizeof(double);
+      CU(cudaMalloc(&st->mpk, m_bytes));
+      CU(cudaMemsetAsync(st->mpk, 0, m_bytes, s0));
+      launch_pack_a(dMu, N, U, 0, U, d_g2r, Ng, st->mpk, 0, st->MT2, 0, st->n_chunks, s0);
     }
   }
   CU(cudaGetLastError());

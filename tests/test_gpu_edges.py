@@ -86,17 +86,33 @@ def test_no_intercept_and_no_covariates(rg):
     assert_stats_close({k: out2[k].to_numpy().reshape(P, G) for k in STATS}, ref2, label='constant last')
 
 
-def test_masked_pass_covariate_limit(rg):
-    from glow_b200.engine import DeviceState
-    N, P, K = 200, 2, 33
+def test_masked_pass_covariate_limit(rg, monkeypatch):
+    """Phenotypes with missing values: the FP64 DMMA form takes K <= 32, the int8 form (chosen automatically beyond
+    that) K <= 64."""
+    from glow_b200.engine import DeviceState, GenotypeBlock
+    N, G, P, K = 200, 40, 2, 33
+    cov = pd.DataFrame(rg.standard_normal((N, K - 1)))
+    Yv = rg.standard_normal((N, P))
+    Yv[3, 0] = np.nan
+    phe = pd.DataFrame(Yv)
+    X = rg.integers(0, 3, (G, N)).astype(np.float64)
+    eng, st = _state(phe, cov)
+    assert_stats_close(eng.run(GenotypeBlock(X, 'f64')), orc.block_stats(X, st), label='K=33 masked')
+    eng.close()
     Q = np.linalg.qr(rg.standard_normal((N, K)))[0]
     Y = rg.standard_normal((N, P))
     mask = np.ones((N, P))
     mask[3, 0] = 0
-    with pytest.raises(ValueError, match='at most 32 covariates'):
-        DeviceState(Q=Q, Y=Y * mask, Y_mask=mask, YdotY=np.sum((Y * mask)**2, axis=0), Y_scale=np.ones(P), dof=N - K - 1)
+    kw = dict(Y=Y * mask, Y_mask=mask, YdotY=np.sum((Y * mask)**2, axis=0), Y_scale=np.ones(P))
+    monkeypatch.setenv('GLR_MASK8', '0')
+    with pytest.raises(ValueError, match='at most 64 covariates'):
+        DeviceState(Q=Q, dof=N - K - 1, **kw)
+    monkeypatch.delenv('GLR_MASK8')
+    Q65 = np.linalg.qr(rg.standard_normal((N, 65)))[0]
+    with pytest.raises(ValueError, match='at most 64 covariates'):
+        DeviceState(Q=Q65, dof=N - 65 - 1, **kw)
     # fully observed phenotypes have no such limit
-    eng = DeviceState(Q=Q, Y=Y, Y_mask=np.ones((N, P)), YdotY=np.sum(Y**2, axis=0), Y_scale=np.ones(P), dof=N - K - 1)
+    eng = DeviceState(Q=Q65, Y=Y, Y_mask=np.ones((N, P)), YdotY=np.sum(Y**2, axis=0), Y_scale=np.ones(P), dof=N - 65 - 1)
     eng.close()
 
 
