@@ -92,6 +92,9 @@ CONFIGS = {
     'cfg4': dict(N=50_000, K_cov=10, P=2_000, G=8_192, fmt='plink2', missing=0.1),
     # configs[4]: 200k samples x 20 phenotypes, LOCO (2 of 22 contig states built here), 2-bit
     'cfg5': dict(N=200_000, K_cov=16, P=20, G=37_888, fmt='plink2', n_contigs=2),
+    # not a BASELINE config: the UK-Biobank shape with missing phenotype values (the usual case in practice)
+    'cfg3m': dict(N=500_000, K_cov=16, P=1, G=37_888, fmt='plink2', missing=0.02),
+    'cfg5m': dict(N=200_000, K_cov=16, P=20, G=37_888, fmt='plink2', missing=0.02),
 }
 
 if __name__ == '__main__':

@@ -109,6 +109,12 @@ struct glr_state {
   int64_t m8_stages = 0;
   double* qg = nullptr;  // [Ng][K] rows of Q in genotype-sample order
   int8_t* m8 = nullptr;  // [mask block][stage][NB][128]
+  // masked pass, sparse complement form (masked_sparse.cu): few unobserved phenotype values
+  int sparse_masked = 0;
+  int64_t sp_total = 0;
+  int32_t* sp_idx = nullptr;  // unobserved genotype-sample indices per distinct mask, concatenated
+  double* sp_qm = nullptr;    // [sp_total][Kp]
+  int64_t* sp_off = nullptr;  // [U + 1]
   // small per-phenotype arrays
   int32_t* mask_id = nullptr;  // [P]
   double* YdotY = nullptr;     // [C][P]
@@ -170,7 +176,7 @@ int glr_state_destroy(glr_state* st) {
   }
   for (void* p : {(void*)st->wpk, (void*)st->qb, (void*)st->mpk, (void*)st->mask_id, (void*)st->YdotY,
                   (void*)st->Y_scale, (void*)st->n_obs, (void*)st->drop_idx, (void*)st->w8, (void*)st->s8_scale,
-                  (void*)st->qg, (void*)st->m8})
+                  (void*)st->qg, (void*)st->m8, (void*)st->sp_idx, (void*)st->sp_qm, (void*)st->sp_off})
     if (p) cudaFree(p);
   delete st;
   return 0;
@@ -433,10 +439,53 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     CU(cudaMalloc(&dMu, mu.size() * sizeof(double)));
     tmp.v.push_back(dMu);
     CU(cudaMemcpy(dMu, mu.data(), mu.size() * sizeof(double), cudaMemcpyHostToDevice));
-    // integer tensor-core form (mask8.cu).  GLR_MASK8: 0 = never, 1 (default) = states with at least 64 distinct masks
-    // or more covariates than the DMMA form takes, 2 = whenever there are masks
+    // Three forms of the pass; cost per variant in FP64-FMA equivalents (measured rates):
+    //   sparse complement (masked_sparse.cu)  T * K            T = unobserved (sample, mask) pairs
+    //   FP64 DMMA (masked_kernel)             Ng * (K + U)     K <= 32
+    //   int8 tensor cores (mask8.cu)          Ng * (115 + 0.055 U)   K <= 64
+    // GLR_MASK_SPARSE / GLR_MASK8: 0 = never, 1 (default) = when cheapest, 2 = always
+    const int sparse_mode = getenv("GLR_MASK_SPARSE") ? atoi(getenv("GLR_MASK_SPARSE")) : 1;
     const int mask8_mode = getenv("GLR_MASK8") ? atoi(getenv("GLR_MASK8")) : 1;
-    if (mask8_mode > 0 && (mask8_mode > 1 || U >= 64 || !dmma_ok) && K <= 64 && Ng < (int64_t)16000000) {
+    std::vector<int32_t> sp_idx;
+    std::vector<int64_t> sp_rows, sp_off(1, 0);
+    for (int u = 0; u < U; ++u) {
+      for (int64_t sg = 0; sg < Ng; ++sg) {
+        const int64_t row = g2r.empty() ? sg : g2r[sg];
+        if (row >= 0 && mask_host[row * P + rep[u]] == 0.0) {
+          sp_idx.push_back((int32_t)sg);
+          sp_rows.push_back(row);
+        }
+      }
+      sp_off.push_back((int64_t)sp_idx.size());
+    }
+    const double T = (double)sp_idx.size();
+    const double cost_sparse = T * std::max(K, 1);
+    const double cost_dmma = dmma_ok ? (double)Ng * (K + U) : 1e300;
+    const bool int8_ok = K <= 64 && Ng < (int64_t)16000000;
+    const double cost_int8 = int8_ok ? (double)Ng * (115.0 + 0.055 * U) : 1e300;
+    const bool sparse_ok = sparse_mode > 0 && K <= 64 && Ng < ((int64_t)1 << 31);
+    bool use_sparse = sparse_ok && (sparse_mode > 1 || (cost_sparse <= cost_dmma && cost_sparse <= cost_int8));
+    bool use_int8 = !use_sparse && mask8_mode > 0 && int8_ok && (mask8_mode > 1 || cost_int8 < cost_dmma);
+    if (mask8_mode > 1 && sparse_mode <= 1 && int8_ok) {  // an explicit request for the int8 form wins over "cheapest"
+      use_sparse = false;
+      use_int8 = true;
+    }
+    if (use_sparse) {
+      st->sparse_masked = sparse_mode;
+      st->sp_total = (int64_t)sp_idx.size();
+      const int Kp = (K + 1) & ~1;
+      int64_t* d_rows = nullptr;
+      CU(cudaMalloc(&st->sp_idx, std::max<size_t>(sp_idx.size(), 1) * sizeof(int32_t)));
+      CU(cudaMalloc(&st->sp_off, sp_off.size() * sizeof(int64_t)));
+      CU(cudaMalloc(&st->sp_qm, std::max<size_t>(sp_idx.size() * Kp, 1) * sizeof(double)));
+      CU(cudaMalloc(&d_rows, std::max<size_t>(sp_rows.size(), 1) * sizeof(int64_t)));
+      tmp.v.push_back(d_rows);
+      CU(cudaMemcpy(st->sp_idx, sp_idx.data(), sp_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(st->sp_off, sp_off.data(), sp_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d_rows, sp_rows.data(), sp_rows.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+      launch_gather_rows(dQ, K, Kp, d_rows, st->sp_total, st->sp_qm, s0);
+    }
+    if (use_int8) {
       mask8_geometry(U, &st->m8_nmb, &st->m8_NB);
       st->m8_stages = ceil_div(Ng, 128);
       const size_t m8_bytes = (size_t)st->m8_nmb * st->m8_stages * st->m8_NB * 128;
@@ -449,7 +498,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
         launch_gather_q(dQ, N, K, d_g2r, Ng, st->qg, s0);
       }
     }
-    if (!st->mask8) {
+    if (!st->mask8 && !st->sparse_masked) {
       if (!dmma_ok)
         return fail(GLR_ERR_INVALID,
                     "phenotypes with missing values are supported with at most 64 covariates (incl. intercept); "
@@ -644,7 +693,39 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   CU(cudaEventRecord(L.ev[2], s));
   // ---- pass 2 (A4 for phenotypes with missing samples): D = Mu^T (X - Q A)^2 ----
   const double* d_D = nullptr;
-  if (st->U > 0 && st->mask8) {
+  bool d_is_complement = false;
+  if (st->U > 0 && st->sparse_masked) {
+    // sparse complement form: sum of r^2 over the unobserved samples of every distinct mask
+    const int U = st->U;
+    const int64_t Upad = (int64_t)st->n_groups2 * st->MT2 * 8;
+    if (int rc = L.d_red.ensure((size_t)Upad * ldS * 8)) return rc;
+    const int64_t vblocks = ceil_div(G, 256);
+    const int64_t longest = std::max<int64_t>(1, ceil_div(st->sp_total, (int64_t)U));
+    int n_parts = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div(4 * st->sm_count, vblocks * U)), ceil_div(longest, 128));
+    n_parts = std::max(1, std::min(n_parts, 64));
+    if (n_parts > 1)
+      if (int rc = L.d_part.ensure((size_t)n_parts * U * ldS * 8)) return rc;
+    SparseMaskedParams sp;
+    sp.x = x;
+    sp.A = L.s_red.as<double>();
+    sp.ldS = ldS;
+    sp.K = K;
+    sp.idx = st->sp_idx;
+    sp.qm = st->sp_qm;
+    sp.off = st->sp_off;
+    sp.U = U;
+    sp.n_parts = n_parts;
+    sp.comp = n_parts > 1 ? L.d_part.as<double>() : L.d_red.as<double>();
+    launch_sparse_masked(sp, s);
+    ++L.launches;
+    if (n_parts > 1) {
+      launch_reduce_splits(L.d_part.as<double>(), L.d_red.as<double>(), U, ldS, n_parts, s);
+      ++L.launches;
+    }
+    d_D = L.d_red.as<double>();
+    d_is_complement = true;
+    L.has_masked = true;
+  } else if (st->U > 0 && st->mask8) {
     // integer tensor-core form (mask8.cu), in sub-ranges of variants that bound the digit image to 3 GiB
     const int64_t Upad = (int64_t)st->n_groups2 * st->MT2 * 8;
     if (int rc = L.d_red.ensure((size_t)Upad * ldS * 8)) return rc;
@@ -719,6 +800,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   ep.S = L.s_red.as<double>();
   ep.sxx = L.mom.as<double>();
   ep.D = d_D;
+  ep.d_is_complement = d_is_complement ? 1 : 0;
   ep.mask_id = st->mask_id;
   ep.YdotY = st->YdotY + (int64_t)b->contig * P;
   ep.Y_scale = st->Y_scale;

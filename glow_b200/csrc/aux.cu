@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpiloguePar
   const int ph = blockIdx.y;
   if (v >= p.G) return;
   const int mid = p.mask_id[ph];
-  const double XdotX = mid < 0 ? xx_full[v] : p.D[(int64_t)mid * p.ldS + v];
+  const double XdotX = mid < 0 ? xx_full[v] : (p.d_is_complement ? xx_full[v] - p.D[(int64_t)mid * p.ldS + v] : p.D[(int64_t)mid * p.ldS + v]);
   const double XdotY = p.S[(int64_t)(p.K + ph) * p.ldS + v];
   const double recip = 1.0 / XdotX;                                             // lin_reg.py:241
   const double beta = XdotY * recip;                                            // :242

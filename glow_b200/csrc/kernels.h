@@ -107,6 +107,22 @@ void launch_pack_mask8(const double* mu, int64_t N, int U, const int64_t* geno_t
 void launch_gather_q(const double* Q, int64_t N, int K, const int64_t* geno_to_row, int64_t Ng, double* qg, cudaStream_t st);
 void launch_mask8(const Mask8Params& p, int sm_count, cudaStream_t st);
 
+// ---- pass 2, sparse complement form (few unobserved phenotype values): see masked_sparse.cu ----
+struct SparseMaskedParams {
+  BlockView x;           // x.v1 = missing substitute per variant
+  const double* A;       // coefficients Q^T X: [K][ldS]
+  int64_t ldS;
+  int32_t K;
+  const int32_t* idx;    // unobserved genotype-sample indices of all distinct masks, concatenated (sorted per mask)
+  const double* qm;      // [total][Kp] Q rows of those samples, Kp = K rounded up to even
+  const int64_t* off;    // [U + 1] list boundaries
+  int32_t U;
+  int32_t n_parts;       // split of every list across grid.y
+  double* comp;          // out: [n_parts][U][ldS] partial sums of r^2 over the unobserved samples
+};
+void launch_sparse_masked(const SparseMaskedParams& p, cudaStream_t st);
+void launch_gather_rows(const double* Q, int K, int Kp, const int64_t* rows, int64_t n, double* qm, cudaStream_t st);
+
 // sums the n_split partial slabs in fixed order: out[r][v] = sum_z part[z][r][v]
 void launch_reduce_splits(const double* part, double* out, int64_t rows, int64_t ld, int n_split, cudaStream_t st);
 
@@ -116,6 +132,7 @@ struct EpilogueParams {
                          // (verbose) K+P..K+2P-1 = mask^T X, K+2P..K+3P-1 = Yraw^T X
   const double* sxx;     // [ldS]
   const double* D;       // reduced [Upad][ldS] or nullptr
+  int32_t d_is_complement; // 1: D holds the sum over the UNOBSERVED samples; XdotX = xx_full - D
   const int32_t* mask_id;// [P]: -1 = fully observed phenotype, else row of D
   const double* YdotY;   // [P] of this contig
   const double* Y_scale; // [P]

@@ -105,9 +105,11 @@ def test_masked_pass_covariate_limit(rg, monkeypatch):
     mask[3, 0] = 0
     kw = dict(Y=Y * mask, Y_mask=mask, YdotY=np.sum((Y * mask)**2, axis=0), Y_scale=np.ones(P))
     monkeypatch.setenv('GLR_MASK8', '0')
+    monkeypatch.setenv('GLR_MASK_SPARSE', '0')
     with pytest.raises(ValueError, match='at most 64 covariates'):
         DeviceState(Q=Q, dof=N - K - 1, **kw)
     monkeypatch.delenv('GLR_MASK8')
+    monkeypatch.delenv('GLR_MASK_SPARSE')
     Q65 = np.linalg.qr(rg.standard_normal((N, 65)))[0]
     with pytest.raises(ValueError, match='at most 64 covariates'):
         DeviceState(Q=Q65, dof=N - 65 - 1, **kw)
