@@ -87,8 +87,8 @@ typedef struct glr_state_desc {
   /* Environment knobs read at state creation: GLR_SPLIT8 = 0 | 1 (default) | 2 selects the exact int8
    * tensor-core contraction for PLINK2 blocks never | for blocks filling >= half the SMs | always
    * (GLR_S8_PAIR = 0 | 1 (default) | 2, read per block: its CTA-pair form never | when the pairs fill | always);
-   * GLR_MASK8 = 0 | 1 (default) | 2 selects the int8 tensor-core form of the masked second pass never | for
-   * states with >= 64 distinct missingness patterns or > 32 covariates | whenever a phenotype has missing values;
+   * GLR_MASK_SPARSE / GLR_MASK8 = 0 | 1 (default) | 2 select the sparse-complement / int8 tensor-core form of the
+   * masked second pass never | when a cost model finds it the cheapest of the three forms | always;
    * GLR_KEEP_INTERCEPT keeps a constant first column of Q inside the GEMM; GLR_NO_TAIL pads the
    * column count to a multiple of 8 instead of using FP64-FMA tail columns. */
   int32_t memspace;        /* glr_memspace of Q, Y, Y_mask, YdotY, Y_scale, Y_raw (keep_idx is always
