@@ -21,7 +21,7 @@ namespace glr {
 
 constexpr int kSpThreads = 256;
 constexpr int kSpTile = 128;
-constexpr int kSpBatch = 16;
+constexpr int kSpBatch = 8;
 
 template <int FMT>
 __device__ __forceinline__ double sp_elem(const uint8_t* row, int64_t s, double miss) {
