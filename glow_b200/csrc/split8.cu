@@ -561,7 +561,7 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   const int pair_mode = pair_env ? atoi(pair_env) : 1;
   const int n_items1 = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb;
   const int n_items2 = (p.x.n_variants + 2 * kS8TileV - 1) / (2 * kS8TileV) * p.n_cb;
-  const bool pair = pair_mode > 0 && (pair_mode > 1 || n_items2 * 2 >= sm_count);
+  bool pair = pair_mode > 0 && (pair_mode > 1 || n_items2 * 2 >= sm_count);
 #ifdef GLR_S8_PROFILE
   static long long zero[160][3][8];
   cudaMemcpyToSymbol(g_s8_prof, zero, sizeof(zero));
@@ -582,8 +582,12 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, p);
-  } else {
+    if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) {  // no cluster launch on this device / partition
+      cudaGetLastError();
+      pair = false;
+    }
+  }
+  if (!pair) {
     const size_t smem = (size_t)kS8WRing * p.NC * kS8K + sizeof(Split8Smem) + 64;
     auto kern = aligned ? split8_kernel<true, false> : split8_kernel<false, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
