@@ -191,6 +191,116 @@ struct XLoaderFloat {
     xb = (double)cur[nt][g].y;
   }
 };
+// float64 / float32 arrays for the first pass: same fragment order, but the prefetch goes through a per-warp ring in
+// shared memory filled with cp.async (16 / 8 bytes per lane, zero-filled past the end of the row) instead of
+// registers: kDepth - 1 units of 32 samples are in flight per warp with no register cost, which is what it takes
+// to keep HBM busy with 9 warps per SM.  Every lane copies exactly the bytes it later reads, so completion is a
+// per-thread cp.async.wait_group.  Rows that are not 16-byte (8-byte for float) aligned use the register path.
+template <typename T, int NT, int DEPTH>
+struct XLoaderFloatAsync {
+  static constexpr int UG = 4;
+  static constexpr int kDepth = DEPTH;
+  using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+  static constexpr int kSlotT2 = NT * UG * 32;                                   // T2 elements per unit
+  static constexpr int kLutDoublesPerWarp = kDepth * kSlotT2 * (int)sizeof(T2) / 8;
+  XLoaderFloat<T, NT> fb;  // register path (unaligned rows)
+  const T* row[NT];
+  T2 cur[NT][UG];
+  int64_t n;
+  int joff, lane, slot_w, slot_r;
+  uint32_t ring;  // shared-memory address of this warp's ring
+  bool vec, primed;
+
+  __device__ __forceinline__ void init(const BlockView& x, int v0, int r, int j, double* warp_smem, int lane_) {
+    n = x.n_geno;
+    joff = 2 * j;
+    lane = lane_;
+    vec = ((reinterpret_cast<uintptr_t>(x.base) | (uintptr_t)x.stride) & (2 * sizeof(T) - 1)) == 0;
+    ring = smem_u32(warp_smem);
+    slot_w = slot_r = 0;
+    primed = false;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      int v = min(v0 + nt * 8 + r, x.n_variants - 1);
+      row[nt] = reinterpret_cast<const T*>(x.base + (int64_t)v * x.stride);
+    }
+    if (!vec) fb.init(x, v0, r, j, warp_smem, lane_);
+  }
+  __device__ __forceinline__ void issue(int64_t s0) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int g = 0; g < UG; ++g) {
+        const int64_t s = s0 + 8 * g + joff;
+        const int64_t left = n - s;
+        const uint32_t bytes = left >= 2 ? 2u * (uint32_t)sizeof(T) : (left == 1 ? (uint32_t)sizeof(T) : 0u);
+        const T* src = row[nt] + (left > 0 ? s : 0);
+        const uint32_t dst = ring + (uint32_t)(((slot_w * NT + nt) * UG + g) * 32 + lane) * (uint32_t)sizeof(T2);
+        if (sizeof(T) == 8)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+      }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    slot_w = slot_w + 1 == kDepth ? 0 : slot_w + 1;
+  }
+  // load(s0): the unit starting at sample s0 must be available at the next advance()
+  __device__ __forceinline__ void load(int64_t s0) {
+    if (!vec) {
+      fb.load(s0);
+      return;
+    }
+    if (!primed) {
+#pragma unroll
+      for (int d = 0; d < kDepth - 2; ++d) issue(s0 + d * (UG * 8));
+      primed = true;
+    }
+    issue(s0 + (kDepth - 2) * (UG * 8));  // kDepth - 1 groups are now in flight
+  }
+  __device__ __forceinline__ void advance() {
+    if (!vec) {
+      fb.advance();
+      return;
+    }
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kDepth - 2) : "memory");  // the oldest group has landed
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int g = 0; g < UG; ++g) {
+        const uint32_t a = ring + (uint32_t)(((slot_r * NT + nt) * UG + g) * 32 + lane) * (uint32_t)sizeof(T2);
+        if (sizeof(T) == 8) {
+          double2 v;
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(a));
+          cur[nt][g].x = v.x;
+          cur[nt][g].y = v.y;
+        } else {
+          float2 v;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(a));
+          cur[nt][g].x = v.x;
+          cur[nt][g].y = v.y;
+        }
+      }
+    slot_r = slot_r + 1 == kDepth ? 0 : slot_r + 1;
+  }
+  __device__ __forceinline__ void get(int g, int nt, double& xa, double& xb) const {
+    if (!vec) {
+      fb.get(g, nt, xa, xb);
+      return;
+    }
+    xa = (double)cur[nt][g].x;
+    xb = (double)cur[nt][g].y;
+  }
+};
+
+// loader of the first pass: the cp.async ring for float formats, the plain loaders otherwise.  The ring depth is what
+// fits next to the W ring (8 warps x 4 KB per unit for f64; the W ring is 8 stages deep up to 4 m-tiles, 4 beyond).
+template <int FMT, int NT, int MT>
+struct GramLoader : XLoader<FMT, NT> {};
+template <int NT, int MT>
+struct GramLoader<GLR_FMT_F64, NT, MT> : XLoaderFloatAsync<double, NT, (MT <= 2 ? 4 : (MT == 4 ? 2 : 3))> {};
+template <int NT, int MT>
+struct GramLoader<GLR_FMT_F32, NT, MT> : XLoaderFloatAsync<float, NT, (MT <= 2 ? 4 : (MT == 4 ? 2 : 3))> {};
+
 template <int NT>
 struct XLoader<GLR_FMT_F64, NT> : XLoaderFloat<double, NT> {};
 template <int NT>
@@ -274,7 +384,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kStageDoubles = kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup);
   constexpr uint32_t kStageBytes = kStageDoubles * 8;
-  using Loader = XLoader<FMT, NT>;
+  using Loader = GramLoader<FMT, NT, MT>;
   constexpr int UG = Loader::UG;
   constexpr int UPC = kChunkGroups / UG;  // units per chunk
 
@@ -585,7 +695,7 @@ void launch_gram_inst(const GramParams& p, cudaStream_t st) {
   const int tile = WARPS * NT * 8;
   dim3 grid((unsigned)ceil_div(p.x.n_variants, tile), (unsigned)p.n_groups, (unsigned)p.n_split);
   const size_t smem = kBarBytes + (size_t)(MT <= 4 ? kMaxStages : kStages) * kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup) * 8 +
-                      (size_t)WARPS * XLoader<FMT, NT>::kLutDoublesPerWarp * 8;
+                      (size_t)WARPS * GramLoader<FMT, NT, MT>::kLutDoublesPerWarp * 8;
   auto kern = gram_kernel<FMT, MT, NT, TAIL, WARPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<grid, (WARPS + 1) * 32, smem, st>>>(p);
