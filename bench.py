@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--variants-per-step', type=int, default=148 * 256)
     ap.add_argument('--samples', type=int, default=N_SAMPLES)
-    ap.add_argument('--e2e-subblocks', type=int, default=8)
+    ap.add_argument('--e2e-subblocks', type=int, default=32)
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-peak', action='store_true', help='do not run the cuBLAS DGEMM peak measurement (ncu runs)')
