@@ -373,11 +373,11 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   const size_t w_bytes = (size_t)C * st->w_contig_doubles * sizeof(double);
   CU(cudaMalloc(&st->wpk, w_bytes));
   CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
-  // integer tensor-core operand (split8.cu): non-verbose states, any number of columns (blocks of up to 18)
+  // integer tensor-core operand (split8.cu): any number of columns (blocks of up to 18)
   double* d_colmax = nullptr;
   // GLR_SPLIT8: 0 = never, 1 (default) = PLINK2 blocks that fill at least half the SMs, 2 = every PLINK2 block
   const int split8_mode = getenv("GLR_SPLIT8") ? atoi(getenv("GLR_SPLIT8")) : 1;
-  if (split8_mode > 0 && !st->verbose && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
+  if (split8_mode > 0 && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
     st->s8_cols = st->Mcols;
     split8_geometry(st->s8_cols, &st->s8_ncb, &st->s8_cpb, &st->s8_NC);
     st->s8_stages = ceil_div(Ng, 128);
@@ -407,6 +407,11 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
       if (Kg > 0)
         launch_pack_split8(dQ, N, K, st->has_icpt, Kg, d_colmax, d_g2r, Ng, d8, 0, st->s8_cpb, st->s8_NC, st->s8_stages, s0);
       launch_pack_split8(dY, N, P, 0, P, d_colmax + Kg, d_g2r, Ng, d8, Kg, st->s8_cpb, st->s8_NC, st->s8_stages, s0);
+      if (st->verbose) {  // mask and raw-phenotype columns of the verbose outputs (lin_reg.py:234-237)
+        launch_pack_split8(dM, N, P, 0, P, d_colmax + Kg + P, d_g2r, Ng, d8, Kg + P, st->s8_cpb, st->s8_NC, st->s8_stages, s0);
+        launch_pack_split8(dYraw, N, P, 0, P, d_colmax + Kg + 2 * P, d_g2r, Ng, d8, Kg + 2 * P, st->s8_cpb, st->s8_NC,
+                           st->s8_stages, s0);
+      }
       CU(cudaMemcpyAsync(st->s8_scale + (int64_t)c * st->s8_cols, d_colmax, (size_t)st->s8_cols * sizeof(double),
                          cudaMemcpyDeviceToDevice, s0));
     }
