@@ -631,8 +631,16 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   x.n_geno = st->Ng;
   x.v1 = L.v1.as<double>();
 
-  const bool use_split8 =
-      st->split8 && b->format == GLR_FMT_PLINK2 && (st->split8 >= 2 || ceil_div(G, 128) * st->s8_ncb * 2 >= st->sm_count);
+  // int8 tensor-core first pass when it is the faster one: a tile of 128 variants costs n_stages x ~540 cycles on one SM
+  // however few tiles there are, the DMMA kernel (which can split the samples of a small block over the SMs) about
+  // 30 TFLOP/s on the padded column count plus its pre-pass
+  bool use_split8 = false;
+  if (st->split8 && b->format == GLR_FMT_PLINK2) {
+    const double waves = (double)ceil_div(ceil_div(G, 128) * st->s8_ncb, (int64_t)st->sm_count);
+    const double t_s8 = waves * (double)st->s8_stages * 540.0 / 1.7e9;
+    const double t_dmma = (double)G * (2.0 * (double)st->Ng * (double)Mpad / 30e12 + (double)st->Ng / 4.0 / 5e12);
+    use_split8 = st->split8 >= 2 || t_s8 < t_dmma;
+  }
   const bool fused_counts = use_split8 && st->n_drop == 0;
   CU(cudaEventRecord(L.ev[0], s));
   // ---- pre-pass (A0): missing substitute + sum of squares from integer counts ----

@@ -85,7 +85,7 @@ typedef struct glr_state_desc {
   int32_t max_block_variants; /* hint for workspace sizing (grown on demand) */
   int32_t n_lanes;         /* independent in-flight blocks (streams); 0 -> default 2 */
   /* Environment knobs read at state creation: GLR_SPLIT8 = 0 | 1 (default) | 2 selects the exact int8
-   * tensor-core contraction for PLINK2 blocks never | for blocks filling >= half the SMs | always
+   * tensor-core contraction for PLINK2 blocks never | when a time model says it beats the DMMA kernel | always
    * (GLR_S8_PAIR = 0 | 1 (default) | 2, read per block: its CTA-pair form never | when the pairs fill | always);
    * GLR_MASK_SPARSE / GLR_MASK8 = 0 | 1 (default) | 2 select the sparse-complement / int8 tensor-core form of the
    * masked second pass never | when a cost model finds it the cheapest of the three forms | always;
