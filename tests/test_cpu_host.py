@@ -223,6 +223,35 @@ def test_plink_source_and_block_checks(golden_dir):
         glow_b200.PlinkBedSource(d['bed'].tobytes(), 9)  # 10 payload bytes are not a multiple of ceil(9/4) = 3
 
 
+def test_plink_file_is_streamed_block_by_block(tmp_path):
+    """A .bed path is read block by block into a ring of staging buffers (parallel preadv); the blocks must be the file's
+    rows in order, including the ragged last block, and a view must stay valid until three more blocks were read."""
+    import glow_b200
+    rg = np.random.default_rng(5)
+    N, G = 1003, 700
+    rb = (N + 3) // 4
+    body = rg.integers(0, 256, (G, rb), dtype=np.uint8)
+    path = tmp_path / 'chr.bed'
+    path.write_bytes(bytes([0x6c, 0x1b, 0x01]) + body.tobytes())
+    src = glow_b200.PlinkBedSource(str(path), N, block_variants=256, read_threads=3)
+    seen, g0 = [], 0
+    for meta, blk in src.blocks():
+        assert blk.format == 'plink2' and len(meta) == blk.data.shape[0]
+        assert np.array_equal(blk.data, body[g0:g0 + blk.data.shape[0]])
+        seen.append((blk.data, g0))
+        if len(seen) >= 3:  # the block two reads back still owns its buffer
+            old, og = seen[-3]
+            assert np.array_equal(old, body[og:og + old.shape[0]])
+        g0 += blk.data.shape[0]
+    assert g0 == G and len(seen) == 3
+    assert meta.index[-1] == G - 1
+    (tmp_path / 'bad.bed').write_bytes(b'\x00\x00\x00' + body.tobytes())
+    with pytest.raises(ValueError):
+        glow_b200.PlinkBedSource(str(tmp_path / 'bad.bed'), N)
+    with pytest.raises(ValueError):
+        glow_b200.PlinkBedSource(str(path), N + 4)
+
+
 def test_arrow_list_columns_become_blocks_without_copy():
     import pyarrow as pa
     from glow_b200.engine import as_block
