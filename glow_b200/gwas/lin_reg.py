@@ -263,7 +263,11 @@ def _run_source(source, Y_state, phenotype_names, verbose_output, np_dt) -> pd.D
     def work():
         for meta, block in source.blocks():
             if is_loco:
-                for contig in pd.unique(meta['contigName']):
+                contigs = pd.unique(meta['contigName'])
+                if len(contigs) == 1:  # the usual case (variants sorted by chromosome): no gather, the block goes as is
+                    yield meta, block, Y_state[contigs[0]]._contig_index
+                    continue
+                for contig in contigs:
                     sel = (meta['contigName'] == contig).to_numpy()
                     sub = GenotypeBlock(np.ascontiguousarray(block.data[sel]), block.format, block.missing)
                     yield meta[sel], sub, Y_state[contig]._contig_index
