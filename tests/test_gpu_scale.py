@@ -84,6 +84,36 @@ def test_config3_shape_plink_subset(rg):
     eng.close()
 
 
+def test_config3_shape_with_missing_phenotype_values(rg, monkeypatch):
+    """configs[2] shape with what phenotypes look like in practice: 2 % of the values unobserved.  The three forms of the
+    masked pass (sparse complement = the default here, FP64 DMMA, int8 tensor cores) must agree with the oracle on a subset
+    and with one another on the whole block."""
+    from glow_b200.engine import GenotypeBlock
+    N, G, K, P = 500_000, 512, 16, 2
+    cov = pd.DataFrame(rg.standard_normal((N, K)))
+    states = _hardcalls(rg, G, N)
+    Y = rg.standard_normal((N, P)) + 0.02 * states[:P].T
+    Y[rg.random((N, P)) < 0.02] = np.nan
+    phe = pd.DataFrame(Y)
+    packed = pack_plink(states)
+    results = {}
+    for form, env in (('sparse', {}), ('dmma', {'GLR_MASK_SPARSE': '0', 'GLR_MASK8': '0'}), ('int8', {'GLR_MASK8': '2'})):
+        for k in ('GLR_MASK_SPARSE', 'GLR_MASK8'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng, st = _engine_for(phe, cov)
+        assert eng.unique_masks == P
+        results[form] = eng.run(GenotypeBlock(packed, 'plink2', 'mean'))
+        eng.close()
+    idx = np.sort(rg.choice(G, 8, replace=False))
+    ref = orc.block_stats(orc.mean_substitute(states[idx].astype(np.float64)), st)
+    for form, res in results.items():
+        assert_stats_close({k: res[k][:, idx] for k in STATS}, ref, label=f'cfg3 missing phenotype, {form} form')
+    for form in ('dmma', 'int8'):
+        assert_stats_close(results[form], results['sparse'], label=f'{form} vs sparse form')
+
+
 def test_config4_shape_many_masked_phenotypes(rg):
     """configs[3] shape scaled in G: 50k samples x 2 000 phenotypes with 10 % missing each, 2-bit genotypes."""
     from glow_b200.engine import GenotypeBlock
