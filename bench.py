@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument('--e2e-subblocks', type=int, default=32)
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-dmma-arm', action='store_true', help='primary path only (ncu launch lists of the step)')
     ap.add_argument('--skip-peak', action='store_true', help='do not run the cuBLAS DGEMM peak measurement (ncu runs)')
     ap.add_argument('--cpu-block-variants', type=int, default=128)
     return ap.parse_args()
@@ -359,13 +360,15 @@ def main():
     t_primary = outs['tvalue'].clone()
 
     # secondary arm in the same run: the FP64 tensor-core (DMMA) path forced for the same batch
-    os.environ['GLR_SPLIT8'] = '0'
-    state_dmma = gdist.device_state_from_flat(flat, header, local_rank, n_lanes=1)
-    os.environ.pop('GLR_SPLIT8', None)
-    ms_dmma, stage_dmma, _, _ = measure(state_dmma, False)
-    paths_agree = bool(torch.allclose(outs['tvalue'], t_primary, rtol=1e-9, atol=1e-12, equal_nan=True))
-    state_dmma.close()
-    state.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=True)
+    ms_dmma, stage_dmma, paths_agree = None, None, None
+    if not args.skip_dmma_arm:
+        os.environ['GLR_SPLIT8'] = '0'
+        state_dmma = gdist.device_state_from_flat(flat, header, local_rank, n_lanes=1)
+        os.environ.pop('GLR_SPLIT8', None)
+        ms_dmma, stage_dmma, _, _ = measure(state_dmma, False)
+        paths_agree = bool(torch.allclose(outs['tvalue'], t_primary, rtol=1e-9, atol=1e-12, equal_nan=True))
+        state_dmma.close()
+        state.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=True)
 
     # sanity: results are real numbers for (nearly) all variants
     pv = outs['pvalue']
@@ -526,8 +529,8 @@ def main():
             }
         }
         dmma_cols = (cols // 8) * 8 if 1 <= cols % 8 <= 3 and cols // 8 >= 1 else ((cols + 7) // 8) * 8
-        d_s = stage_dmma['gram_ms'] / 1e3
-        dmma = {
+        d_s = stage_dmma['gram_ms'] / 1e3 if stage_dmma else float('nan')
+        dmma = None if stage_dmma is None else {
             'note': 'same batch through the FP64 tensor-core path (GLR_SPLIT8=0): what float / dosage input, verbose '
                     'states and small blocks use',
             'value': world * G * P / (ms_dmma / 1e3),
