@@ -471,6 +471,18 @@ def main():
             except Exception as exc:  # noqa: BLE001
                 int8_peak = 4280.0
                 int8_src = f'tcgen05.mma kind::i8 issue-rate microbenchmark (torch._int_mm unavailable: {type(exc).__name__})'
+        # what the int8 tensor pipe does on this box right now: back-to-back tcgen05.mma with resident operands on every
+        # SM, ~6 ms (long enough for the clocks to settle), through the library's own probe
+        issue_rate, issue_src = 4340.0, 'benchmarks/micro/umma_i8_ts.cu (0.6 ms burst, measured earlier on this pool)'
+        if not args.skip_peak:
+            try:
+                import ctypes as C
+                from glow_b200 import _capi
+                r = C.c_double()
+                _capi.check(_capi.load().glr_tensor_i8_issue_rate(local_rank, 6.0, C.byref(r)))
+                issue_rate, issue_src = float(r.value), 'glr_tensor_i8_issue_rate: 6 ms of back-to-back tcgen05.mma kind::i8, measured in this run'
+            except Exception as exc:  # noqa: BLE001
+                issue_src += f' (live probe failed: {type(exc).__name__})'
         # Executed formulation: S = [Q(:,1:) | Ytilde]^T X.  The intercept column of Q is constant, so its product
         # with x is q0 * sum(x) and comes from the genotype counts: its flops are NOT executed and not counted.
         cols = (K - 1) + P
@@ -490,21 +502,22 @@ def main():
                       '2-bit decode + genotype counts fused, FP64 recombination in the epilogue)',
             'bound': 'tensor',
             'achieved': achieved,
-            'peak': int8_peak,
+            'peak': issue_rate,
             'unit': 'TFLOP/s',
             'op_type': 'int8 tensor-core operations (2 per multiply-accumulate), algorithmic = digit rows actually needed',
-            'frac': achieved / int8_peak,
+            'frac': achieved / issue_rate,
             # dram bytes of one launch at the default shape, ncu --set full, profiles/r01_split8_full.txt
             'traffic': 4.876e9 if (n == N_SAMPLES and G == 148 * 256) else None,
-            'peak_source': int8_src,
-            # back-to-back tcgen05.mma kind::i8 from one thread per SM, operands resident (benchmarks/micro/umma_i8_ts.cu):
-            # 64 clk per M128 N128 K32 = 4.34 Pop/s in a 0.6 ms burst; a library GEMM and this kernel both run below it
-            'frac_of_mma_issue_rate': achieved / 4340.0,
-            'note': 'frac can exceed 1: the peak is a library GEMM on random int8 data measured in this run (as '
-                    'MEASURED_PEAKS.json does for bf16: 1625 TFLOP/s burst, i.e. 3250 TOP/s for int8 on the same pipe); '
-                    'under either load the board sits at its power cap and the SM clock drops (ncu: 1.59 GHz with the '
-                    'tensor pipe 97.5 % active for this kernel), and this kernel\'s operands (genotypes 0/1/2 and a sparse '
-                    'missing-call indicator) toggle fewer bits than random data, so it holds a higher clock',
+            'peak_source': issue_src,
+            # back-to-back tcgen05.mma kind::i8 from one thread per SM, operands resident: 64 clk per M128 N128 K32; a
+            # library GEMM and this kernel both run below it
+            'library_int8_gemm_tops': int8_peak,
+            'library_int8_gemm_source': int8_src,
+            'frac_of_library_int8_gemm': achieved / int8_peak,
+            'note': 'peak = the int8 tensor pipe fed back to back with constant resident operands on every SM (it holds '
+                    '~1.9 GHz); a library int8 GEMM on random data (as MEASURED_PEAKS.json measures bf16: 1625 TFLOP/s burst, '
+                    'i.e. 3250 TOP/s for int8 on the same pipe) runs BELOW this kernel: under a real load the board sits at '
+                    'its power cap and the SM clock drops (ncu: 1.59 GHz with the tensor pipe 97.5 % active for this kernel)',
             'ops_per_launch_algorithmic': ops_int8,
             'issued_tops_incl_padding': ops_int8_issued / gram_s / 1e12,
             'fp64_equivalent_tflops': flops_f64_equiv / gram_s / 1e12,

@@ -60,6 +60,7 @@ SYMBOLS = {
     'glr_host_free': (C.c_int, [C.c_void_p]),
     'glr_t_two_sided_pvalues': (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     'glr_decode_block': (C.c_int, [C.c_int, C.POINTER(BlockDesc), C.c_int64, C.c_void_p]),
+    'glr_tensor_i8_issue_rate': (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -895,6 +895,19 @@ int glr_host_free(void* ptr) {
   return 0;
 }
 
+int glr_tensor_i8_issue_rate(int device, double milliseconds, double* tops) {
+  if (!tops || !(milliseconds > 0.0)) return fail(GLR_ERR_INVALID, "bad arguments");
+  int rc = check_device(device);
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  int sm_count = 0;
+  CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  const double r = measure_s8_issue_rate(sm_count, milliseconds, nullptr);
+  if (r < 0.0) return fail(GLR_ERR_CUDA, "tensor-core issue-rate probe failed");
+  *tops = r;
+  return 0;
+}
+
 int glr_t_two_sided_pvalues(int device, const double* tvalues, int64_t n, double dof, double* pvalues) {
   if (n < 0 || (n > 0 && (!tvalues || !pvalues))) return fail(GLR_ERR_INVALID, "bad arguments");
   int rc = check_device(device);

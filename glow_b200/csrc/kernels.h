@@ -61,6 +61,7 @@ struct Split8Params {
 };
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st);
 void split8_geometry(int n_cols, int* n_cb, int* cpb, int* NC);
+double measure_s8_issue_rate(int sm_count, double ms_target, cudaStream_t st);  // TOP/s, < 0 on failure
 void launch_pack_split8(const double* src, int64_t N, int64_t ld, int c0, int ncols, double* colmax_scratch,
                         const int64_t* geno_to_row, int64_t Ng, int8_t* dst, int dst_col0, int cpb, int NC,
                         int64_t n_stages, cudaStream_t st);

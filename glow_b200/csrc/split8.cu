@@ -613,6 +613,89 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Issue-rate probe: every SM issues `iters` x 8 back-to-back tcgen05.mma kind::i8 (A in TMEM, B in shared memory,
+// M128 N128 K32, operands resident, two accumulators alternating as in split8_kernel) and nothing else.  bench.py runs
+// it next to the real kernel so that the roofline's "what the tensor pipe can do on this box, right now" is measured,
+// not quoted.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) s8_issue_rate_kernel(int iters) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 2 * 128 * kS8K / 4; i += 128) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x01010101u;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  {
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0x01010101u;
+    tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + kS8ColA, v);
+    tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + kS8ColA + 16, v);
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) {
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t base = smem_u32(smem_raw);
+    for (int it = 0; it < iters; ++it) {
+      const uint64_t db0 = s8_desc(base + (uint32_t)(it & 1) * 128 * kS8K);
+      if (s8_elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          s8_mma_ts(tmem, tmem + kS8ColA + kk * 8, db0 + (uint64_t)(kk * 2), idesc, 1u);
+          s8_mma_ts(tmem + kS8ColDe, tmem + kS8ColA + kk * 8, db0 + (uint64_t)(kk * 2), idesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (s8_elect_one()) s8_commit(&bar);
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+}
+
+// returns the int8 tensor-core rate in TOP/s (2 ops per multiply-accumulate) of a run of about `ms_target` milliseconds
+double measure_s8_issue_rate(int sm_count, double ms_target, cudaStream_t st) {
+  const size_t smem = (size_t)2 * 128 * kS8K + 1024;
+  cudaFuncSetAttribute(s8_issue_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  s8_issue_rate_kernel<<<sm_count, 128, smem, st>>>(64);  // warm-up
+  // 8 MMAs of 64 cycles per iteration at roughly 1.8 GHz
+  const int iters = std::max(256, (int)(ms_target * 1e-3 * 1.8e9 / (8 * 64)));
+  cudaEventRecord(e0, st);
+  s8_issue_rate_kernel<<<sm_count, 128, smem, st>>>(iters);
+  cudaEventRecord(e1, st);
+  double tops = -1.0;
+  if (cudaEventSynchronize(e1) == cudaSuccess && cudaGetLastError() == cudaSuccess) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    tops = 2.0 * (double)sm_count * iters * 8.0 * 128.0 * 128.0 * 32.0 / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return tops;
+}
+
+// ------------------------------------------------------------------------------------------------
 // packing: W (row-major [N x ld], columns c0..c0+ncols) -> per column block and 128-sample stage a
 // swizzled image [NC digit rows][128 bytes]; row of (local column c, digit i) = 7 c + i, row 7 cpb = ones.
 // Inside each 16-sample group the bytes follow the sample order the decode produces (see split8_kernel).

@@ -170,6 +170,12 @@ int glr_t_two_sided_pvalues(int device, const double* tvalues, int64_t n, double
  * tests the fused decode against PlinkReaderSuite / MeanSubstitute semantics. */
 int glr_decode_block(int device, const glr_block_desc* blk, int64_t n_geno_samples, double* out_values);
 
+/* Measurement aid (no reference counterpart): the int8 tensor-core rate of this device right now, in TOP/s
+ * (2 operations per multiply-accumulate), from a run of about `milliseconds` of back-to-back
+ * tcgen05.mma kind::i8 with resident operands on every SM -- the upper bound of the int8 first pass.
+ * bench.py reports it next to the roofline of that kernel. */
+int glr_tensor_i8_issue_rate(int device, double milliseconds, double* tops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -192,6 +192,16 @@ def test_error_codes(rg):
     eng.close()
 
 
+def test_tensor_issue_rate_probe():
+    """The measurement aid bench.py uses as the roofline ceiling of the int8 first pass."""
+    from glow_b200 import _capi
+    r = C.c_double()
+    _capi.check(_capi.load().glr_tensor_i8_issue_rate(0, 1.0, C.byref(r)))
+    assert 1000.0 < r.value < 9000.0  # dense int8 on a B200: 4.5 POP/s nominal
+    with pytest.raises(ValueError):
+        _capi.check(_capi.load().glr_tensor_i8_issue_rate(0, 0.0, C.byref(r)))
+
+
 def test_smoke_entry_point():
     import __graft_entry__ as ge
     ge.smoke()
