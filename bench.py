@@ -602,6 +602,9 @@ def main():
             'scaling': 'weak',
             'vs_baseline': None,
             'dtype': 'f64',
+            'dtype_detail': 'results and the DMMA path are FP64; the default first pass computes the same FP64 contraction '
+                            'exactly as int8 x int8 -> int32 tensor-core products of a 55-bit fixed-point operand '
+                            '(7 radix-256 digits), recombined in FP64',
             'data': 'synthetic',
             'config': workload_config(args, G),
             'clocks': clocks,
