@@ -1,14 +1,14 @@
 // Pass 2 for states with FEW missing phenotype values (the usual case: a handful of phenotypes, each with a few percent
 // of the samples unobserved):  D_u[v] = sum_s mask_u[s] r_v[s]^2  =  |r_v|^2  -  sum_{s : mask_u[s] = 0} r_v[s]^2.
 // The first term is the fully observed XdotX the epilogue already has (sum x^2 - |Q^T x|^2); this kernel evaluates the
-// COMPLEMENT: r_v[s] = x_v[s] - q_s . (Q^T x_v) only at the unobserved samples of each distinct mask, with FP64 FMAs.
-// Work is K FMAs per (variant, unobserved sample) instead of a dense N x U contraction: at the UK-Biobank shape with 2 %
-// of one phenotype missing that is 10 000 samples per variant instead of 500 000.
+// COMPLEMENT: r_v[s] = x_v[s] - q_s . (Q^T x_v) only at the unobserved samples of each distinct mask, on the FP64
+// tensor cores.  Work is 2 K flops per (variant, unobserved sample) instead of a dense N x U contraction: at the
+// UK-Biobank shape with 2 % of one phenotype missing that is 10 000 samples per variant instead of 500 000.
 //
-// Block = 8 warps, lane = variant (256 consecutive variants); grid.y splits a mask's list of unobserved samples, grid.z
-// walks the masks.  The Q rows of 128 list entries are staged in shared memory and read as warp-wide broadcasts
-// (16 bytes = two coefficients per load); the genotype of the entry is gathered from the lane's own packed row (the list
-// is sorted, so a lane walks forward through its row and re-uses the sectors it has pulled into L1).
+// Block = 8 warps, each with NV blocks of 8 variants (256 variants per block for NV = 4); grid.y splits a mask's sorted
+// list of unobserved samples, grid.z walks the masks.  The Q rows of 128 list entries are staged in shared memory; the
+// genotypes of the entries are gathered from the packed rows (the list is sorted, so a lane walks forward through its
+// rows and re-uses the sectors it has pulled into L1).
 #include <algorithm>
 #include <cstdlib>
 
@@ -21,7 +21,6 @@ namespace glr {
 
 constexpr int kSpThreads = 256;
 constexpr int kSpTile = 128;
-constexpr int kSpBatch = 8;
 
 template <int FMT>
 __device__ __forceinline__ double sp_elem(const uint8_t* row, int64_t s, double miss) {
@@ -35,65 +34,13 @@ __device__ __forceinline__ double sp_elem(const uint8_t* row, int64_t s, double 
   return XLoader<GLR_FMT_PLINK2, 1>::dec(code, miss);
 }
 
-// KT: compile-time bound of Kp = K rounded up to even (coefficients stay in registers)
-template <int FMT, int KT>
-__global__ void __launch_bounds__(kSpThreads) sparse_masked_kernel(const SparseMaskedParams p) {
-  extern __shared__ __align__(16) unsigned char sp_smem[];
-  const int Kp = (p.K + 1) & ~1;
-  double* qs = reinterpret_cast<double*>(sp_smem);                        // [128][Kp]
-  int32_t* sidx = reinterpret_cast<int32_t*>(qs + (size_t)kSpTile * Kp);  // [128]
-  const int u = blockIdx.z;
-  const int64_t l0 = p.off[u], l1 = p.off[u + 1];
-  const int64_t per = ceil_div(l1 - l0, (int64_t)gridDim.y);
-  const int64_t j0 = l0 + (int64_t)blockIdx.y * per, j1 = min(l1, j0 + per);
-
-  const int vraw = blockIdx.x * kSpThreads + threadIdx.x;
-  const int v = min(vraw, p.x.n_variants - 1);
-  const uint8_t* row = p.x.base + (int64_t)v * p.x.stride;
-  const double miss = (FMT == GLR_FMT_I8 || FMT == GLR_FMT_PLINK2) ? p.x.v1[v] : 0.0;
-  double a[KT];
-#pragma unroll
-  for (int k = 0; k < KT; ++k) a[k] = k < p.K ? p.A[(int64_t)k * p.ldS + v] : 0.0;
-
-  double acc = 0.0;
-  for (int64_t t0 = j0; t0 < j1; t0 += kSpTile) {
-    const int cnt = (int)min((int64_t)kSpTile, j1 - t0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < cnt * Kp; i += kSpThreads) qs[i] = p.qm[t0 * Kp + i];
-    if ((int)threadIdx.x < cnt) sidx[threadIdx.x] = p.idx[t0 + threadIdx.x];
-    __syncthreads();
-    // kSpBatch gathers are issued back to back before their FMA chains: the gathers are what the kernel waits for
-    // (each one is a sector of a different row), so memory-level parallelism per lane is what matters
-    for (int jb = 0; jb < cnt; jb += kSpBatch) {
-      double r[kSpBatch];
-#pragma unroll
-      for (int i = 0; i < kSpBatch; ++i) r[i] = jb + i < cnt ? sp_elem<FMT>(row, (int64_t)sidx[jb + i], miss) : 0.0;
-#pragma unroll
-      for (int i = 0; i < kSpBatch; ++i) {
-        if (jb + i < cnt) {
-          const double2* q2 = reinterpret_cast<const double2*>(qs + (size_t)(jb + i) * Kp);
-#pragma unroll
-          for (int k = 0; k < KT; k += 2) {
-            if (k < Kp) {
-              const double2 q = q2[k >> 1];  // warp-wide broadcast
-              r[i] = fma(-q.x, a[k], r[i]);
-              r[i] = fma(-q.y, a[k + 1], r[i]);
-            }
-          }
-          acc = fma(r[i], r[i], acc);
-        }
-      }
-    }
-  }
-  if (vraw < p.x.n_variants) p.comp[((int64_t)blockIdx.y * p.U + u) * p.ldS + vraw] = acc;
-}
-
-// DMMA form of the same sum.  The residuals of 8 variants x 8 list entries are one m8n8k4 accumulator tile:
+// The residuals of 8 variants x 8 list entries are one m8n8k4 accumulator tile:
 //   C[variant r][entry c] = x  -  sum_k a[variant r][k] Q[entry c][k]     (ceil(K/4) DMMAs, C initialised with x)
 // A operand = -a (per lane KT4 values per variant block, kept in registers for the whole kernel), B operand = the Q rows of
 // the 8 entries (one LDS.64 per k-step from the tile in shared memory, re-used by the warp's NV variant blocks), and
-// the lane then squares its two residuals into a per-variant-row accumulator.  Against the FMA kernel above this is one
-// DMMA per 64 x 4 multiply-adds instead of one DFMA per 32: 5x fewer instructions for the same FP64 datapath time.
+// the lane then squares its two residuals into a per-variant-row accumulator.  (A first version with one DFMA chain per
+// (variant, entry) kept the FP64 pipe 14 % busy: one DMMA per 64 x 4 multiply-adds instead of one DFMA per 32 is 5x
+// fewer instructions for the same FP64 datapath time.)
 // Lane (r, j) = 4 r + j of the m8n8k4 fragment layout: A[r][j], B[j][r], C[r][2j..2j+1].
 template <int FMT, int KT4, int NV>
 __global__ void __launch_bounds__(kSpThreads) sparse_dmma_kernel(const SparseMaskedParams p) {
@@ -186,39 +133,13 @@ static void launch_spd_fmt(const SparseMaskedParams& p, cudaStream_t st) {
   else launch_spd<FMT, 16, 2>(p, st);
 }
 
-template <int FMT, int KT>
-static void launch_sp_kt(const SparseMaskedParams& p, cudaStream_t st) {
-  const int Kp = (p.K + 1) & ~1;
-  const size_t smem = (size_t)kSpTile * Kp * sizeof(double) + kSpTile * sizeof(int32_t);
-  cudaFuncSetAttribute(sparse_masked_kernel<FMT, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const dim3 grid((unsigned)ceil_div(p.x.n_variants, kSpThreads), (unsigned)p.n_parts, (unsigned)p.U);
-  sparse_masked_kernel<FMT, KT><<<grid, kSpThreads, smem, st>>>(p);
-}
-template <int FMT>
-static void launch_sp_fmt(const SparseMaskedParams& p, cudaStream_t st) {
-  if (p.K <= 12) launch_sp_kt<FMT, 12>(p, st);
-  else if (p.K <= 18) launch_sp_kt<FMT, 18>(p, st);
-  else if (p.K <= 24) launch_sp_kt<FMT, 24>(p, st);
-  else launch_sp_kt<FMT, 64>(p, st);
-}
-
 void launch_sparse_masked(const SparseMaskedParams& p, cudaStream_t st) {
   if (p.x.n_variants <= 0 || p.U <= 0) return;
-  static const bool use_fma = getenv("GLR_SPARSE_FMA") != nullptr;  // the plain FMA kernel, kept for comparison
-  if (!use_fma) {
-    switch (p.x.format) {
-      case GLR_FMT_F64: launch_spd_fmt<GLR_FMT_F64>(p, st); break;
-      case GLR_FMT_F32: launch_spd_fmt<GLR_FMT_F32>(p, st); break;
-      case GLR_FMT_I8: launch_spd_fmt<GLR_FMT_I8>(p, st); break;
-      default: launch_spd_fmt<GLR_FMT_PLINK2>(p, st); break;
-    }
-    return;
-  }
   switch (p.x.format) {
-    case GLR_FMT_F64: launch_sp_fmt<GLR_FMT_F64>(p, st); break;
-    case GLR_FMT_F32: launch_sp_fmt<GLR_FMT_F32>(p, st); break;
-    case GLR_FMT_I8: launch_sp_fmt<GLR_FMT_I8>(p, st); break;
-    default: launch_sp_fmt<GLR_FMT_PLINK2>(p, st); break;
+    case GLR_FMT_F64: launch_spd_fmt<GLR_FMT_F64>(p, st); break;
+    case GLR_FMT_F32: launch_spd_fmt<GLR_FMT_F32>(p, st); break;
+    case GLR_FMT_I8: launch_spd_fmt<GLR_FMT_I8>(p, st); break;
+    default: launch_spd_fmt<GLR_FMT_PLINK2>(p, st); break;
   }
 }
 
