@@ -8,13 +8,42 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libglow_b200.so')
 
-GLR_ABI_VERSION = 1
+GLR_ABI_VERSION = 2
 FMT_F64, FMT_F32, FMT_I8, FMT_PLINK2 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 MISSING_AS_MINUS_ONE, MISSING_MEAN = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = -1, -2, -3, -4
 
+AUTO, OFF, FORCE = 0, 1, 2  # glr_tristate
+PATH_SPLIT8, PATH_SPLIT8_PAIR, PATH_SPLIT8_NSPLIT, PATH_PREPASS, PATH_DMMA = 1, 2, 4, 8, 16
+PATH_MASK_SPARSE, PATH_MASK_INT8, PATH_MASK_DMMA, PATH_OPTIMISTIC, PATH_REPLAYED, PATH_MASK_GENERIC = 32, 64, 128, 256, 512, 1024
+
 _dp = C.POINTER(C.c_double)
+
+
+class Options(C.Structure):
+    """glr_options: kernel-selection knobs, all zero = defaults."""
+    _fields_ = [('split8', C.c_int32), ('split8_pair', C.c_int32), ('mask_sparse', C.c_int32), ('mask_int8', C.c_int32),
+                ('keep_intercept', C.c_int32), ('no_tail', C.c_int32), ('sample_split', C.c_int32),
+                ('optimistic_calls', C.c_int32)]
+
+
+_TRI = {None: AUTO, 'auto': AUTO, 'off': OFF, 'never': OFF, 'force': FORCE, 'always': FORCE}
+
+
+def make_options(opts=None) -> 'Options':
+    """dict -> glr_options.  Tri-state knobs take 'auto' | 'off' | 'force'."""
+    o = Options()
+    for k, v in (opts or {}).items():
+        if k not in dict(Options._fields_):
+            raise ValueError(f'unknown option {k!r}')
+        if k in ('keep_intercept', 'no_tail', 'sample_split'):
+            setattr(o, k, int(v))
+        else:
+            if v not in _TRI:
+                raise ValueError(f'option {k!r}: expected auto | off | force, got {v!r}')
+            setattr(o, k, _TRI[v])
+    return o
 
 
 class StateDesc(C.Structure):
@@ -23,7 +52,7 @@ class StateDesc(C.Structure):
                 ('n_contigs', C.c_int32), ('verbose', C.c_int32), ('Q', C.c_void_p), ('Y', C.c_void_p),
                 ('Y_mask', C.c_void_p), ('YdotY', C.c_void_p), ('Y_scale', C.c_void_p), ('Y_raw', C.c_void_p),
                 ('keep_idx', C.c_void_p), ('dof', C.c_int64), ('max_block_variants', C.c_int32),
-                ('n_lanes', C.c_int32), ('memspace', C.c_int32), ('reserved', C.c_int32)]
+                ('n_lanes', C.c_int32), ('memspace', C.c_int32), ('reserved', C.c_int32), ('opt', Options)]
 
 
 class BlockDesc(C.Structure):
@@ -40,7 +69,7 @@ class BlockOut(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [('total_ms', C.c_float), ('prepass_ms', C.c_float), ('gram_ms', C.c_float), ('masked_ms', C.c_float),
-                ('epilogue_ms', C.c_float), ('kernel_launches', C.c_int32), ('reserved', C.c_int32)]
+                ('epilogue_ms', C.c_float), ('kernel_launches', C.c_int32), ('path', C.c_int32)]
 
 
 # every symbol include/glow_b200.h declares: (restype, argtypes)

@@ -61,12 +61,28 @@ struct DevBuf {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
-  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx, m8_rmax, m8_z8, m8_Z;
+  DevBuf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red, xx, m8_rmax, m8_z8, m8_Z, s8_ws, s8_n00, flags;
+  int32_t* h_flags = nullptr;  // pinned mirror of `flags` ([0] optimistic form met a missing call, [1] missing calls of the block)
   bool busy = false;
   bool has_masked = false, has_prepass = false;
+  bool optimistic = false;  // the block in flight runs the form without the missing-call operand
+  bool counted = false;     // flags[1] of the block in flight is meaningful
+  glr_block_desc blk{};     // the block in flight (for the re-run of an optimistic block that had missing calls)
+  glr_block_out blk_out{};
   int launches = 0;
+  int path = 0;
   glr_timing timing{};
 };
+
+// knob = desc field (glr_tristate), overridden by the environment variable when set (tests): env 0 = never, 1 = auto, 2 = always
+int tri_knob(int32_t field, const char* env) {
+  if (const char* e = getenv(env)) {
+    const int v = atoi(e);
+    return v <= 0 ? GLR_OFF : (v == 1 ? GLR_AUTO : GLR_FORCE);
+  }
+  return (field == GLR_OFF || field == GLR_FORCE) ? field : GLR_AUTO;
+}
+bool flag_knob(int32_t field, const char* env) { return field != 0 || getenv(env) != nullptr; }
 
 int pick_mt(int n_mtiles) {
   return n_mtiles < 1 ? 1 : (n_mtiles > 8 ? 8 : n_mtiles);
@@ -126,6 +142,9 @@ struct glr_state {
   std::vector<Lane> lanes;
   int sm_count = 148;
   int force_split = 0;
+  int s8_pair_mode = GLR_AUTO;
+  int optimistic_mode = GLR_AUTO;
+  bool expect_missing = true;  // the last counted PLINK2 block had missing calls (or none has been seen yet)
 };
 
 extern "C" {
@@ -170,8 +189,9 @@ int glr_state_destroy(glr_state* st) {
     for (auto& e : l.ev)
       if (e) cudaEventDestroy(e);
     for (DevBuf* b : {&l.geno, &l.out, &l.s_part, &l.s_red, &l.mom_part, &l.mom, &l.v1, &l.d_part, &l.d_red, &l.xx, &l.m8_rmax, &l.m8_z8,
-                       &l.m8_Z})
+                       &l.m8_Z, &l.s8_ws, &l.s8_n00, &l.flags})
       b->release();
+    if (l.h_flags) cudaFreeHost(l.h_flags);
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   for (void* p : {(void*)st->wpk, (void*)st->qb, (void*)st->mpk, (void*)st->mask_id, (void*)st->YdotY,
@@ -218,7 +238,10 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   st->pc = make_pval_const((double)d->dof);
   st->n_chunks = ceil_div(st->Ng, kChunk);
   CU(cudaDeviceGetAttribute(&st->sm_count, cudaDevAttrMultiProcessorCount, d->device));
+  st->force_split = d->opt.sample_split > 0 ? d->opt.sample_split : 0;
   if (const char* e = getenv("GLR_SPLIT")) st->force_split = atoi(e);
+  st->s8_pair_mode = tri_knob(d->opt.split8_pair, "GLR_S8_PAIR");
+  st->optimistic_mode = tri_knob(d->opt.optimistic_calls, "GLR_OPTIMISTIC");
 
   const int64_t N = st->N, Ng = st->Ng;
   const int K = st->K, P = st->P, C = st->C;
@@ -282,17 +305,25 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     struct KeyHash {
       size_t operator()(const std::pair<uint64_t, uint64_t>& k) const { return (size_t)(k.first ^ (k.second * 31)); }
     };
-    std::unordered_map<std::pair<uint64_t, uint64_t>, int, KeyHash> seen;
+    // hash -> candidate mask ids; a hit is confirmed by comparing the columns, so a collision cannot merge two masks
+    std::unordered_map<std::pair<uint64_t, uint64_t>, std::vector<int>, KeyHash> seen;
+    auto same_mask = [&](int a, int b) {
+      for (int64_t s = 0; s < N; ++s)
+        if ((mask_host[s * P + a] != 0.0) != (mask_host[s * P + b] != 0.0)) return false;
+      return true;
+    };
     for (int p = 0; p < P; ++p) {
       if (nobs[p] == N) continue;
-      auto key = std::make_pair(h1[p], h2[p]);
-      auto it = seen.find(key);
-      if (it == seen.end()) {
-        seen.emplace(key, (int)rep.size());
+      auto& cands = seen[std::make_pair(h1[p], h2[p])];
+      for (int id : cands)
+        if (same_mask(p, rep[id])) {
+          mask_id[p] = id;
+          break;
+        }
+      if (mask_id[p] < 0) {
         mask_id[p] = (int)rep.size();
+        cands.push_back(mask_id[p]);
         rep.push_back(p);
-      } else {
-        mask_id[p] = it->second;
       }
     }
   }
@@ -334,7 +365,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
 
   // ---- intercept column: np.linalg.qr of [1 | covariates] (lin_reg.py:142-147) gives a constant
   // first column +-1/sqrt(N); its product with x is q0 * sum(x), which the pre-pass already has ----
-  if (K > 0 && !getenv("GLR_KEEP_INTERCEPT")) {
+  if (K > 0 && !flag_knob(d->opt.keep_intercept, "GLR_KEEP_INTERCEPT")) {
     std::vector<double> col0(N);
     CU(cudaMemcpy2D(col0.data(), sizeof(double), dQ, (size_t)K * sizeof(double), sizeof(double), N,
                     cudaMemcpyDeviceToHost));
@@ -354,7 +385,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   st->Mcols = Kg + P * (st->verbose ? 3 : 1);
   const int n_mtiles = (int)ceil_div(st->Mcols, 8);
   const int full_tiles = st->Mcols / 8, rem_cols = st->Mcols % 8;
-  const bool no_tail = getenv("GLR_NO_TAIL") != nullptr;
+  const bool no_tail = flag_knob(d->opt.no_tail, "GLR_NO_TAIL");
   if (!no_tail && full_tiles >= 1 && full_tiles <= 4 && rem_cols >= 1 && rem_cols <= 3) {
     // 8*MT + 1..3 columns: the remainder goes through FP64 FMAs instead of a zero-padded m-tile
     st->MT = full_tiles;
@@ -375,15 +406,14 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
   // integer tensor-core operand (split8.cu): any number of columns (blocks of up to 18)
   double* d_colmax = nullptr;
-  // GLR_SPLIT8: 0 = never, 1 (default) = PLINK2 blocks that fill at least half the SMs, 2 = every PLINK2 block
-  const int split8_mode = getenv("GLR_SPLIT8") ? atoi(getenv("GLR_SPLIT8")) : 1;
-  if (split8_mode > 0 && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
+  const int split8_mode = tri_knob(d->opt.split8, "GLR_SPLIT8");
+  if (split8_mode != GLR_OFF && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
     st->s8_cols = st->Mcols;
     split8_geometry(st->s8_cols, &st->s8_ncb, &st->s8_cpb, &st->s8_NC);
     st->s8_stages = ceil_div(Ng, 128);
     st->s8_contig_bytes = (int64_t)st->s8_ncb * st->s8_stages * st->s8_NC * 128;
     // the digit image costs about 7.1 bytes per W entry (the FP64 image costs 8): built while it fits 16 GiB
-    if ((int64_t)C * st->s8_contig_bytes <= ((int64_t)16 << 30)) st->split8 = split8_mode;
+    if ((int64_t)C * st->s8_contig_bytes <= ((int64_t)16 << 30)) st->split8 = split8_mode == GLR_FORCE ? 2 : 1;
   }
   if (st->split8) {
     CU(cudaMalloc(&st->w8, (size_t)C * st->s8_contig_bytes));
@@ -449,8 +479,10 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     //   FP64 DMMA (masked_kernel)             Ng * (K + U)     K <= 32
     //   int8 tensor cores (mask8.cu)          Ng * (115 + 0.055 U)   K <= 64
     // GLR_MASK_SPARSE / GLR_MASK8: 0 = never, 1 (default) = when cheapest, 2 = always
-    const int sparse_mode = getenv("GLR_MASK_SPARSE") ? atoi(getenv("GLR_MASK_SPARSE")) : 1;
-    const int mask8_mode = getenv("GLR_MASK8") ? atoi(getenv("GLR_MASK8")) : 1;
+    // (0 = never, 1 = when cheapest, 2 = always)
+    const int tri2mode[3] = {1, 0, 2};
+    const int sparse_mode = tri2mode[tri_knob(d->opt.mask_sparse, "GLR_MASK_SPARSE")];
+    const int mask8_mode = tri2mode[tri_knob(d->opt.mask_int8, "GLR_MASK8")];
     std::vector<int32_t> sp_idx;
     std::vector<int64_t> sp_rows, sp_off(1, 0);
     for (int u = 0; u < U; ++u) {
@@ -466,17 +498,24 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     const double T = (double)sp_idx.size();
     const double cost_sparse = T * std::max(K, 1);
     const double cost_dmma = dmma_ok ? (double)Ng * (K + U) : 1e300;
-    const bool int8_ok = K <= 64 && Ng < (int64_t)16000000;
+    int m8_nmb = 0, m8_NB = 0;
+    mask8_geometry(U, &m8_nmb, &m8_NB);
+    const bool int8_ok = K <= 64 && Ng < (int64_t)16000000 &&
+                         (size_t)m8_nmb * (size_t)ceil_div(Ng, 128) * m8_NB * 128 <= ((size_t)8 << 30);
     const double cost_int8 = int8_ok ? (double)Ng * (115.0 + 0.055 * U) : 1e300;
-    const bool sparse_ok = sparse_mode > 0 && K <= 64 && Ng < ((int64_t)1 << 31);
-    bool use_sparse = sparse_ok && (sparse_mode > 1 || (cost_sparse <= cost_dmma && cost_sparse <= cost_int8));
+    // the sparse-complement form has a generic FP64 kernel for any number of covariates: with K > 64 it is the only
+    // form, whatever the knobs say (the reference has no limit on K, lin_reg.py:241)
+    const bool only_sparse = !dmma_ok && !int8_ok;
+    const bool sparse_ok = (sparse_mode > 0 || only_sparse) && Ng < ((int64_t)1 << 31);
+    bool use_sparse = sparse_ok && (sparse_mode > 1 || only_sparse || (cost_sparse <= cost_dmma && cost_sparse <= cost_int8));
     bool use_int8 = !use_sparse && mask8_mode > 0 && int8_ok && (mask8_mode > 1 || cost_int8 < cost_dmma);
-    if (mask8_mode > 1 && sparse_mode <= 1 && int8_ok) {  // an explicit request for the int8 form wins over "cheapest"
+    if (mask8_mode > 1 && sparse_mode <= 1 && int8_ok && !only_sparse) {  // an explicit request for the int8 form wins over "cheapest"
       use_sparse = false;
       use_int8 = true;
     }
+    if (!use_sparse && !use_int8 && !dmma_ok && Ng < ((int64_t)1 << 31)) use_sparse = true;  // the only form left
     if (use_sparse) {
-      st->sparse_masked = sparse_mode;
+      st->sparse_masked = std::max(sparse_mode, 1);
       st->sp_total = (int64_t)sp_idx.size();
       const int Kp = (K + 1) & ~1;
       int64_t* d_rows = nullptr;
@@ -505,9 +544,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     }
     if (!st->mask8 && !st->sparse_masked) {
       if (!dmma_ok)
-        return fail(GLR_ERR_INVALID,
-                    "phenotypes with missing values are supported with at most 64 covariates (incl. intercept); "
-                    "at most 32 when the int8 masked pass is disabled");
+        return fail(GLR_ERR_INVALID, "masked pass: no applicable form (more than 2^31 genotype samples with more than 32 covariates)");
       const size_t qb_bytes = (size_t)st->n_chunks * kChunkGroups * st->KT2 * kAtomDoubles * sizeof(double);
       CU(cudaMalloc(&st->qb, qb_bytes));
       CU(cudaMemsetAsync(st->qb, 0, qb_bytes, s0));
@@ -535,7 +572,11 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   for (auto& l : st->lanes) {
     CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     for (auto& e : l.ev) CU(cudaEventCreate(&e));
+    if (int rc2 = l.flags.ensure(2 * sizeof(int32_t))) return rc2;
+    CU(cudaHostAlloc((void**)&l.h_flags, 2 * sizeof(int32_t), cudaHostAllocDefault));
+    l.h_flags[0] = l.h_flags[1] = 0;
   }
+  st->expect_missing = st->optimistic_mode != GLR_FORCE;
   guard.s = nullptr;
   *out = st;
   return 0;
@@ -550,11 +591,12 @@ static size_t row_bytes_of(int format, int64_t n) {
   }
 }
 
-int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const glr_block_out* o) {
+// `replay`: second run of a block whose optimistic form met a missing call; its genotypes are already on the device
+static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, const glr_block_out* o, bool replay) {
   if (!st || !b || !o) return fail(GLR_ERR_INVALID, "null argument");
   if (lane_id < 0 || lane_id >= (int)st->lanes.size()) return fail(GLR_ERR_INVALID, "lane out of range");
   Lane& L = st->lanes[lane_id];
-  if (L.busy) return fail(GLR_ERR_STATE, "lane already has a block in flight");
+  if (L.busy && !replay) return fail(GLR_ERR_STATE, "lane already has a block in flight");
   if (b->format < GLR_FMT_F64 || b->format > GLR_FMT_PLINK2) return fail(GLR_ERR_INVALID, "unknown genotype format");
   if (b->contig < 0 || b->contig >= st->C) return fail(GLR_ERR_INVALID, "contig index out of range");
   if (b->n_variants < 0) return fail(GLR_ERR_INVALID, "negative n_variants");
@@ -573,6 +615,13 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   L.launches = 0;
   L.has_masked = false;
   L.has_prepass = false;
+  L.optimistic = false;
+  L.counted = false;
+  L.path = replay ? GLR_PATH_REPLAYED : 0;
+  if (!replay) {
+    L.blk = *b;
+    L.blk_out = *o;
+  }
   if (G == 0) {
     L.busy = true;
     for (auto& e : L.ev) CU(cudaEventRecord(e, L.stream));
@@ -594,14 +643,20 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   }
   if (st->force_split > 0) n_split = (int)std::min<int64_t>(st->force_split, st->n_chunks);
   const int64_t Mpad = st->s_rows;
-  const bool float_fmt = b->format == GLR_FMT_F64 || b->format == GLR_FMT_F32;
 
   // ---- buffers ----
   const uint8_t* d_geno = reinterpret_cast<const uint8_t*>(b->genotypes);
-  if (b->memspace == GLR_MEM_HOST) {
+  const bool float_fmt = b->format == GLR_FMT_F64 || b->format == GLR_FMT_F32;
+  // float blocks with dropped samples (intersect_samples) are staged so that the dropped entries can be zeroed: the
+  // reference deletes those rows before any arithmetic (lin_reg.py:228-229), so a NaN there must not reach the sums
+  const bool scrub = float_fmt && st->n_drop > 0;
+  if (replay) {
+    if (b->memspace == GLR_MEM_HOST) d_geno = L.geno.as<uint8_t>();  // staged by the first run
+  } else if (b->memspace == GLR_MEM_HOST || scrub) {
     const size_t bytes = (size_t)(G - 1) * b->row_stride_bytes + rb;
     if (int rc = L.geno.ensure(bytes + 64)) return rc;
-    CU(cudaMemcpyAsync(L.geno.p, b->genotypes, bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(L.geno.p, b->genotypes, bytes,
+                       b->memspace == GLR_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     d_geno = L.geno.as<uint8_t>();
   }
   if (int rc = L.s_red.ensure((size_t)Mpad * ldS * 8)) return rc;
@@ -631,22 +686,37 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
   x.n_geno = st->Ng;
   x.v1 = L.v1.as<double>();
 
-  // int8 tensor-core first pass when it is the faster one: a tile of 128 variants costs n_stages x ~540 cycles on one SM
-  // however few tiles there are, the DMMA kernel (which can split the samples of a small block over the SMs) about
-  // 30 TFLOP/s on the padded column count plus its pre-pass
+  // int8 tensor-core first pass when it is the faster one: a work unit (CTA or CTA pair) spends ~540 cycles per 128-sample
+  // stage; the plan splits the sample range of small blocks so that every SM has work.  The DMMA kernel does about
+  // 30 TFLOP/s on the padded column count plus its pre-pass.
   bool use_split8 = false;
+  Split8Plan plan;
   if (st->split8 && b->format == GLR_FMT_PLINK2) {
-    const double waves = (double)ceil_div(ceil_div(G, 128) * st->s8_ncb, (int64_t)st->sm_count);
-    const double t_s8 = waves * (double)st->s8_stages * 540.0 / 1.7e9;
-    const double t_dmma = (double)G * (2.0 * (double)st->Ng * (double)Mpad / 30e12 + (double)st->Ng / 4.0 / 5e12);
+    plan = split8_plan(G, st->s8_ncb, st->s8_stages, st->sm_count, st->s8_pair_mode, st->force_split);
+    const double t_s8 = plan.makespan_stages * 540.0 / 1.7e9 + (plan.n_split > 1 ? 8e-6 : 0.0);
+    const double t_dmma = (double)G * (2.0 * (double)st->Ng * (double)Mpad / 30e12 + (double)st->Ng / 4.0 / 5e12) /
+                              std::min(1.0, (double)(ctas * n_split) / st->sm_count) + 10e-6;
     use_split8 = st->split8 >= 2 || t_s8 < t_dmma;
   }
   const bool fused_counts = use_split8 && st->n_drop == 0;
+  // optimistic form: no missing-call operand while the stream of blocks has shown no missing call (validated in the
+  // kernel; a violation re-runs the block at wait time)
+  const bool optimistic = use_split8 && fused_counts && !replay && st->optimistic_mode != GLR_OFF && !st->expect_missing;
+  if (scrub) {
+    launch_zero_dropped(d_geno, b->row_stride_bytes, G, b->format, st->drop_idx, st->n_drop, s);
+    ++L.launches;
+  }
+  if (use_split8 && plan.n_split > 1) {
+    if (int rc = L.s8_ws.ensure(split8_ws_bytes(st->s8_ncb, st->s8_NC, ldS))) return rc;
+    if (int rc = L.s8_n00.ensure((size_t)ldS * sizeof(int32_t))) return rc;
+  }
+  CU(cudaMemsetAsync(L.flags.p, 0, 2 * sizeof(int32_t), s));
   CU(cudaEventRecord(L.ev[0], s));
   // ---- pre-pass (A0): missing substitute + sum of squares from integer counts ----
   if (!float_fmt && !fused_counts) {
     launch_prepass(x, b->missing_policy, L.v1.as<double>(), L.mom.as<double>(), ldS, s);
     L.has_prepass = true;
+    L.path |= GLR_PATH_PREPASS;
     ++L.launches;
   }
   CU(cudaEventRecord(L.ev[1], s));
@@ -682,9 +752,22 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
     sp.ldS = ldS;
     sp.v1_out = L.v1.as<double>();
     sp.mom_out = L.mom.as<double>();
+    sp.pair = plan.pair;
+    sp.no_e = optimistic ? 1 : 0;
+    sp.n_split = plan.n_split;
+    sp.split_stages = plan.split_stages;
+    sp.z_ws = L.s8_ws.as<int32_t>();
+    sp.n00_ws = L.s8_n00.as<int32_t>();
+    sp.flags = L.flags.as<int32_t>();
     launch_split8(sp, st->sm_count, s);
+    L.optimistic = optimistic;
+    L.counted = fused_counts;
+    L.path |= GLR_PATH_SPLIT8 | (plan.pair ? GLR_PATH_SPLIT8_PAIR : 0) | (plan.n_split > 1 ? GLR_PATH_SPLIT8_NSPLIT : 0) |
+              (optimistic ? GLR_PATH_OPTIMISTIC : 0);
+    if (plan.n_split > 1) L.launches += 1;
   } else {
     launch_gram(gp, s);
+    L.path |= GLR_PATH_DMMA;
   }
   ++L.launches;
   if (n_split > 1 && !use_split8) {
@@ -695,7 +778,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
       ++L.launches;
     }
   }
-  if (st->n_drop > 0) {
+  if (st->n_drop > 0 && !scrub) {  // (scrubbed float blocks hold zeros at the dropped samples: nothing to subtract)
     launch_dropped_moments(x, st->drop_idx, st->n_drop, L.mom.as<double>(), ldS, s);
     ++L.launches;
   }
@@ -738,6 +821,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
     d_D = L.d_red.as<double>();
     d_is_complement = true;
     L.has_masked = true;
+    L.path |= K > 64 ? GLR_PATH_MASK_GENERIC : GLR_PATH_MASK_SPARSE;
   } else if (st->U > 0 && st->mask8) {
     // integer tensor-core form (mask8.cu), in sub-ranges of variants that bound the digit image to 3 GiB
     const int64_t Upad = (int64_t)st->n_groups2 * st->MT2 * 8;
@@ -772,6 +856,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
     }
     d_D = L.d_red.as<double>();
     L.has_masked = true;
+    L.path |= GLR_PATH_MASK_INT8;
   } else if (st->U > 0) {
     const int64_t Upad = (int64_t)st->n_groups2 * st->MT2 * 8;
     const int tile2 = gram_tile_variants(2);
@@ -806,6 +891,7 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
     }
     d_D = L.d_red.as<double>();
     L.has_masked = true;
+    L.path |= GLR_PATH_MASK_DMMA;
   }
   CU(cudaEventRecord(L.ev[3], s));
   // ---- epilogue (A5-A7) ----
@@ -840,9 +926,14 @@ int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const 
     for (int i = 0; i < n_out; ++i)
       CU(cudaMemcpyAsync(outs[i], d_outs[i], out_elems * 8, cudaMemcpyDeviceToHost, s));
   }
+  if (L.counted) CU(cudaMemcpyAsync(L.h_flags, L.flags.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(L.ev[5], s));
   L.busy = true;
   return 0;
+}
+
+int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const glr_block_out* o) {
+  return submit_impl(st, lane_id, b, o, false);
 }
 
 int glr_block_wait(glr_state* st, int lane_id) {
@@ -850,9 +941,21 @@ int glr_block_wait(glr_state* st, int lane_id) {
   if (lane_id < 0 || lane_id >= (int)st->lanes.size()) return fail(GLR_ERR_INVALID, "lane out of range");
   Lane& L = st->lanes[lane_id];
   if (!L.busy) return fail(GLR_ERR_STATE, "no block in flight on this lane");
-  L.busy = false;
   CU(cudaSetDevice(st->device));
   CU(cudaStreamSynchronize(L.stream));
+  if (L.counted) {
+    if (L.optimistic && L.h_flags[0] != 0) {
+      // the block had missing calls after all: its results are void; run it again in the full form
+      st->expect_missing = true;
+      if (int rc = submit_impl(st, lane_id, &L.blk, &L.blk_out, true)) {
+        L.busy = false;
+        return rc;
+      }
+      CU(cudaStreamSynchronize(L.stream));
+    }
+    if (!L.optimistic) st->expect_missing = L.h_flags[1] != 0;
+  }
+  L.busy = false;
   glr_timing t{};
   cudaEventElapsedTime(&t.total_ms, L.ev[0], L.ev[4]);
   cudaEventElapsedTime(&t.prepass_ms, L.ev[0], L.ev[1]);
@@ -860,6 +963,7 @@ int glr_block_wait(glr_state* st, int lane_id) {
   cudaEventElapsedTime(&t.masked_ms, L.ev[2], L.ev[3]);
   cudaEventElapsedTime(&t.epilogue_ms, L.ev[3], L.ev[4]);
   t.kernel_launches = L.launches;
+  t.path = L.path;
   L.timing = t;
   CU(cudaGetLastError());
   return 0;

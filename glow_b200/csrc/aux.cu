@@ -252,6 +252,25 @@ void launch_dropped_moments(const BlockView& x, const int64_t* drop_idx, int64_t
   dropped_moments_kernel<<<(unsigned)ceil_div(x.n_variants, 128), 128, 0, st>>>(x, drop_idx, n_drop, mom, ld);
 }
 
+// Float blocks with dropped samples: the reference removes those rows before any arithmetic (np.delete, lin_reg.py:228-229),
+// so whatever they hold (NaN included) must not reach a sum.  The block is staged in library memory and the dropped
+// entries are set to zero there; W has zero rows for them and their moments are then zero as well.
+__global__ void zero_dropped_kernel(uint8_t* base, int64_t stride, int G, int elem_bytes, const int64_t* drop_idx, int64_t n_drop) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)G * n_drop) return;
+  const int64_t g = idx / n_drop, i = idx - g * n_drop;
+  uint8_t* row = base + g * stride;
+  if (elem_bytes == 8) reinterpret_cast<double*>(row)[drop_idx[i]] = 0.0;
+  else reinterpret_cast<float*>(row)[drop_idx[i]] = 0.0f;
+}
+void launch_zero_dropped(const uint8_t* base, int64_t stride, int G, int format, const int64_t* drop_idx, int64_t n_drop,
+                         cudaStream_t st) {
+  if (G <= 0 || n_drop <= 0) return;
+  const int64_t total = (int64_t)G * n_drop;
+  zero_dropped_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(const_cast<uint8_t*>(base), stride, G,
+                                                                       format == GLR_FMT_F64 ? 8 : 4, drop_idx, n_drop);
+}
+
 __global__ void intercept_row_kernel(const double* sum_x, double q0, double* row0, int G) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < G) row0[v] = q0 * sum_x[v];

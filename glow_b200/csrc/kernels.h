@@ -58,7 +58,21 @@ struct Split8Params {
   int64_t ldS;
   double* v1_out;        // [ldS]      (fused_counts)
   double* mom_out;       // [2][ldS]   (fused_counts): sum x^2, sum x
+  int32_t pair;          // 1: CTA pairs (cta_group::2)
+  int32_t no_e;          // 1: optimistic form without the missing-call operand (raises flags[0] if the block has one)
+  int32_t n_split;       // split of the sample range across work items (1 = none)
+  int32_t split_stages;  // stages per range (even; the last range takes the remainder)
+  int32_t* z_ws;         // n_split > 1: zero-initialised by the launcher, [n_cb][2][NC][ldS] int32 partial digit sums
+  int32_t* n00_ws;       // n_split > 1: [ldS] int32 code-00 counts
+  int32_t* flags;        // [2] device ints: [0] |= 1 when the optimistic form met a missing call,
+                         //                  [1] += number of missing calls of the block (full form, fused_counts)
 };
+struct Split8Plan {
+  int pair = 0, n_split = 1, split_stages = 0;
+  double makespan_stages = 0.0;  // stages one work unit runs for
+};
+Split8Plan split8_plan(int n_variants, int n_cb, int64_t n_stages, int sm_count, int pair_mode, int force_split);
+size_t split8_ws_bytes(int n_cb, int NC, int64_t ldS);
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st);
 void split8_geometry(int n_cols, int* n_cb, int* cpb, int* NC);
 double measure_s8_issue_rate(int sm_count, double ms_target, cudaStream_t st);  // TOP/s, < 0 on failure
@@ -154,6 +168,9 @@ void launch_decode(const BlockView& x, double* out, cudaStream_t st);  // out [G
 // sums over the listed (dropped) samples of x^2 and x, subtracted from mom[0] / mom[1] when rows are dropped
 void launch_dropped_moments(const BlockView& x, const int64_t* drop_idx, int64_t n_drop, double* mom, int64_t ld,
                             cudaStream_t st);
+// zeroes the listed (dropped) samples of a STAGED float block (base is library-owned memory)
+void launch_zero_dropped(const uint8_t* base, int64_t stride, int G, int format, const int64_t* drop_idx, int64_t n_drop,
+                         cudaStream_t st);
 // S row of an intercept column that is not in the GEMM: row0[v] = q0 * sum_x[v]
 void launch_intercept_row(const double* sum_x, double q0, double* row0, int G, cudaStream_t st);
 

@@ -116,6 +116,31 @@ __global__ void __launch_bounds__(kSpThreads) sparse_dmma_kernel(const SparseMas
   }
 }
 
+// Generic form for any number of covariates (K > 64, where the coefficients no longer fit the DMMA kernel's registers):
+// thread = variant, plain FP64 FMAs.  The coefficient reads a[k][v] are coalesced across the warp (consecutive variants),
+// the Q row of the list entry is a broadcast read.  Same output as sparse_dmma_kernel.
+template <int FMT>
+__global__ void __launch_bounds__(kSpThreads) sparse_generic_kernel(const SparseMaskedParams p) {
+  const int K = p.K, Kp = (K + 1) & ~1;
+  const int u = blockIdx.z;
+  const int64_t l0 = p.off[u], l1 = p.off[u + 1];
+  const int64_t per = ceil_div(l1 - l0, (int64_t)gridDim.y);
+  const int64_t j0 = l0 + (int64_t)blockIdx.y * per, j1 = min(l1, j0 + per);
+  const int v = blockIdx.x * kSpThreads + threadIdx.x;
+  if (v >= p.x.n_variants) return;
+  const uint8_t* row = p.x.base + (int64_t)v * p.x.stride;
+  const double miss = (FMT == GLR_FMT_I8 || FMT == GLR_FMT_PLINK2) ? p.x.v1[v] : 0.0;
+  const double* a = p.A + v;
+  double acc = 0.0;
+  for (int64_t e = j0; e < j1; ++e) {
+    double r = sp_elem<FMT>(row, (int64_t)p.idx[e], miss);
+    const double* q = p.qm + e * Kp;
+    for (int k = 0; k < K; ++k) r = fma(-__ldg(a + (int64_t)k * p.ldS), __ldg(q + k), r);
+    acc = fma(r, r, acc);
+  }
+  p.comp[((int64_t)blockIdx.y * p.U + u) * p.ldS + v] = acc;
+}
+
 template <int FMT, int KT4, int NV>
 static void launch_spd(const SparseMaskedParams& p, cudaStream_t st) {
   const int Ks = 4 * KT4 + 2;
@@ -130,7 +155,11 @@ static void launch_spd_fmt(const SparseMaskedParams& p, cudaStream_t st) {
   if (p.K <= 12) launch_spd<FMT, 3, 4>(p, st);
   else if (p.K <= 20) launch_spd<FMT, 5, 4>(p, st);
   else if (p.K <= 32) launch_spd<FMT, 8, 4>(p, st);
-  else launch_spd<FMT, 16, 2>(p, st);
+  else if (p.K <= 64) launch_spd<FMT, 16, 2>(p, st);
+  else {
+    const dim3 grid((unsigned)ceil_div(p.x.n_variants, kSpThreads), (unsigned)p.n_parts, (unsigned)p.U);
+    sparse_generic_kernel<FMT><<<grid, kSpThreads, 0, st>>>(p);
+  }
 }
 
 void launch_sparse_masked(const SparseMaskedParams& p, cudaStream_t st) {

@@ -99,6 +99,13 @@ __device__ __forceinline__ void s8_wait_keep(uint64_t* bar, uint32_t parity, uin
                  "+r"(b[i + 6]), "+r"(b[i + 7]));
   mbar_wait(bar, parity);
 }
+__device__ __forceinline__ void s8_wait_keep1(uint64_t* bar, uint32_t parity, uint32_t (&a)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8)
+    asm volatile("" : "+r"(a[i]), "+r"(a[i + 1]), "+r"(a[i + 2]), "+r"(a[i + 3]), "+r"(a[i + 4]), "+r"(a[i + 5]), "+r"(a[i + 6]),
+                 "+r"(a[i + 7]));
+  mbar_wait(bar, parity);
+}
 // ---- CTA-pair (cta_group::2) forms: one MMA drives the tensor cores of both SMs of a TPC; each CTA holds its own 128
 // variants (A, D in its TMEM) and HALF of the digit rows (B) in its shared memory ----
 __device__ __forceinline__ void s8_mma_ts2(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -191,6 +198,22 @@ __device__ __forceinline__ void s8_item(int item, int n_tiles, int n_cb, int& ti
   cb = grp * kS8CbGroup + (rem - tile * gsz);
 }
 
+// Sample-range split (small blocks: fewer (tile, column block) items than SMs).  Item = (tile, column block, z); split z
+// covers the stages [z per, (z + 1) per), the last one up to n_stages (per is even and every range has >= 2 stages, so both
+// MMA issuers and both decode groups take part in every item).  The partial digit sums are int32: they are added into a
+// zeroed workspace with integer atomics (exact, any order gives the same bits) and split8_finalize_kernel recombines.
+__device__ __forceinline__ void s8_item_split(int item, int n_tiles, int n_cb, int n_split, int per, int n_st, int& tile, int& cb,
+                                              int& kbeg, int& kcnt) {
+  int z = 0, base = item;
+  if (n_split > 1) {
+    base = item / n_split;
+    z = item - base * n_split;
+  }
+  s8_item(base, n_tiles, n_cb, tile, cb);
+  kbeg = z * per;
+  kcnt = (z == n_split - 1) ? n_st - kbeg : per;
+}
+
 #ifdef GLR_S8_PROFILE
 __device__ long long g_s8_prof[160][3][8];  // [cta][issuer 0 / issuer 1 / decode warp 4][phase] clock64 sums
 #define S8_T(var) const long long var = clock64()
@@ -205,7 +228,9 @@ __device__ long long g_s8_prof[160][3][8];  // [cta][issuer 0 / issuer 1 / decod
 // stage (each CTA loads and holds half of the rows), which halves the shared-memory and L2 traffic of the digit stream.
 // Only the leader (rank 0) issues MMAs; barriers the leader waits on collect arrivals from both CTAs, and the MMA
 // completion is multicast to both.
-template <bool kAligned, bool kPair>
+// kNoE: "optimistic" form for blocks expected to have no missing call: no indicator operand, no De MMAs (half the tensor
+// work).  The decode still checks every code; a missing call raises *p.flags and the host re-runs the block in the full form.
+template <bool kAligned, bool kPair, bool kNoE>
 __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NC = p.NC;
@@ -247,10 +272,11 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
   // a work unit (one CTA, or one CTA pair) takes items first_item, first_item + item_stride, ...
   const int tile_v = kPair ? 2 * kS8TileV : kS8TileV;
   const int n_tiles = (p.x.n_variants + tile_v - 1) / tile_v;
-  const int n_items = n_tiles * p.n_cb;  // work item = (tile [pair], column block)
+  const int n_split = p.n_split, per = p.split_stages;
+  const int n_items = n_tiles * p.n_cb * n_split;  // work item = (tile [pair], column block, sample range)
   const int first_item = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int item_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int64_t n_st = p.n_stages;       // 128-sample stages covering the genotype samples (>= 2)
+  const int n_st_all = (int)p.n_stages;  // 128-sample stages covering the genotype samples (>= 2)
 
   // Every role walks the same sequence of stages; g = running ("global") stage index of this CTA.  Ring slots and
   // barrier parities are functions of g (power-of-two depths: masks and shifts only).
@@ -259,10 +285,11 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     if (lane == 0) {
       uint32_t g = 0;
       for (int item = first_item; item < n_items; item += item_stride) {
-        int tile, cb;
-        s8_item(item, n_tiles, p.n_cb, tile, cb);
-        const int8_t* src = p.w8 + (int64_t)cb * n_st * w_stage_bytes + rank * w_bytes;  // pair: rows [rank NC/2, ..)
-        for (int64_t k = 0; k < n_st; ++k, ++g) {
+        int tile, cb, kbeg, kcnt;
+        s8_item_split(item, n_tiles, p.n_cb, n_split, per, n_st_all, tile, cb, kbeg, kcnt);
+        // pair: rows [rank NC/2, ..)
+        const int8_t* src = p.w8 + ((int64_t)cb * n_st_all + kbeg) * w_stage_bytes + rank * w_bytes;
+        for (int64_t k = 0; k < kcnt; ++k, ++g) {
           const uint32_t s = g & (kS8WRing - 1);
           if (g >= (uint32_t)kS8WRing) mbar_wait_backoff(&sm->done[s], ((g >> 3) & 1u) ^ 1u);  // stage g - 8 consumed
           mbar_expect_tx(&sm->full_w[s], w_bytes);
@@ -280,9 +307,10 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     if (kPair && rank != 0) {
       // peer CTA of a pair: no MMAs to issue; these two warps forward "my half of digit stage g has landed" to the leader
       const uint32_t j = __shfl_sync(0xffffffffu, warp, 0) == 1 ? 0u : 1u;
-      const int n_st32 = (int)n_st;
       uint32_t g0 = 0;
       for (int item = first_item; item < n_items; item += item_stride) {
+        int tile_, cb_, kbeg_, n_st32;
+        s8_item_split(item, n_tiles, p.n_cb, n_split, per, n_st_all, tile_, cb_, kbeg_, n_st32);
         for (int k = (int)((j ^ g0) & 1u); k < n_st32; k += kS8Issuers) {
           const uint32_t g = g0 + (uint32_t)k;
           const uint32_t sw = g & (kS8WRing - 1);
@@ -298,11 +326,12 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       const uint32_t idesc =
           (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)((kPair ? 2 : 1) * kS8TileV >> 4) << 24);
       const uint32_t w_ring_addr = smem_u32(w_ring);
-      const int n_st32 = (int)n_st;
       uint32_t g0 = 0;  // global index of the item's first stage
       int icount = 0;
       S8_T(t_begin);
       for (int item = first_item; item < n_items; item += item_stride, ++icount) {
+        int tile_, cb_, kbeg_, n_st32;
+        s8_item_split(item, n_tiles, p.n_cb, n_split, per, n_st_all, tile_, cb_, kbeg_, n_st32);
         for (int k = (int)((j ^ g0) & 1u); k < n_st32; k += kS8Issuers) {
           const uint32_t g = g0 + (uint32_t)k;
           S8_T(t0);
@@ -334,10 +363,10 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
               const uint64_t db = db0 + (uint64_t)(kk * 2);
               if (kPair) {
                 s8_mma_ts2(tmem, a_x + kk * 8, db, idesc, acc);
-                s8_mma_ts2(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
+                if (!kNoE) s8_mma_ts2(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
               } else {
                 s8_mma_ts(tmem, a_x + kk * 8, db, idesc, acc);
-                s8_mma_ts(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
+                if (!kNoE) s8_mma_ts(tmem + kS8ColDe, a_e + kk * 8, db, idesc, acc);
               }
             }
             if (k == 0) mbar_arrive(&sm->tile_started);
@@ -381,15 +410,16 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     const int64_t full_bytes = n_geno >> 2;
     uint32_t g0 = 0;
     int icount = 0;
+    uint32_t miss_seen = 0;  // kNoE: OR of the code-01 bits met
     for (int item = first_item; item < n_items; item += item_stride, ++icount) {
-      int tile, cb;
-      s8_item(item, n_tiles, p.n_cb, tile, cb);
+      int tile, cb, kbeg, kcnt;
+      s8_item_split(item, n_tiles, p.n_cb, n_split, per, n_st_all, tile, cb, kbeg, kcnt);
       if (kPair) tile = tile * 2 + (int)rank;  // the pair's two 128-variant halves
       const int v = min(tile * kS8TileV + vloc, p.x.n_variants - 1);
       const uint8_t* row = p.x.base + (int64_t)v * p.x.stride;
       uint32_t nxt[kS8Words + 1];
       uint32_t sh_nxt;
-      auto load = [&](int64_t k) {
+      auto load = [&](int64_t k) {  // k = absolute stage
         const int64_t b0 = k * 32;
         if (b0 + 4 * kS8Words + 3 <= full_bytes) {  // every word touched lies inside the whole bytes of the row
           const uint8_t* q8 = row + b0;
@@ -420,30 +450,32 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         }
       };
       int n00 = 0;
-      const int64_t k_first = (grp ^ g0) & 1u;
+      const int k_first = (int)((grp ^ g0) & 1u);
       // a 128-byte line of the row feeds 4 stages: the group on the even stages pulls lines into L2 well ahead
       if (k_first == 0) {
 #pragma unroll
         for (int l = 0; l < 4; ++l)
-          if ((int64_t)l * 128 < row_bytes) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + l * 128));
+          if ((int64_t)kbeg * 32 + l * 128 < row_bytes) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (int64_t)kbeg * 32 + l * 128));
       }
-      load(k_first);
-      for (int64_t k = k_first; k < n_st; k += 2) {
+      load(kbeg + k_first);
+      for (int k = k_first; k < kcnt; k += 2) {
         const uint32_t g = g0 + (uint32_t)k;
+        const int64_t ka = kbeg + k;
         S8_T(d0);
         uint32_t w[kS8Words];
 #pragma unroll
         for (int i = 0; i < kS8Words; ++i) w[i] = kAligned ? nxt[i] : __funnelshift_r(nxt[i], nxt[i + 1], sh_nxt);
-        if (k + 2 < n_st) load(k + 2);
-        if ((k & 3) == 0 && (k + 16) * 32 < row_bytes)
-          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (k + 16) * 32));
+        if (k + 2 < kcnt) load(ka + 2);
+        if ((ka & 3) == 0 && (ka + 16) * 32 < row_bytes)
+          asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (ka + 16) * 32));
         // decode into registers first, THEN wait for the TMEM slot: the slot frees up when the MMAs of stage g - 4
         // complete, and the hand-off back to the issuer must not include the decode arithmetic
-        uint32_t xs[32], es[32];
+        uint32_t xs[32], es[kNoE ? 1 : 32];
 #pragma unroll
         for (int i = 0; i < kS8Words; ++i) {
           const uint32_t ww = w[i];
           n00 += __popc(~(ww | (ww << 1)) & 0xAAAAAAAAu);  // both bits of a code clear (left shift: FMA pipe, not ALU)
+          if (kNoE) miss_seen |= ww & ~(ww >> 1) & 0x55555555u;  // code 01: the optimistic form does not apply to this block
           // PRMT selectors: nibble n of `ev` = code 2n (bit 2 is a stray bit of the neighbouring code: the table
           // is passed in both source registers, so it does not matter; bit 3 must be clear), of `od` = code 2n+1.
           // Sample order inside a 16-sample group is therefore 0,2,4,6 | 8,10,12,14 | 1,3,5,7 | 9,11,13,15;
@@ -456,22 +488,31 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           xs[4 * i + 1] = __byte_perm(0x00010002u, 0x00010002u, ev_hi);
           xs[4 * i + 2] = __byte_perm(0x00010002u, 0x00010002u, od);
           xs[4 * i + 3] = __byte_perm(0x00010002u, 0x00010002u, od_hi);
-          es[4 * i + 0] = __byte_perm(0x00000100u, 0x00000100u, ev);
-          es[4 * i + 1] = __byte_perm(0x00000100u, 0x00000100u, ev_hi);
-          es[4 * i + 2] = __byte_perm(0x00000100u, 0x00000100u, od);
-          es[4 * i + 3] = __byte_perm(0x00000100u, 0x00000100u, od_hi);
+          if (!kNoE) {
+            es[4 * i + 0] = __byte_perm(0x00000100u, 0x00000100u, ev);
+            es[4 * i + 1] = __byte_perm(0x00000100u, 0x00000100u, ev_hi);
+            es[4 * i + 2] = __byte_perm(0x00000100u, 0x00000100u, od);
+            es[4 * i + 3] = __byte_perm(0x00000100u, 0x00000100u, od_hi);
+          }
         }
         const uint32_t sa = g & (kS8ARing - 1);
         S8_T(d1);
         // the MMAs that read this TMEM slot last (stage g - 4) must have completed
-        if (g >= (uint32_t)kS8ARing) s8_wait_keep(&sm->done[(g - kS8ARing) & (kS8WRing - 1)], ((g - kS8ARing) >> 3) & 1u, xs, es);
+        if (g >= (uint32_t)kS8ARing) {
+          uint64_t* bar = &sm->done[(g - kS8ARing) & (kS8WRing - 1)];
+          const uint32_t par = ((g - kS8ARing) >> 3) & 1u;
+          if constexpr (kNoE) s8_wait_keep1(bar, par, xs);
+          else s8_wait_keep(bar, par, xs, es);
+        }
         S8_T(d2);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t a_x = lane_addr + kS8ColA + sa * 64, a_e = a_x + 32;
         tmem_st16(a_x, xs);
         tmem_st16(a_x + 16, xs + 16);
-        tmem_st16(a_e, es);
-        tmem_st16(a_e + 16, es + 16);
+        if constexpr (!kNoE) {
+          tmem_st16(a_e, es);
+          tmem_st16(a_e + 16, es + 16);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
@@ -489,45 +530,78 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         }
 #endif
       }
-      sm->n00[grp][vloc] = n00;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");  // all decode warps: both groups' counts are in shared memory
+      const int64_t vg = (int64_t)tile * kS8TileV + vloc;
+      const bool v_ok = vg < p.x.n_variants;
+      if (n_split == 1) {
+        sm->n00[grp][vloc] = n00;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // all decode warps: both groups' counts are in shared memory
+      } else if (cb == 0 && v_ok && n00 != 0) {
+        atomicAdd(p.n00_ws + vg, n00);
+      }
 
       // ---- epilogue: thread = variant; the two groups split the columns ----
       mbar_wait(&sm->tmem_full, (uint32_t)(icount & 1));
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const int64_t vg = (int64_t)tile * kS8TileV + vloc;
       const int col0 = cb * p.cpb, ncols = min(p.cpb, p.n_cols - col0);
-      double mu = -1.0;
-      {
-        uint32_t zx[8], ze[8];
-        tmem_ld8(lane_addr + p.cpb * kS8Digits, zx);  // column 7 cpb = the row of ones
-        tmem_ld8(lane_addr + kS8ColDe + p.cpb * kS8Digits, ze);
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (p.fused_counts) {
-          const double sx = (double)(int32_t)zx[0];   // 2 n00 + n10
-          const double c01 = (double)(int32_t)ze[0];  // missing calls
-          const double c00 = (double)(sm->n00[0][vloc] + sm->n00[1][vloc]);
-          if (p.missing_policy == GLR_MISSING_MEAN && c01 < (double)n_geno)
-            mu = sx / ((double)n_geno - c01);  // MeanSubstitute.scala:57-84
-          if (cb == 0 && grp == 0 && vg < p.x.n_variants) {
-            p.v1_out[vg] = mu;
-            p.mom_out[vg] = sx + 2.0 * c00 + (mu * mu) * c01;
-            p.mom_out[p.ldS + vg] = sx + mu * c01;
-          }
-        } else {
-          mu = p.x.v1[min(vg, (int64_t)p.x.n_variants - 1)];
-        }
-      }
-      for (int c = (int)grp; c < ncols; c += 2) {
-        uint32_t zx[8], ze[8];
-        tmem_ld8(lane_addr + c * kS8Digits, zx);
-        tmem_ld8(lane_addr + kS8ColDe + c * kS8Digits, ze);
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        double acc = 0.0;
+      if (n_split == 1) {
+        double mu = -1.0;
+        {
+          uint32_t zx[8], ze[8];
+          tmem_ld8(lane_addr + p.cpb * kS8Digits, zx);  // column 7 cpb = the row of ones
+          if (!kNoE) tmem_ld8(lane_addr + kS8ColDe + p.cpb * kS8Digits, ze);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          if (p.fused_counts) {
+            const double sx = (double)(int32_t)zx[0];                  // 2 n00 + n10
+            const double c01 = kNoE ? 0.0 : (double)(int32_t)ze[0];    // missing calls
+            const double c00 = (double)(sm->n00[0][vloc] + sm->n00[1][vloc]);
+            if (p.missing_policy == GLR_MISSING_MEAN && c01 < (double)n_geno)
+              mu = sx / ((double)n_geno - c01);  // MeanSubstitute.scala:57-84
+            if (cb == 0 && grp == 0) {
+              if (v_ok) {
+                p.v1_out[vg] = mu;
+                p.mom_out[vg] = sx + 2.0 * c00 + (mu * mu) * c01;
+                p.mom_out[p.ldS + vg] = sx + mu * c01;
+              }
+              if (!kNoE) {  // total number of missing calls of the block (drives the optimistic form of the NEXT block)
+                int cm = v_ok ? (int32_t)ze[0] : 0;
 #pragma unroll
-        for (int i = kS8Digits - 1; i >= 0; --i)
-          acc = fma(acc, 256.0, fma(mu, (double)(int32_t)ze[i], (double)(int32_t)zx[i]));
-        p.S[(int64_t)(col0 + c) * p.ldS + vg] = acc * p.scale[col0 + c];
+                for (int o = 16; o > 0; o >>= 1) cm += __shfl_xor_sync(0xffffffffu, cm, o);
+                if (lane == 0 && cm != 0) atomicAdd(p.flags + 1, cm);
+              }
+            }
+          } else {
+            mu = p.x.v1[min(vg, (int64_t)p.x.n_variants - 1)];
+          }
+        }
+        for (int c = (int)grp; c < ncols; c += 2) {
+          uint32_t zx[8], ze[8];
+          tmem_ld8(lane_addr + c * kS8Digits, zx);
+          if (!kNoE) tmem_ld8(lane_addr + kS8ColDe + c * kS8Digits, ze);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          double acc = 0.0;
+#pragma unroll
+          for (int i = kS8Digits - 1; i >= 0; --i)
+            acc = fma(acc, 256.0, kNoE ? (double)(int32_t)zx[i] : fma(mu, (double)(int32_t)ze[i], (double)(int32_t)zx[i]));
+          p.S[(int64_t)(col0 + c) * p.ldS + vg] = acc * p.scale[col0 + c];
+        }
+      } else {
+        // partial digit sums of this sample range: exact integer atomics into the zeroed workspace
+        // zws[cb][accumulator][digit row][ldS]; the two groups split the 8-row chunks
+        int32_t* zx_ws = p.z_ws + (int64_t)cb * 2 * NC * p.ldS + vg;
+        for (int ch = (int)grp; ch < (NC >> 3); ch += 2) {  // rows of absent columns hold zeros: no atomics issued
+          uint32_t zx[8], ze[8];
+          tmem_ld8(lane_addr + ch * 8, zx);
+          if (!kNoE) tmem_ld8(lane_addr + kS8ColDe + ch * 8, ze);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          if (v_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int64_t r = ch * 8 + i;
+              if (zx[i]) atomicAdd(zx_ws + r * p.ldS, (int32_t)zx[i]);
+              if (!kNoE && ze[i]) atomicAdd(zx_ws + ((int64_t)NC + r) * p.ldS, (int32_t)ze[i]);
+            }
+          }
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncwarp();
@@ -535,8 +609,11 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         if (kPair) s8_arrive_cta(&sm->tmem_empty, 0);
         else mbar_arrive(&sm->tmem_empty);
       }
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");  // n00[] may be rewritten
-      g0 += (uint32_t)n_st;
+      if (n_split == 1) asm volatile("bar.sync 1, 256;\n" ::: "memory");  // n00[] may be rewritten
+      g0 += (uint32_t)kcnt;
+    }
+    if (kNoE) {
+      if (__any_sync(0xffffffffu, miss_seen != 0) && lane == 0) atomicOr(p.flags, 1);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -553,22 +630,105 @@ void split8_geometry(int n_cols, int* n_cb, int* cpb, int* NC) {
   *NC = (int)round_up((int64_t)*cpb * kS8Digits + 1, 16);
 }
 
+// Recombination of the split form: thread = (variant, column block) reads the summed int32 digit rows and does exactly
+// what the fused epilogue does (same operations in the same order: bit-identical S, v1, moments).
+__global__ void split8_finalize_kernel(const Split8Params p, int no_e) {
+  const int64_t vg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cb = blockIdx.y;
+  if (vg >= p.x.n_variants) return;
+  const int NC = p.NC;
+  const int32_t* zx = p.z_ws + (int64_t)cb * 2 * NC * p.ldS + vg;
+  const int32_t* ze = zx + (int64_t)NC * p.ldS;
+  const double n_geno = (double)p.x.n_geno;
+  double mu = -1.0;
+  if (p.fused_counts) {
+    const int64_t r1 = (int64_t)p.cpb * kS8Digits;
+    const double sx = (double)zx[r1 * p.ldS];
+    const int32_t cm = no_e ? 0 : ze[r1 * p.ldS];
+    const double c01 = (double)cm;
+    const double c00 = (double)p.n00_ws[vg];
+    if (p.missing_policy == GLR_MISSING_MEAN && c01 < n_geno) mu = sx / (n_geno - c01);
+    if (cb == 0) {
+      p.v1_out[vg] = mu;
+      p.mom_out[vg] = sx + 2.0 * c00 + (mu * mu) * c01;
+      p.mom_out[p.ldS + vg] = sx + mu * c01;
+      if (cm != 0) atomicAdd(p.flags + 1, cm);
+    }
+  } else {
+    mu = p.x.v1[vg];
+  }
+  const int col0 = cb * p.cpb, ncols = min(p.cpb, p.n_cols - col0);
+  for (int c = 0; c < ncols; ++c) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = kS8Digits - 1; i >= 0; --i) {
+      const int64_t r = (int64_t)c * kS8Digits + i;
+      const double dx = (double)zx[r * p.ldS];
+      acc = fma(acc, 256.0, no_e ? dx : fma(mu, (double)ze[r * p.ldS], dx));
+    }
+    p.S[(int64_t)(col0 + c) * p.ldS + vg] = acc * p.scale[col0 + c];
+  }
+}
+
+// Plan of a launch: CTA pairs or single CTAs, and the split of the sample range that fills the GPU when the block has
+// fewer (tile, column block) items than work units.  Returned makespan is in stages of one unit (cost model for api.cu).
+Split8Plan split8_plan(int n_variants, int n_cb, int64_t n_stages, int sm_count, int pair_mode, int force_split) {
+  Split8Plan pl;
+  const int items1 = (n_variants + kS8TileV - 1) / kS8TileV * n_cb;
+  const int items2 = (n_variants + 2 * kS8TileV - 1) / (2 * kS8TileV) * n_cb;
+  const int max_split = (int)std::max<int64_t>(1, std::min<int64_t>(64, n_stages / 8));
+  auto best = [&](int items, int units, int& ns_out, int& per_out) {
+    const int kOverhead = 8;  // pipeline fill + epilogue of an item, in stages
+    double best_cost = 1e300;
+    for (int ns = 1; ns <= max_split; ++ns) {
+      if (force_split > 0 && ns != std::min(force_split, max_split)) continue;
+      const int per = (int)round_up(ceil_div(n_stages, ns), 2);
+      const int eff = (int)std::max<int64_t>(1, n_stages / per);  // ranges in use (the last one takes the remainder)
+      const int64_t longest = n_stages - (int64_t)(eff - 1) * per;
+      const double waves = (double)ceil_div((int64_t)items * eff, units);
+      const double cost = waves * (double)(longest + kOverhead);
+      if (cost < best_cost * (ns > 1 ? 0.98 : 1.0)) {  // prefer fewer ranges unless clearly better
+        best_cost = cost;
+        ns_out = eff;
+        per_out = per;
+      }
+      if (items >= 8 * units && force_split <= 0) break;  // many items per unit: the tail is negligible
+    }
+    return best_cost;
+  };
+  int ns1 = 1, per1 = (int)n_stages, ns2 = 1, per2 = (int)n_stages;
+  const double c1 = best(items1, sm_count, ns1, per1);
+  const double c2 = best(items2, sm_count / 2, ns2, per2) * 1.0;
+  // pairs halve the digit stream's L2 / shared-memory traffic: preferred whenever they are not slower
+  bool pair = pair_mode == GLR_FORCE || (pair_mode != GLR_OFF && c2 <= c1 * 1.02);
+  pl.pair = pair ? 1 : 0;
+  pl.n_split = pair ? ns2 : ns1;
+  pl.split_stages = pair ? per2 : per1;
+  pl.makespan_stages = pair ? c2 : c1;
+  return pl;
+}
+
+size_t split8_ws_bytes(int n_cb, int NC, int64_t ldS) { return (size_t)n_cb * 2 * NC * ldS * sizeof(int32_t); }
+
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;
   const bool aligned = (reinterpret_cast<uintptr_t>(p.x.base) & 3) == 0 && (p.x.stride & 3) == 0;
-  // CTA pairs (GLR_S8_PAIR=0 turns them off) once the block has enough variants to occupy the pairs
-  const char* pair_env = getenv("GLR_S8_PAIR");  // 0 = never, 1 (default) = when the pairs can be filled, 2 = always
-  const int pair_mode = pair_env ? atoi(pair_env) : 1;
-  const int n_items1 = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb;
-  const int n_items2 = (p.x.n_variants + 2 * kS8TileV - 1) / (2 * kS8TileV) * p.n_cb;
-  bool pair = pair_mode > 0 && (pair_mode > 1 || n_items2 * 2 >= sm_count);
+  const int n_items1 = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb * p.n_split;
+  const int n_items2 = (p.x.n_variants + 2 * kS8TileV - 1) / (2 * kS8TileV) * p.n_cb * p.n_split;
+  bool pair = p.pair != 0;
+  const bool no_e = p.no_e != 0;
+  if (p.n_split > 1) {
+    cudaMemsetAsync(p.z_ws, 0, split8_ws_bytes(p.n_cb, p.NC, p.ldS), st);
+    cudaMemsetAsync(p.n00_ws, 0, (size_t)p.ldS * sizeof(int32_t), st);
+  }
 #ifdef GLR_S8_PROFILE
   static long long zero[160][3][8];
   cudaMemcpyToSymbol(g_s8_prof, zero, sizeof(zero));
 #endif
   if (pair) {
     const size_t smem = (size_t)kS8WRing * (p.NC / 2) * kS8K + sizeof(Split8Smem) + 64;
-    auto kern = aligned ? split8_kernel<true, true> : split8_kernel<false, true>;
+    auto kern = no_e ? (aligned ? split8_kernel<true, true, true> : split8_kernel<false, true, true>)
+                     : (aligned ? split8_kernel<true, true, false> : split8_kernel<false, true, false>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * std::min(n_items2, sm_count / 2));
@@ -589,9 +749,14 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   }
   if (!pair) {
     const size_t smem = (size_t)kS8WRing * p.NC * kS8K + sizeof(Split8Smem) + 64;
-    auto kern = aligned ? split8_kernel<true, false> : split8_kernel<false, false>;
+    auto kern = no_e ? (aligned ? split8_kernel<true, false, true> : split8_kernel<false, false, true>)
+                     : (aligned ? split8_kernel<true, false, false> : split8_kernel<false, false, false>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<std::min(n_items1, sm_count), kS8Threads, smem, st>>>(p);
+  }
+  if (p.n_split > 1) {
+    const dim3 grid((unsigned)ceil_div(p.x.n_variants, 128), (unsigned)p.n_cb);
+    split8_finalize_kernel<<<grid, 128, 0, st>>>(p, no_e ? 1 : 0);
   }
 #ifdef GLR_S8_PROFILE
   static long long h[160][3][8];

@@ -96,10 +96,12 @@ class DeviceState:
                  device: int = 0,
                  n_lanes: int = 2,
                  memspace: int = _capi.MEM_HOST,
-                 dims: Optional[Tuple[int, int, int, int]] = None):
+                 dims: Optional[Tuple[int, int, int, int]] = None,
+                 options: Optional[dict] = None):
         """Host arrays (float64, C order): Q [N,K]; Y [C,N,P] or [N,P]; Y_mask [N,P]; YdotY [C,P] or [P];
         Y_scale [P].  With memspace=MEM_DEVICE the array arguments are integer device addresses and
-        ``dims`` = (N, K, P, C) must be given."""
+        ``dims`` = (N, K, P, C) must be given.  ``options``: kernel-selection knobs (glr_options fields, e.g.
+        ``{'split8': 'force', 'split8_pair': 'off'}``); the default leaves every choice to the library."""
         self._lib = _capi.load()
         self._handle = C.c_void_p()
         if memspace == _capi.MEM_HOST:
@@ -152,7 +154,8 @@ class DeviceState:
                             dof=int(dof),
                             max_block_variants=0,
                             n_lanes=n_lanes,
-                            memspace=memspace)
+                            memspace=memspace,
+                            opt=_capi.make_options(options))
         _capi.check(self._lib.glr_state_create(C.byref(d), C.byref(self._handle)))
         self._pending: Dict[int, tuple] = {}
 
@@ -234,7 +237,7 @@ class DeviceState:
     def timing(self, lane: int = 0) -> Dict[str, float]:
         t = _capi.Timing()
         _capi.check(self._lib.glr_block_timing(self._handle, lane, C.byref(t)))
-        return {k: getattr(t, k) for k, _ in _capi.Timing._fields_ if k != 'reserved'}
+        return {k: getattr(t, k) for k, _ in _capi.Timing._fields_}
 
     def lane_stream(self, lane: int = 0) -> int:
         s = C.c_void_p()

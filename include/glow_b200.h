@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GLR_ABI_VERSION 1
+#define GLR_ABI_VERSION 2
 
 typedef enum glr_status {
   GLR_OK = 0,
@@ -60,7 +60,25 @@ typedef enum glr_missing_policy {
                                    core/.../sql/expressions/MeanSubstitute.scala:39-108; all-missing -> -1 */
 } glr_missing_policy;
 
+/* Kernel-selection knobs.  All zero = the defaults (every choice made by the library's cost models). */
+typedef enum glr_tristate { GLR_AUTO = 0, GLR_OFF = 1, GLR_FORCE = 2 } glr_tristate;
+
+typedef struct glr_options {
+  int32_t split8;          /* glr_tristate: exact int8 tensor-core contraction (tcgen05) for PLINK2 blocks: when a time
+                              model says it beats the FP64 DMMA kernel | never | always */
+  int32_t split8_pair;     /* glr_tristate: its CTA-pair form (cta_group::2): when the pairs fill the GPU | never | always */
+  int32_t mask_sparse;     /* glr_tristate: sparse-complement form of the masked second pass: when cheapest | never | always */
+  int32_t mask_int8;       /* glr_tristate: int8 tensor-core form of the masked second pass: when cheapest | never | always */
+  int32_t keep_intercept;  /* 1: keep a constant first column of Q inside the GEMM */
+  int32_t no_tail;         /* 1: pad the column count to a multiple of 8 instead of FP64-FMA tail columns */
+  int32_t sample_split;    /* > 0: force this split of the sample range across CTAs (small blocks); 0 = automatic */
+  int32_t optimistic_calls;/* glr_tristate: run PLINK2 blocks without the missing-call operand while the previous block of
+                              the state had no missing call, re-running a block that turns out to have one (results are
+                              identical either way): automatic | never | (FORCE = start optimistic at the first block) */
+} glr_options;
+
 typedef struct glr_state glr_state; /* opaque */
+typedef struct glr_comm glr_comm;   /* opaque: a set of devices of one process */
 
 /* Driver-side state: what map_func closes over at lin_reg.py:277-282.
  * All matrices are row-major float64 in PHENOTYPE sample order. */
@@ -84,17 +102,14 @@ typedef struct glr_state_desc {
   int64_t dof;             /* N - K - 1, lin_reg.py:159 */
   int32_t max_block_variants; /* hint for workspace sizing (grown on demand) */
   int32_t n_lanes;         /* independent in-flight blocks (streams); 0 -> default 2 */
-  /* Environment knobs read at state creation: GLR_SPLIT8 = 0 | 1 (default) | 2 selects the exact int8
-   * tensor-core contraction for PLINK2 blocks never | when a time model says it beats the DMMA kernel | always
-   * (GLR_S8_PAIR = 0 | 1 (default) | 2, read per block: its CTA-pair form never | when the pairs fill | always);
-   * GLR_MASK_SPARSE / GLR_MASK8 = 0 | 1 (default) | 2 select the sparse-complement / int8 tensor-core form of the
-   * masked second pass never | when a cost model finds it the cheapest of the three forms | always;
-   * GLR_KEEP_INTERCEPT keeps a constant first column of Q inside the GEMM; GLR_NO_TAIL pads the
-   * column count to a multiple of 8 instead of using FP64-FMA tail columns. */
   int32_t memspace;        /* glr_memspace of Q, Y, Y_mask, YdotY, Y_scale, Y_raw (keep_idx is always
                               host): GLR_MEM_DEVICE lets ranks != 0 build their replica straight
                               from the buffer an NCCL broadcast filled, without a host round trip */
   int32_t reserved;
+  glr_options opt;         /* kernel-selection knobs; all zero = defaults.  For tests every knob can also be overridden
+                              from the environment at state creation: GLR_SPLIT8, GLR_S8_PAIR, GLR_MASK_SPARSE, GLR_MASK8,
+                              GLR_OPTIMISTIC = 0 (never) | 1 (automatic) | 2 (always); GLR_KEEP_INTERCEPT, GLR_NO_TAIL,
+                              GLR_SPLIT = n */
 } glr_state_desc;
 
 /* One genotype block in, = the `genotype_pdf` argument of _linear_regression_inner. */
@@ -130,8 +145,22 @@ typedef struct glr_timing {
   float masked_ms;   /* masked sum-of-squares kernel (0 when every phenotype is fully observed) */
   float epilogue_ms; /* statistics + p-values */
   int32_t kernel_launches;
-  int32_t reserved;
+  int32_t path;      /* glr_path_flags of the block: which kernels ran (tests assert the path they mean to cover) */
 } glr_timing;
+
+typedef enum glr_path_flags {
+  GLR_PATH_SPLIT8 = 1,        /* first pass on the int8 tensor cores (split8_kernel) */
+  GLR_PATH_SPLIT8_PAIR = 2,   /*   ... in its CTA-pair form */
+  GLR_PATH_SPLIT8_NSPLIT = 4, /*   ... with the sample range split across CTAs (small blocks) */
+  GLR_PATH_PREPASS = 8,       /* separate count / impute pre-pass */
+  GLR_PATH_DMMA = 16,         /* first pass on the FP64 tensor cores (gram_kernel) */
+  GLR_PATH_MASK_SPARSE = 32,  /* masked pass: sparse complement */
+  GLR_PATH_MASK_INT8 = 64,    /* masked pass: int8 tensor cores */
+  GLR_PATH_MASK_DMMA = 128,   /* masked pass: FP64 DMMA */
+  GLR_PATH_OPTIMISTIC = 256,  /* block ran without the missing-call operand */
+  GLR_PATH_REPLAYED = 512,    /* ... and was re-run because it had missing calls */
+  GLR_PATH_MASK_GENERIC = 1024 /* masked pass: generic FP64 form (more than 64 covariates) */
+} glr_path_flags;
 
 int glr_abi_version(void);
 const char* glr_last_error(void);

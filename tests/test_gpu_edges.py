@@ -86,33 +86,85 @@ def test_no_intercept_and_no_covariates(rg):
     assert_stats_close({k: out2[k].to_numpy().reshape(P, G) for k in STATS}, ref2, label='constant last')
 
 
-def test_masked_pass_covariate_limit(rg, monkeypatch):
-    """Phenotypes with missing values: the FP64 DMMA form takes K <= 32, the int8 form (chosen automatically beyond
-    that) K <= 64."""
+@pytest.mark.parametrize('K', [33, 64, 65, 100])
+@pytest.mark.parametrize('knobs', [{}, {'mask_sparse': 'off', 'mask_int8': 'off'}])
+def test_masked_pass_any_covariate_count(rg, K, knobs):
+    """Phenotypes with missing values and many covariates: the reference has no limit on K (lin_reg.py:241).  The FP64
+    DMMA form takes K <= 32 and the int8 form K <= 64; beyond that (or with those forms switched off) the
+    sparse-complement form runs, with its generic FP64 kernel for K > 64."""
+    from glow_b200 import _capi
     from glow_b200.engine import DeviceState, GenotypeBlock
-    N, G, P, K = 200, 40, 2, 33
+    N, G, P = 400, 40, 3
     cov = pd.DataFrame(rg.standard_normal((N, K - 1)))
     Yv = rg.standard_normal((N, P))
-    Yv[3, 0] = np.nan
+    Yv[rg.random((N, P)) < 0.2] = np.nan
+    Yv[:, 2] = rg.standard_normal(N)  # one fully observed phenotype
     phe = pd.DataFrame(Yv)
     X = rg.integers(0, 3, (G, N)).astype(np.float64)
-    eng, st = _state(phe, cov)
-    assert_stats_close(eng.run(GenotypeBlock(X, 'f64')), orc.block_stats(X, st), label='K=33 masked')
+    st = orc.prepare_state(phe, cov)
+    eng = DeviceState(Q=st.Q, Y=st.y_state.Y[None], Y_mask=st.Y_mask, YdotY=st.y_state.YdotY[None], Y_scale=st.Y_scale, dof=st.dof,
+                      options=knobs)
+    ref = orc.block_stats(X, st)
+    assert_stats_close(eng.run(GenotypeBlock(X, 'f64')), ref, label=f'K={K} masked f64')
+    path = eng.timing(0)['path']
+    if K > 64:
+        assert path & _capi.PATH_MASK_GENERIC
+    assert_stats_close(eng.run(GenotypeBlock(pack_plink(X.astype(np.int64)), 'plink2')), ref, label=f'K={K} masked plink2')
     eng.close()
-    Q = np.linalg.qr(rg.standard_normal((N, K)))[0]
+
+
+def test_dropped_sample_nan_does_not_propagate(rg):
+    """intersect_samples: the reference deletes the dropped genotype samples before any arithmetic (np.delete,
+    lin_reg.py:228-229), so a NaN / inf in a dropped sample must not reach the statistics."""
+    import glow_b200
+    N, G, P, K = 230, 21, 2, 3
+    samples = [f's{i}' for i in range(N)]
+    X = rg.integers(0, 3, (G, N)).astype(np.float64) + 0.25 * rg.random((G, N))
+    keep = [i for i in range(N) if i % 7 != 3]
+    dropped = [i for i in range(N) if i % 7 == 3]
+    X[:, dropped[0]] = np.nan
+    X[5, dropped[1]] = np.inf
+    X[6, dropped[2]] = -np.inf
+    Yv = rg.standard_normal((N, P))
+    Yv[rg.random((N, P)) < 0.1] = np.nan  # masked second pass as well
+    phe = pd.DataFrame(Yv, index=samples).iloc[keep]
+    cov = pd.DataFrame(rg.standard_normal((N, K)), index=samples)
+    for dt in (np.float64, np.float32):
+        pdf = pd.DataFrame({'values': list(X.astype(dt)), 'idx': np.arange(G)})
+        out = glow_b200.gwas.linear_regression(pdf, phe, cov, intersect_samples=True, genotype_sample_ids=samples, dt=dt,
+                                               verbose_output=True)
+        st = orc.prepare_state(phe, cov, intersect_samples=True, genotype_sample_ids=samples, verbose_output=True, dt=dt)
+        ref = orc.block_frame(pd.DataFrame({'values': list(X.astype(dt).astype(np.float64)), 'idx': np.arange(G)}), 'values', st)
+        assert np.isfinite(out['effect'].to_numpy()).all()
+        tol = dict(rtol_stat=1e-9, rtol_p=1e-6) if dt == np.float64 else dict(rtol_stat=1e-3, rtol_p=1e-2)
+        assert_stats_close({k: out[k].to_numpy() for k in STATS}, {k: ref[k].to_numpy() for k in STATS},
+                           label=f'NaN in dropped sample {dt.__name__}', **tol)
+        np.testing.assert_allclose(out['sum_x'].to_numpy(), ref['sum_x'].to_numpy(), rtol=1e-5)
+
+
+def test_masks_differing_in_one_sample_are_not_merged(rg):
+    """Mask de-duplication compares the columns on a hash hit; masks with equal counts that differ in a single sample
+    stay distinct, identical masks share one."""
+    from glow_b200.engine import DeviceState, GenotypeBlock
+    N, G, P = 300, 16, 4
+    Yv = rg.standard_normal((N, P))
+    Yv[10, 0] = np.nan
+    Yv[11, 1] = np.nan
+    Yv[10, 2] = np.nan   # same mask as phenotype 0
+    phe, cov = pd.DataFrame(Yv), pd.DataFrame(rg.standard_normal((N, 2)))
+    st = orc.prepare_state(phe, cov)
+    eng = DeviceState(Q=st.Q, Y=st.y_state.Y[None], Y_mask=st.Y_mask, YdotY=st.y_state.YdotY[None], Y_scale=st.Y_scale, dof=st.dof)
+    assert eng.unique_masks == 2
+    X = rg.integers(0, 3, (G, N)).astype(np.float64)
+    assert_stats_close(eng.run(GenotypeBlock(X, 'f64')), orc.block_stats(X, st), label='mask dedup')
+    eng.close()
+
+
+def test_fully_observed_phenotypes_take_any_covariate_count(rg):
+    from glow_b200.engine import DeviceState
+    N, P = 200, 2
     Y = rg.standard_normal((N, P))
-    mask = np.ones((N, P))
-    mask[3, 0] = 0
-    kw = dict(Y=Y * mask, Y_mask=mask, YdotY=np.sum((Y * mask)**2, axis=0), Y_scale=np.ones(P))
-    monkeypatch.setenv('GLR_MASK8', '0')
-    monkeypatch.setenv('GLR_MASK_SPARSE', '0')
-    with pytest.raises(ValueError, match='at most 64 covariates'):
-        DeviceState(Q=Q, dof=N - K - 1, **kw)
-    monkeypatch.delenv('GLR_MASK8')
-    monkeypatch.delenv('GLR_MASK_SPARSE')
     Q65 = np.linalg.qr(rg.standard_normal((N, 65)))[0]
-    with pytest.raises(ValueError, match='at most 64 covariates'):
-        DeviceState(Q=Q65, dof=N - 65 - 1, **kw)
     # fully observed phenotypes have no such limit
     eng = DeviceState(Q=Q65, Y=Y, Y_mask=np.ones((N, P)), YdotY=np.sum(Y**2, axis=0), Y_scale=np.ones(P), dof=N - 65 - 1)
     eng.close()

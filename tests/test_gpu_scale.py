@@ -11,14 +11,17 @@ from oracle import linreg_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-def _engine_for(phe, cov, off=None, **kw):
-    """DeviceState built from the oracle's own driver-side preparation (lin_reg.py:142-159)."""
+def _engine_from(st, options=None):
     from glow_b200.engine import DeviceState
-    st = orc.prepare_state(phe, cov, off, **kw)
     ys = list(st.y_state.values()) if isinstance(st.y_state, dict) else [st.y_state]
-    eng = DeviceState(Q=st.Q, Y=np.stack([y.Y for y in ys]), Y_mask=st.Y_mask, YdotY=np.stack([y.YdotY for y in ys]),
-                      Y_scale=st.Y_scale, dof=st.dof)
-    return eng, st
+    return DeviceState(Q=st.Q, Y=np.stack([y.Y for y in ys]), Y_mask=st.Y_mask, YdotY=np.stack([y.YdotY for y in ys]),
+                       Y_scale=st.Y_scale, dof=st.dof, options=options)
+
+
+def _engine_for(phe, cov, off=None, options=None, **kw):
+    """DeviceState built from the oracle's own driver-side preparation (lin_reg.py:142-159)."""
+    st = orc.prepare_state(phe, cov, off, **kw)
+    return _engine_from(st, options), st
 
 
 def _hardcalls(rg, G, N, missing=0.01):
@@ -150,4 +153,165 @@ def test_config5_shape_loco(rg):
         X = orc.mean_substitute(states[ci * 100 + idx].astype(np.float64))
         ref = orc.block_stats(X, st, c)
         assert_stats_close({k: res[k][:, idx] for k in STATS}, ref, label=f'cfg5 contig {c}')
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# The headline kernel (split8_kernel, tcgen05 int8 digit-split contraction) at the headline shapes, ALL FOUR statistics
+# against the oracle.  N = 500 000 is 3 907 stages per tile: the ring parities wrap ~490 times and the int32 digit sums
+# reach 1.3e8.
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def ukb_block():
+    """4 096 variants x 500 000 samples, PLINK 2-bit, 1 % missing calls (configs[2] shape), with its state."""
+    from gpu_utils import gen_packed_gpu
+    N, G, K = 500_000, 4096, 16
+    rg = np.random.default_rng(20261020)
+    packed = gen_packed_gpu(G, N, seed=77, missing=0.01)
+    cov = pd.DataFrame(rg.standard_normal((N, K)))
+    from gpu_utils import unpack_states
+    phe = pd.DataFrame(rg.standard_normal((N, 1)) + 0.02 * unpack_states(packed[:1], N).T.astype(np.float64))
+    st = orc.prepare_state(phe, cov)
+    return packed, st, N, G
+
+
+def _subset_ref(packed, st, N, idx, contig=None):
+    from gpu_utils import unpack_states
+    X = orc.mean_substitute(unpack_states(packed[idx], N).astype(np.float64))
+    return orc.block_stats(X, st) if contig is None else orc.block_stats(X, st, contig)
+
+
+@pytest.mark.parametrize('pair', ['force', 'off'])
+def test_split8_headline_shape_all_statistics(ukb_block, pair):
+    """N = 500 000, K = 17, P = 1, 1 % missing, mean-imputed: split8 forced (CTA pairs / single CTAs) vs the oracle on a
+    scattered subset that includes the tile and pair boundaries."""
+    from glow_b200 import _capi
+    from glow_b200.engine import GenotypeBlock
+    packed, st, N, G = ukb_block
+    eng = _engine_from(st, {'split8': 'force', 'split8_pair': pair, 'optimistic_calls': 'off'})
+    res = eng.run(GenotypeBlock(packed, 'plink2', 'mean'))
+    path = eng.timing(0)['path']
+    assert path & _capi.PATH_SPLIT8 and bool(path & _capi.PATH_SPLIT8_PAIR) == (pair == 'force')
+    assert not path & (_capi.PATH_PREPASS | _capi.PATH_DMMA)
+    rg = np.random.default_rng(5)
+    idx = np.unique(np.concatenate([[0, 127, 128, 255, 256, 2047, 2048, G - 129, G - 128, G - 1], rg.choice(G, 14, replace=False)]))
+    assert_stats_close({k: res[k][:, idx] for k in STATS}, _subset_ref(packed, st, N, idx), label=f'split8 pair={pair} N=500k')
+    assert np.isfinite(res['pvalue']).all()
+    eng.close()
+
+
+def test_default_knobs_reach_split8_at_headline_shape(ukb_block):
+    """With default knobs the 4 096-variant block takes the int8 tensor-core path (no env, no options), a 1 024-variant
+    block takes it too -- with the sample range split across CTAs -- and both agree with the oracle; the integer partial
+    sums make the split form bit-identical to the unsplit one."""
+    from glow_b200 import _capi
+    from glow_b200.engine import GenotypeBlock
+    packed, st, N, G = ukb_block
+    eng = _engine_from(st)
+    res = eng.run(GenotypeBlock(packed, 'plink2', 'mean'))
+    assert eng.timing(0)['path'] & _capi.PATH_SPLIT8
+    idx = np.array([1, 130, 1999, 4000])
+    assert_stats_close({k: res[k][:, idx] for k in STATS}, _subset_ref(packed, st, N, idx), label='default knobs N=500k')
+    small = eng.run(GenotypeBlock(packed[1000:2024], 'plink2', 'mean'))
+    path = eng.timing(0)['path']
+    assert path & _capi.PATH_SPLIT8 and path & _capi.PATH_SPLIT8_NSPLIT, path
+    for k in STATS:
+        assert np.array_equal(small[k], res[k][:, 1000:2024], equal_nan=True), k
+    # every split factor gives the same bits
+    for ns in (1, 3, 7):
+        e2 = _engine_from(st, {'split8': 'force', 'sample_split': ns})
+        r2 = e2.run(GenotypeBlock(packed[1000:1300], 'plink2', 'mean'))
+        for k in STATS:
+            assert np.array_equal(r2[k], res[k][:, 1000:1300], equal_nan=True), (k, ns)
+        e2.close()
+    eng.close()
+
+
+def test_optimistic_form_without_missing_calls(ukb_block):
+    """Fully called blocks: after one block without a missing call the next ones run without the missing-call operand
+    (half the tensor work); a block that does have missing calls is detected in the kernel and re-run.  Identical bits
+    either way."""
+    from glow_b200 import _capi
+    from glow_b200.engine import GenotypeBlock
+    from gpu_utils import gen_packed_gpu
+    packed_m, st, N, G = ukb_block
+    full = gen_packed_gpu(1024, N, seed=99, missing=0.0)
+    ref_eng = _engine_from(st, {'split8': 'force', 'optimistic_calls': 'off'})
+    want_full = ref_eng.run(GenotypeBlock(full, 'plink2', 'mean'))
+    want_miss = ref_eng.run(GenotypeBlock(packed_m[:1024], 'plink2', 'mean'))
+    ref_eng.close()
+    eng = _engine_from(st, {'split8': 'force'})
+    r1 = eng.run(GenotypeBlock(full, 'plink2', 'mean'))
+    assert not eng.timing(0)['path'] & _capi.PATH_OPTIMISTIC  # nothing known about the stream yet
+    r2 = eng.run(GenotypeBlock(full, 'plink2', 'mean'))
+    assert eng.timing(0)['path'] & _capi.PATH_OPTIMISTIC
+    r3 = eng.run(GenotypeBlock(packed_m[:1024], 'plink2', 'mean'))  # has missing calls: optimistic run is void, re-run
+    assert eng.timing(0)['path'] & _capi.PATH_REPLAYED
+    r4 = eng.run(GenotypeBlock(full, 'plink2', 'mean'))
+    assert not eng.timing(0)['path'] & _capi.PATH_OPTIMISTIC  # the stream has shown missing calls
+    for k in STATS:
+        assert np.array_equal(r1[k], want_full[k], equal_nan=True), k
+        assert np.array_equal(r2[k], want_full[k], equal_nan=True), k
+        assert np.array_equal(r3[k], want_miss[k], equal_nan=True), k
+        assert np.array_equal(r4[k], want_full[k], equal_nan=True), k
+    idx = np.array([0, 500, 1023])
+    assert_stats_close({k: r2[k][:, idx] for k in STATS}, _subset_ref(full, st, N, idx), label='optimistic form')
+    eng.close()
+
+
+@pytest.mark.parametrize('pair', ['force', 'off'])
+def test_split8_loco_200k_all_statistics(pair):
+    """configs[4] shape: 200 000 samples x 20 phenotypes, K = 17, LOCO offsets for 3 contigs, split8 forced."""
+    from glow_b200 import _capi
+    from glow_b200.engine import GenotypeBlock
+    from gpu_utils import gen_packed_gpu
+    rg = np.random.default_rng(11)
+    N, G, P, K = 200_000, 3 * 640, 20, 16
+    contigs = ['1', '2', '3']
+    cov = pd.DataFrame(rg.standard_normal((N, K)))
+    phe = pd.DataFrame(rg.standard_normal((N, P)))
+    off = pd.DataFrame(0.1 * rg.standard_normal((N * 3, P)), index=pd.MultiIndex.from_product([phe.index, contigs]))
+    packed = gen_packed_gpu(G, N, seed=5, missing=0.01)
+    eng, st = _engine_for(phe, cov, off, options={'split8': 'force', 'split8_pair': pair})
+    for ci, c in enumerate(contigs):
+        blk = packed[ci * 640:(ci + 1) * 640]
+        res = eng.run(GenotypeBlock(blk, 'plink2', 'mean'), contig=ci)
+        assert eng.timing(0)['path'] & _capi.PATH_SPLIT8
+        idx = np.array([0, 127, 128, 300, 639])
+        assert_stats_close({k: res[k][:, idx] for k in STATS}, _subset_ref(blk, st, N, idx, c), label=f'split8 LOCO contig {c}')
+    eng.close()
+
+
+@pytest.mark.parametrize('form', ['split8_pair', 'split8_single', 'dmma'])
+def test_adversarial_dynamic_range(form):
+    """Pins the quantisation bound of the digit split (2^-54 of each column's maximum): a one-hot covariate, a covariate
+    with a 1e6 x outlier, a heavy-tailed phenotype (Student t, 1.5 degrees of freedom) and heavy-tailed LOCO offsets --
+    columns whose maximum is far above their typical entry.  Every variant against the oracle at the north-star
+    tolerances."""
+    from glow_b200.engine import GenotypeBlock
+    rg = np.random.default_rng(3)
+    N, G, P = 65_537, 384, 3
+    cov = rg.standard_normal((N, 6))
+    cov[:, 0] = 0.0
+    cov[12_345, 0] = 1.0                      # one-hot covariate
+    cov[777, 1] = 1e6                         # outlier 1e6 x the column's scale
+    cov[:, 2] = rg.standard_t(1.5, N)         # heavy-tailed covariate
+    phe = rg.standard_normal((N, P))
+    phe[:, 0] = rg.standard_t(1.5, N)
+    phe[4242, 1] = 1e5
+    contigs = ['1', '2']
+    off = pd.DataFrame(rg.standard_t(1.5, (N * 2, P)) * 0.05, index=pd.MultiIndex.from_product([range(N), contigs]))
+    f = rg.uniform(0.001, 0.5, (G, 1))
+    states = rg.binomial(2, f, (G, N)).astype(np.int8)
+    states[rg.random((G, N), dtype=np.float32) < 0.01] = -1
+    states[:, 12_345] = 2                     # the one-hot sample carries the allele in every variant
+    states[:3, 777] = [0, 1, 2]
+    opts = {'split8_pair': {'split8': 'force', 'split8_pair': 'force'}, 'split8_single': {'split8': 'force', 'split8_pair': 'off'},
+            'dmma': {'split8': 'off'}}[form]
+    eng, st = _engine_for(pd.DataFrame(phe), pd.DataFrame(cov), off, options=opts)
+    X = orc.mean_substitute(states.astype(np.float64))
+    packed = pack_plink(states)
+    for ci, c in enumerate(contigs):
+        res = eng.run(GenotypeBlock(packed, 'plink2', 'mean'), contig=ci)
+        assert_stats_close(res, orc.block_stats(X, st, c), label=f'adversarial range, {form}, contig {c}')
     eng.close()
