@@ -7,8 +7,9 @@ The block loop runs in hand-written sm_100a CUDA behind the C ABI in include/glo
 (glow_b200/lib/libglow_b200.so, built by ``python -m glow_b200.build``); there is no CPU fallback.
 """
 from . import gwas
-from .engine import DeviceState, GenotypeBlock
-from .sources import ArraySource, GenotypeSource, PlinkBedSource
+from .engine import DeviceGroup, DeviceState, GenotypeBlock
+from .sources import ArraySource, GenotypeSource, PlinkBedSource, ResidentSource
 
-__all__ = ['gwas', 'DeviceState', 'GenotypeBlock', 'ArraySource', 'GenotypeSource', 'PlinkBedSource']
+__all__ = ['gwas', 'DeviceGroup', 'DeviceState', 'GenotypeBlock', 'ArraySource', 'GenotypeSource', 'PlinkBedSource',
+           'ResidentSource']
 __version__ = '0.1.0'

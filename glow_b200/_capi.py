@@ -90,6 +90,14 @@ SYMBOLS = {
     'glr_t_two_sided_pvalues': (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     'glr_decode_block': (C.c_int, [C.c_int, C.POINTER(BlockDesc), C.c_int64, C.c_void_p]),
     'glr_tensor_i8_issue_rate': (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double)]),
+    'glr_device_alloc': (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    'glr_device_free': (C.c_int, [C.c_int, C.c_void_p]),
+    'glr_device_upload': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    'glr_comm_init': (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
+    'glr_comm_destroy': (C.c_int, [C.c_void_p]),
+    'glr_comm_size': (C.c_int, [C.c_void_p]),
+    'glr_comm_transport': (C.c_char_p, [C.c_void_p]),
+    'glr_comm_broadcast_state': (C.c_int, [C.c_void_p, C.POINTER(StateDesc), C.POINTER(C.c_void_p)]),
 }
 
 _lib = None

@@ -1,4 +1,6 @@
 // C ABI (include/glow_b200.h): state packing, lanes (streams + staging), block execution.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -145,6 +147,16 @@ struct glr_state {
   int s8_pair_mode = GLR_AUTO;
   int optimistic_mode = GLR_AUTO;
   bool expect_missing = true;  // the last counted PLINK2 block had missing calls (or none has been seen yet)
+  int n_lanes_req = 2;
+  // persistent device arrays: (offset of the pointer field inside this struct, bytes) -- what glr_comm_broadcast_state
+  // replicates to the other devices
+  std::vector<std::pair<size_t, size_t>> arrays;
+  template <typename T>
+  cudaError_t alloc(T** field, size_t bytes) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(field), bytes ? bytes : 1);
+    if (e == cudaSuccess) arrays.emplace_back((size_t)(reinterpret_cast<char*>(field) - reinterpret_cast<char*>(this)), bytes);
+    return e;
+  }
 };
 
 extern "C" {
@@ -194,15 +206,31 @@ int glr_state_destroy(glr_state* st) {
     if (l.h_flags) cudaFreeHost(l.h_flags);
     if (l.stream) cudaStreamDestroy(l.stream);
   }
-  for (void* p : {(void*)st->wpk, (void*)st->qb, (void*)st->mpk, (void*)st->mask_id, (void*)st->YdotY,
-                  (void*)st->Y_scale, (void*)st->n_obs, (void*)st->drop_idx, (void*)st->w8, (void*)st->s8_scale,
-                  (void*)st->qg, (void*)st->m8, (void*)st->sp_idx, (void*)st->sp_qm, (void*)st->sp_off})
+  for (auto& a : st->arrays) {
+    void* p = *reinterpret_cast<void**>(reinterpret_cast<char*>(st) + a.first);
     if (p) cudaFree(p);
+  }
   delete st;
   return 0;
 }
 
 int glr_state_unique_masks(glr_state* st) { return st ? st->U : 0; }
+
+// lanes = independent streams with their own workspaces (current device = st->device)
+static int create_lanes(glr_state* st) {
+  int n_lanes = st->n_lanes_req > 0 ? st->n_lanes_req : 2;
+  if (n_lanes > 8) n_lanes = 8;
+  st->lanes.resize(n_lanes);
+  for (auto& l : st->lanes) {
+    CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    for (auto& e : l.ev) CU(cudaEventCreate(&e));
+    if (int rc2 = l.flags.ensure(2 * sizeof(int32_t))) return rc2;
+    CU(cudaHostAlloc((void**)&l.h_flags, 2 * sizeof(int32_t), cudaHostAllocDefault));
+    l.h_flags[0] = l.h_flags[1] = 0;
+  }
+  st->expect_missing = st->optimistic_mode != GLR_FORCE;
+  return 0;
+}
 
 int glr_state_create(const glr_state_desc* d, glr_state** out) {
   if (!d || !out) return fail(GLR_ERR_INVALID, "null argument");
@@ -266,7 +294,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     CU(cudaMalloc(&d_g2r, Ng * sizeof(int64_t)));
     CU(cudaMemcpy(d_g2r, g2r.data(), Ng * sizeof(int64_t), cudaMemcpyHostToDevice));
     if (st->n_drop) {
-      CU(cudaMalloc(&st->drop_idx, drop.size() * sizeof(int64_t)));
+      CU(st->alloc(&st->drop_idx, drop.size() * sizeof(int64_t)));
       CU(cudaMemcpy(st->drop_idx, drop.data(), drop.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
     }
   }
@@ -330,16 +358,16 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   st->U = (int)rep.size();
 
   // ---- small arrays ----
-  CU(cudaMalloc(&st->mask_id, P * sizeof(int32_t)));
+  CU(st->alloc(&st->mask_id, P * sizeof(int32_t)));
   CU(cudaMemcpy(st->mask_id, mask_id.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CU(cudaMalloc(&st->YdotY, (size_t)C * P * sizeof(double)));
+  CU(st->alloc(&st->YdotY, (size_t)C * P * sizeof(double)));
   CU(cudaMemcpy(st->YdotY, d->YdotY, (size_t)C * P * sizeof(double), in_kind));
-  CU(cudaMalloc(&st->Y_scale, P * sizeof(double)));
+  CU(st->alloc(&st->Y_scale, P * sizeof(double)));
   CU(cudaMemcpy(st->Y_scale, d->Y_scale, P * sizeof(double), in_kind));
   {
     std::vector<double> nf(P);
     for (int p = 0; p < P; ++p) nf[p] = (double)nobs[p];
-    CU(cudaMalloc(&st->n_obs, P * sizeof(double)));
+    CU(st->alloc(&st->n_obs, P * sizeof(double)));
     CU(cudaMemcpy(st->n_obs, nf.data(), P * sizeof(double), cudaMemcpyHostToDevice));
   }
 
@@ -402,7 +430,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   st->w_contig_doubles =
       (int64_t)st->n_groups * st->n_chunks * kChunkGroups * (st->MT * kAtomDoubles + st->tail * kGroup);
   const size_t w_bytes = (size_t)C * st->w_contig_doubles * sizeof(double);
-  CU(cudaMalloc(&st->wpk, w_bytes));
+  CU(st->alloc(&st->wpk, w_bytes));
   CU(cudaMemsetAsync(st->wpk, 0, w_bytes, s0));
   // integer tensor-core operand (split8.cu): any number of columns (blocks of up to 18)
   double* d_colmax = nullptr;
@@ -416,9 +444,9 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     if ((int64_t)C * st->s8_contig_bytes <= ((int64_t)16 << 30)) st->split8 = split8_mode == GLR_FORCE ? 2 : 1;
   }
   if (st->split8) {
-    CU(cudaMalloc(&st->w8, (size_t)C * st->s8_contig_bytes));
+    CU(st->alloc(&st->w8, (size_t)C * st->s8_contig_bytes));
     CU(cudaMemsetAsync(st->w8, 0, (size_t)C * st->s8_contig_bytes, s0));
-    CU(cudaMalloc(&st->s8_scale, (size_t)C * st->s8_cols * sizeof(double)));
+    CU(st->alloc(&st->s8_scale, (size_t)C * st->s8_cols * sizeof(double)));
     CU(cudaMalloc(&d_colmax, (size_t)st->s8_cols * sizeof(double)));
     tmp.v.push_back(d_colmax);
   }
@@ -519,9 +547,9 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
       st->sp_total = (int64_t)sp_idx.size();
       const int Kp = (K + 1) & ~1;
       int64_t* d_rows = nullptr;
-      CU(cudaMalloc(&st->sp_idx, std::max<size_t>(sp_idx.size(), 1) * sizeof(int32_t)));
-      CU(cudaMalloc(&st->sp_off, sp_off.size() * sizeof(int64_t)));
-      CU(cudaMalloc(&st->sp_qm, std::max<size_t>(sp_idx.size() * Kp, 1) * sizeof(double)));
+      CU(st->alloc(&st->sp_idx, std::max<size_t>(sp_idx.size(), 1) * sizeof(int32_t)));
+      CU(st->alloc(&st->sp_off, sp_off.size() * sizeof(int64_t)));
+      CU(st->alloc(&st->sp_qm, std::max<size_t>(sp_idx.size() * Kp, 1) * sizeof(double)));
       CU(cudaMalloc(&d_rows, std::max<size_t>(sp_rows.size(), 1) * sizeof(int64_t)));
       tmp.v.push_back(d_rows);
       CU(cudaMemcpy(st->sp_idx, sp_idx.data(), sp_idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -535,10 +563,10 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
       const size_t m8_bytes = (size_t)st->m8_nmb * st->m8_stages * st->m8_NB * 128;
       if (m8_bytes <= ((size_t)8 << 30)) {
         st->mask8 = mask8_mode;
-        CU(cudaMalloc(&st->m8, m8_bytes));
+        CU(st->alloc(&st->m8, m8_bytes));
         CU(cudaMemsetAsync(st->m8, 0, m8_bytes, s0));
         launch_pack_mask8(dMu, N, U, d_g2r, Ng, st->m8_NB, st->m8_stages, st->m8, s0);
-        CU(cudaMalloc(&st->qg, (size_t)std::max<int64_t>(Ng * K, 1) * sizeof(double)));
+        CU(st->alloc(&st->qg, (size_t)std::max<int64_t>(Ng * K, 1) * sizeof(double)));
         launch_gather_q(dQ, N, K, d_g2r, Ng, st->qg, s0);
       }
     }
@@ -546,12 +574,12 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
       if (!dmma_ok)
         return fail(GLR_ERR_INVALID, "masked pass: no applicable form (more than 2^31 genotype samples with more than 32 covariates)");
       const size_t qb_bytes = (size_t)st->n_chunks * kChunkGroups * st->KT2 * kAtomDoubles * sizeof(double);
-      CU(cudaMalloc(&st->qb, qb_bytes));
+      CU(st->alloc(&st->qb, qb_bytes));
       CU(cudaMemsetAsync(st->qb, 0, qb_bytes, s0));
       if (K > 0) launch_pack_qb(dQ, N, K, d_g2r, Ng, st->qb, st->KT2, st->n_chunks, s0);
       const size_t m_bytes =
           (size_t)st->n_groups2 * st->n_chunks * kChunkGroups * st->MT2 * kAtomDoubles * sizeof(double);
-      CU(cudaMalloc(&st->mpk, m_bytes));
+      CU(st->alloc(&st->mpk, m_bytes));
       CU(cudaMemsetAsync(st->mpk, 0, m_bytes, s0));
       launch_pack_a(dMu, N, U, 0, U, d_g2r, Ng, st->mpk, 0, st->MT2, 0, st->n_chunks, s0);
     }
@@ -565,18 +593,8 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     CU(cudaMemcpy(st->s8_scale, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
 
-  // ---- lanes ----
-  int n_lanes = d->n_lanes > 0 ? d->n_lanes : 2;
-  if (n_lanes > 8) n_lanes = 8;
-  st->lanes.resize(n_lanes);
-  for (auto& l : st->lanes) {
-    CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-    for (auto& e : l.ev) CU(cudaEventCreate(&e));
-    if (int rc2 = l.flags.ensure(2 * sizeof(int32_t))) return rc2;
-    CU(cudaHostAlloc((void**)&l.h_flags, 2 * sizeof(int32_t), cudaHostAllocDefault));
-    l.h_flags[0] = l.h_flags[1] = 0;
-  }
-  st->expect_missing = st->optimistic_mode != GLR_FORCE;
+  st->n_lanes_req = d->n_lanes;
+  if (int rc2 = create_lanes(st)) return rc2;
   guard.s = nullptr;
   *out = st;
   return 0;
@@ -999,6 +1017,25 @@ int glr_host_free(void* ptr) {
   return 0;
 }
 
+int glr_device_alloc(int device, size_t bytes, void** ptr) {
+  if (!ptr) return fail(GLR_ERR_INVALID, "null argument");
+  if (int rc = check_device(device)) return rc;
+  CU(cudaMalloc(ptr, bytes ? bytes : 1));
+  return 0;
+}
+int glr_device_free(int device, void* ptr) {
+  if (!ptr) return 0;
+  if (int rc = check_device(device)) return rc;
+  CU(cudaFree(ptr));
+  return 0;
+}
+int glr_device_upload(int device, void* dst, const void* src_host, size_t bytes) {
+  if (bytes && (!dst || !src_host)) return fail(GLR_ERR_INVALID, "null argument");
+  if (int rc = check_device(device)) return rc;
+  CU(cudaMemcpy(dst, src_host, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
 int glr_tensor_i8_issue_rate(int device, double milliseconds, double* tops) {
   if (!tops || !(milliseconds > 0.0)) return fail(GLR_ERR_INVALID, "bad arguments");
   int rc = check_device(device);
@@ -1062,6 +1099,170 @@ int glr_decode_block(int device, const glr_block_desc* b, int64_t n_geno, double
   cudaFree(dsxx);
   cudaFree(dout);
   if (e != cudaSuccess) return fail(GLR_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU inside one process (SURVEY.md section 8e / 8b export group 5).  Variants shard across devices, the state
+// is replicated ONCE: it is packed on the first device and every packed array is broadcast to the others in one grouped
+// NCCL call (ncclBroadcast over NVLink / NVSwitch).  NCCL is loaded at run time (dlopen of libnccl.so.2; GLR_NCCL_LIB
+// overrides the name) so that the library has no link-time dependency on it; without NCCL the same copies go through
+// cudaMemcpyPeerAsync.  There is no collective in the block loop.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*CommInitAll)(void** comms, int ndev, const int* devlist) = nullptr;
+  int (*CommDestroy)(void* comm) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Broadcast)(const void* send, void* recv, size_t count, int dtype, int root, void* comm, cudaStream_t stream) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok() const { return CommInitAll && CommDestroy && GroupStart && GroupEnd && Broadcast; }
+};
+NcclApi load_nccl() {
+  NcclApi a;
+  const char* names[] = {getenv("GLR_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n || !*n) continue;
+    a.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) return a;
+  a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(a.lib, "ncclCommInitAll"));
+  a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.lib, "ncclCommDestroy"));
+  a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(a.lib, "ncclGroupStart"));
+  a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(a.lib, "ncclGroupEnd"));
+  a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(dlsym(a.lib, "ncclBroadcast"));
+  a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.lib, "ncclGetErrorString"));
+  return a;
+}
+}  // namespace
+
+struct glr_comm {
+  std::vector<int> devices;
+  std::vector<cudaStream_t> streams;
+  std::vector<void*> nccl;  // ncclComm_t per device, empty when the peer-copy transport is used
+  NcclApi api;
+  std::string transport;
+};
+
+int glr_comm_destroy(glr_comm* c) {
+  if (!c) return 0;
+  for (size_t i = 0; i < c->devices.size(); ++i) {
+    cudaSetDevice(c->devices[i]);
+    if (i < c->nccl.size() && c->nccl[i]) c->api.CommDestroy(c->nccl[i]);
+    if (i < c->streams.size() && c->streams[i]) cudaStreamDestroy(c->streams[i]);
+  }
+  delete c;
+  return 0;
+}
+
+int glr_comm_init(const int32_t* devices, int32_t n_devices, glr_comm** out) {
+  if (!devices || n_devices <= 0 || !out) return fail(GLR_ERR_INVALID, "bad arguments");
+  *out = nullptr;
+  for (int i = 0; i < n_devices; ++i) {
+    if (int rc = check_device(devices[i])) return rc;
+    for (int j = 0; j < i; ++j)
+      if (devices[j] == devices[i]) return fail(GLR_ERR_INVALID, "duplicate device in glr_comm_init");
+  }
+  glr_comm* c = new glr_comm();
+  c->devices.assign(devices, devices + n_devices);
+  c->streams.resize(n_devices, nullptr);
+  for (int i = 0; i < n_devices; ++i) {
+    if (cudaSetDevice(devices[i]) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) != cudaSuccess) {
+      glr_comm_destroy(c);
+      return fail(GLR_ERR_CUDA, "cannot create a stream on a device of the communicator");
+    }
+  }
+  c->transport = "p2p";
+  const char* no_nccl = getenv("GLR_COMM_NO_NCCL");
+  if (n_devices > 1 && !(no_nccl && atoi(no_nccl))) {
+    c->api = load_nccl();
+    if (c->api.ok()) {
+      c->nccl.assign(n_devices, nullptr);
+      if (c->api.CommInitAll(c->nccl.data(), n_devices, c->devices.data()) == 0) c->transport = "nccl";
+      else c->nccl.clear();
+    }
+  }
+  if (c->transport == "p2p") {
+    for (int i = 1; i < n_devices; ++i) {  // direct NVLink copies from the first device
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[i], devices[0]);
+      if (can) {
+        cudaSetDevice(devices[i]);
+        if (cudaDeviceEnablePeerAccess(devices[0], 0) != cudaSuccess) cudaGetLastError();
+      }
+    }
+  }
+  *out = c;
+  return 0;
+}
+
+int glr_comm_size(glr_comm* c) { return c ? (int)c->devices.size() : 0; }
+const char* glr_comm_transport(glr_comm* c) { return c ? c->transport.c_str() : ""; }
+
+int glr_comm_broadcast_state(glr_comm* c, const glr_state_desc* desc, glr_state** out_states) {
+  if (!c || !desc || !out_states) return fail(GLR_ERR_INVALID, "null argument");
+  const int n = (int)c->devices.size();
+  for (int i = 0; i < n; ++i) out_states[i] = nullptr;
+  glr_state_desc d0 = *desc;
+  d0.device = c->devices[0];
+  if (int rc = glr_state_create(&d0, &out_states[0])) return rc;
+  glr_state* src = out_states[0];
+  auto fail_all = [&](int code, const std::string& msg) {
+    for (int i = 0; i < n; ++i) {
+      if (out_states[i]) glr_state_destroy(out_states[i]);
+      out_states[i] = nullptr;
+    }
+    return fail(code, msg);
+  };
+  // replicas: same metadata, own device arrays (same sizes), own lanes
+  for (int i = 1; i < n; ++i) {
+    glr_state* r = new glr_state(*src);
+    r->lanes.clear();
+    r->device = c->devices[i];
+    for (auto& a : r->arrays) *reinterpret_cast<void**>(reinterpret_cast<char*>(r) + a.first) = nullptr;
+    out_states[i] = r;
+    if (cudaSetDevice(r->device) != cudaSuccess) return fail_all(GLR_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, r->device);
+    for (auto& a : r->arrays) {
+      void* p = nullptr;
+      if (cudaMalloc(&p, a.second ? a.second : 1) != cudaSuccess) return fail_all(GLR_ERR_CUDA, "cudaMalloc of a state replica failed");
+      *reinterpret_cast<void**>(reinterpret_cast<char*>(r) + a.first) = p;
+    }
+    if (create_lanes(r)) return fail_all(GLR_ERR_CUDA, g_err);
+  }
+  if (n == 1) return 0;
+  auto field = [](glr_state* s, size_t off) { return *reinterpret_cast<void**>(reinterpret_cast<char*>(s) + off); };
+  if (c->transport == "nccl") {
+    // ONE group: every array, every device (root = the first device, in place there)
+    int e = c->api.GroupStart();
+    for (auto& a : src->arrays) {
+      if (!a.second) continue;
+      for (int i = 0; i < n && e == 0; ++i) {
+        cudaSetDevice(c->devices[i]);
+        e = c->api.Broadcast(field(src, a.first), field(out_states[i], a.first), a.second, /*ncclUint8*/ 1, 0, c->nccl[i], c->streams[i]);
+      }
+    }
+    const int e2 = c->api.GroupEnd();
+    if (e || e2)
+      return fail_all(GLR_ERR_CUDA, std::string("ncclBroadcast: ") + (c->api.GetErrorString ? c->api.GetErrorString(e ? e : e2) : "error"));
+  } else {
+    for (int i = 1; i < n; ++i) {
+      cudaSetDevice(c->devices[i]);
+      for (auto& a : src->arrays)
+        if (a.second &&
+            cudaMemcpyPeerAsync(field(out_states[i], a.first), c->devices[i], field(src, a.first), c->devices[0], a.second, c->streams[i]) !=
+                cudaSuccess)
+          return fail_all(GLR_ERR_CUDA, "cudaMemcpyPeerAsync of a state array failed");
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    cudaSetDevice(c->devices[i]);
+    if (cudaStreamSynchronize(c->streams[i]) != cudaSuccess) return fail_all(GLR_ERR_CUDA, "state broadcast failed");
+  }
   return 0;
 }
 

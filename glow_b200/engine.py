@@ -28,6 +28,18 @@ class GenotypeBlock:
     data: np.ndarray  # 2-D, C-contiguous rows: float64/float32/int8 [G, Ng] or uint8 [G, ceil(Ng/4)]
     format: str  # 'f64' | 'f32' | 'i8' | 'plink2'
     missing: str = 'minus_one'  # 'minus_one' (genotype_states) | 'mean' (mean_substitute)
+    pinned: bool = False  # `data` lives in page-locked memory (glr_host_alloc): it is copied to the device as is
+
+
+@dataclass
+class ResidentBlock:
+    """A block that already lives in the HBM of one GPU (glow_b200.sources.ResidentSource)."""
+    addr: int          # device address of the first row
+    stride: int        # bytes between variants
+    n_variants: int
+    format: str
+    missing: str
+    device: int        # CUDA ordinal that owns the memory
 
 
 def _arrow_list_to_matrix(col):
@@ -97,13 +109,16 @@ class DeviceState:
                  n_lanes: int = 2,
                  memspace: int = _capi.MEM_HOST,
                  dims: Optional[Tuple[int, int, int, int]] = None,
-                 options: Optional[dict] = None):
+                 options: Optional[dict] = None,
+                 _handle=None):
         """Host arrays (float64, C order): Q [N,K]; Y [C,N,P] or [N,P]; Y_mask [N,P]; YdotY [C,P] or [P];
         Y_scale [P].  With memspace=MEM_DEVICE the array arguments are integer device addresses and
         ``dims`` = (N, K, P, C) must be given.  ``options``: kernel-selection knobs (glr_options fields, e.g.
         ``{'split8': 'force', 'split8_pair': 'off'}``); the default leaves every choice to the library."""
         self._lib = _capi.load()
         self._handle = C.c_void_p()
+        self._pending: Dict[int, tuple] = {}
+        self._stage: Dict[int, dict] = {}
         if memspace == _capi.MEM_HOST:
             Q = np.ascontiguousarray(Q, dtype=np.float64)
             Y = np.ascontiguousarray(Y, dtype=np.float64)
@@ -156,8 +171,24 @@ class DeviceState:
                             n_lanes=n_lanes,
                             memspace=memspace,
                             opt=_capi.make_options(options))
-        _capi.check(self._lib.glr_state_create(C.byref(d), C.byref(self._handle)))
-        self._pending: Dict[int, tuple] = {}
+        self._desc = d
+        if _handle is None:
+            _capi.check(self._lib.glr_state_create(C.byref(d), C.byref(self._handle)))
+        elif _handle:  # replica created by glr_comm_broadcast_state (DeviceGroup)
+            self._handle = C.c_void_p(_handle)
+
+    @classmethod
+    def _replica(cls, template: 'DeviceState', handle: int, device: int) -> 'DeviceState':
+        """Wraps a state handle that glr_comm_broadcast_state created on another device."""
+        r = cls.__new__(cls)
+        r._lib = template._lib
+        r._handle = C.c_void_p(handle)
+        r._pending, r._stage = {}, {}
+        for k in ('N', 'K', 'P', 'n_contigs', 'Ng', 'verbose', 'n_lanes'):
+            setattr(r, k, getattr(template, k))
+        r.device = device
+        r._desc = None
+        return r
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -196,24 +227,55 @@ class DeviceState:
                              f'in format {block.format}')
         return fmt, data
 
-    def submit(self, lane: int, block: GenotypeBlock, contig: int = 0, out: Optional[Dict[str, np.ndarray]] = None):
-        """Queues one block on a lane (H2D copy, kernels, D2H copy all asynchronous)."""
-        fmt, data = self._check_block(block)
-        G = int(data.shape[0])
+    # Pinned staging (per lane, grown on demand).  A device-to-host copy into pageable memory returns only when it has
+    # finished, which would serialise the lanes; results therefore land in pinned buffers and wait() copies them out.
+    # Pageable genotype blocks are staged the same way so that their H2D copy is asynchronous as well.
+    _STAGE_INPUT_LIMIT = 2 << 30
+
+    def _pinned(self, lane: int, key: str, nbytes: int) -> np.ndarray:
+        st = self._stage.setdefault(lane, {})
+        buf = st.get(key)
+        if buf is None or buf.size < nbytes:
+            st[key] = buf = _capi.pinned_empty((max(nbytes + nbytes // 4, 4096), ), np.uint8)
+        return buf
+
+    def submit(self, lane: int, block: GenotypeBlock, contig: int = 0, out: Optional[Dict[str, np.ndarray]] = None,
+               pinned_input: bool = False):
+        """Queues one block on a lane: H2D copy, kernels and D2H copy are all asynchronous.  ``out`` (optional) must be
+        pinned arrays; without it the results land in the lane's pinned staging and wait() returns copies.
+        ``pinned_input``: the block's memory is already page-locked (sources that stage their own blocks)."""
+        resident = isinstance(block, ResidentBlock)
+        if resident:
+            if block.device != self.device:
+                raise ValueError(f'resident block lives on GPU {block.device}, this state on GPU {self.device}')
+            fmt, data, G = FORMATS[block.format], None, int(block.n_variants)
+        else:
+            fmt, data = self._check_block(block)
+            G = int(data.shape[0])
         names = STAT_NAMES + (VERBOSE_NAMES if self.verbose else ())
-        if out is None:
-            out = {k: np.empty((self.P, G), dtype=np.float64) for k in names}
-        bd = self._block_desc(fmt, data.ctypes.data if G else None, data.strides[0] if G else 0, G, contig,
-                              block.missing, _capi.MEM_HOST)
+        staged_out = out is None
+        if staged_out:
+            n = self.P * G
+            flat = self._pinned(lane, 'out', 8 * n * len(names)).view(np.float64)
+            out = {k: flat[i * n:(i + 1) * n].reshape(self.P, G) for i, k in enumerate(names)}
+        if resident:
+            bd = self._block_desc(fmt, block.addr if G else None, block.stride, G, contig, block.missing, _capi.MEM_DEVICE)
+        else:
+            if G and not pinned_input and not getattr(block, 'pinned', False) and data.nbytes <= self._STAGE_INPUT_LIMIT:
+                stage = self._pinned(lane, 'in', data.nbytes)[:data.nbytes].view(data.dtype).reshape(data.shape)
+                np.copyto(stage, data)
+                data = stage
+            bd = self._block_desc(fmt, data.ctypes.data if G else None, data.strides[0] if G else 0, G, contig,
+                                  block.missing, _capi.MEM_HOST)
         bo = _capi.BlockOut(memspace=_capi.MEM_HOST, **{k: out[k].ctypes.data if G else None for k in names})
         _capi.check(self._lib.glr_block_submit(self._handle, lane, C.byref(bd), C.byref(bo)))
-        self._pending[lane] = (out, data)  # keep host buffers alive until wait()
+        self._pending[lane] = (out, data, staged_out)  # keep host buffers alive until wait()
         return out
 
     def wait(self, lane: int) -> Dict[str, np.ndarray]:
         _capi.check(self._lib.glr_block_wait(self._handle, lane))
-        out, _ = self._pending.pop(lane)
-        return out
+        out, _, staged = self._pending.pop(lane)
+        return {k: v.copy() for k, v in out.items()} if staged else out
 
     def run(self, block: GenotypeBlock, contig: int = 0) -> Dict[str, np.ndarray]:
         """One block, synchronously: the device counterpart of lin_reg.py:226-249.
@@ -257,6 +319,134 @@ class DeviceState:
             lane = (lane + 1) % self.n_lanes
         while inflight:
             yield self.wait(inflight.pop(0))
+
+
+def contiguous_blocks(n_blocks: int, rank: int, world: int) -> Tuple[int, int]:
+    """Blocks [start, stop) of shard `rank` of `world`: contiguous ranges, so concatenating the shards in rank order
+    reproduces the single-GPU order, and whole blocks, so every block is the one a single GPU would have run."""
+    return (n_blocks * rank) // world, (n_blocks * (rank + 1)) // world
+
+
+class DeviceGroup:
+    """State replicated on several GPUs of this process: built and packed on the first device,
+    every packed array sent to the others by one grouped NCCL broadcast (glr_comm_broadcast_state), then variant blocks
+    are spread over (device, lane) slots and the results gathered in submission order.  The counterpart of the
+    reference's Spark partitioning of variant rows with the state captured in the closure (lin_reg.py:277-284)."""
+
+    def __init__(self, devices: Sequence[int], **state_kwargs):
+        devices = [int(d) for d in devices]
+        if not devices or len(set(devices)) != len(devices):
+            raise ValueError('devices must be a non-empty list of distinct CUDA ordinals')
+        self._lib = _capi.load()
+        self.devices = devices
+        self._comm = C.c_void_p()
+        if len(devices) == 1:
+            self.states = [DeviceState(device=devices[0], **state_kwargs)]
+            self.transport = 'single'
+            return
+        arr = (C.c_int32 * len(devices))(*devices)
+        _capi.check(self._lib.glr_comm_init(arr, len(devices), C.byref(self._comm)))
+        first = DeviceState(device=devices[0], _handle=0, **state_kwargs)  # validates + builds the descriptor only
+        handles = (C.c_void_p * len(devices))()
+        rc = self._lib.glr_comm_broadcast_state(self._comm, C.byref(first._desc), handles)
+        if rc:
+            self._lib.glr_comm_destroy(self._comm)
+            self._comm = C.c_void_p()
+            _capi.check(rc)
+        first._handle = C.c_void_p(handles[0])
+        self.states = [first] + [DeviceState._replica(first, handles[i], devices[i]) for i in range(1, len(devices))]
+        self.transport = self._lib.glr_comm_transport(self._comm).decode()
+
+    def __len__(self):
+        return len(self.states)
+
+    @property
+    def unique_masks(self) -> int:
+        return self.states[0].unique_masks
+
+    @property
+    def verbose(self) -> bool:
+        return self.states[0].verbose
+
+    def close(self):
+        for s in getattr(self, 'states', []):
+            s.close()
+        self.states = []
+        if getattr(self, '_comm', None) is not None and self._comm.value:
+            self._lib.glr_comm_destroy(self._comm)
+            self._comm = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def slots(self) -> List[Tuple[int, int]]:
+        """(device index, lane) pairs, device-minor: consecutive blocks go to different GPUs."""
+        n_lanes = self.states[0].n_lanes
+        return [(d, l) for l in range(n_lanes) for d in range(len(self.states))]
+
+    def run_pipelined(self, blocks: Iterable[Tuple[GenotypeBlock, int]], assign=None) -> Iterator[Dict[str, np.ndarray]]:
+        """Streams (block, contig) pairs over every (device, lane) slot and yields the results in SUBMISSION order (the
+        ordered gather): the output is identical, bit for bit, to running the same blocks on one GPU.
+        ``assign(k)`` -> device index of block k (default: round robin)."""
+        n_dev, n_lanes = len(self.states), self.states[0].n_lanes
+        free = [list(range(n_lanes)) for _ in range(n_dev)]
+        inflight: List[Tuple[int, int]] = []
+        for k, (block, contig) in enumerate(blocks):
+            d = assign(k) if assign is not None else k % n_dev
+            while not free[d]:  # results come back in order: drain from the front until this device has a lane
+                dd, ll = inflight.pop(0)
+                yield self.states[dd].wait(ll)
+                free[dd].append(ll)
+            lane = free[d].pop(0)
+            self.states[d].submit(lane, block, contig)
+            inflight.append((d, lane))
+        while inflight:
+            dd, ll = inflight.pop(0)
+            yield self.states[dd].wait(ll)
+
+
+    def run_shards(self, shard_iters: Sequence[Iterator[Tuple[GenotypeBlock, int]]]):
+        """Contiguous sharding: ``shard_iters[d]`` yields the (block, contig) pairs of device d's variant range.  All
+        devices are fed concurrently (each keeps its lanes full); yields ``(d, seq, result)`` as blocks complete, in
+        order within a device.  Concatenating by (d, seq) gives the single-GPU order."""
+        n_dev, n_lanes = len(self.states), self.states[0].n_lanes
+        if len(shard_iters) != n_dev:
+            raise ValueError('one shard iterator per device')
+        iters = [iter(it) for it in shard_iters]
+        free = [list(range(n_lanes)) for _ in range(n_dev)]
+        inflight: List[List[Tuple[int, int, int]]] = [[] for _ in range(n_dev)]  # (lane, seq, submit counter)
+        done = [False] * n_dev
+        seq = [0] * n_dev
+        counter = 0
+        while True:
+            progressed = False
+            for d in range(n_dev):
+                if done[d] or not free[d]:
+                    continue
+                try:
+                    block, contig = next(iters[d])
+                except StopIteration:
+                    done[d] = True
+                    continue
+                lane = free[d].pop(0)
+                self.states[d].submit(lane, block, contig)
+                inflight[d].append((lane, seq[d], counter))
+                seq[d] += 1
+                counter += 1
+                progressed = True
+            if progressed:
+                continue
+            oldest = [(q[0][2], d) for d, q in enumerate(inflight) if q]
+            if not oldest:
+                return
+            _, d = min(oldest)
+            lane, sq, _ = inflight[d].pop(0)
+            res = self.states[d].wait(lane)
+            free[d].append(lane)
+            yield d, sq, res
 
 
 def t_two_sided_pvalues(t: np.ndarray, dof: float, device: int = 0) -> np.ndarray:

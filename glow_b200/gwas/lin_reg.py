@@ -15,14 +15,14 @@ ABI in include/glow_b200.h.  There is no CPU fallback for the block loop.
     device undecoded and the 2-bit decode / mean substitution is fused into the GEMM operand load.
 """
 from dataclasses import dataclass, field
-from typing import Any, Dict, Iterable, Iterator, List, Optional, Union
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Union
 
 import numpy as np
 import pandas as pd
 
 from . import functions as gwas_fx
 from .functions import _VALUES_COLUMN_NAME, _get_indices_to_drop, _get_contigs_from_loco_df
-from ..engine import DeviceState, GenotypeBlock, as_block, STAT_NAMES, VERBOSE_NAMES
+from ..engine import (DeviceGroup, DeviceState, GenotypeBlock, as_block, contiguous_blocks, STAT_NAMES, VERBOSE_NAMES)
 
 __all__ = ['linear_regression']
 
@@ -55,11 +55,16 @@ def linear_regression(genotype_df,
                       verbose_output: bool = False,
                       intersect_samples: bool = False,
                       genotype_sample_ids: Optional[List[str]] = None,
-                      device: int = 0):
+                      device: int = 0,
+                      devices: Optional[Sequence[int]] = None,
+                      options: Optional[dict] = None):
     """Linear-regression association test of every variant against every phenotype.
 
     Arguments, defaults, validation errors and the output columns are those of the reference
-    (lin_reg.py:18-116); ``device`` (CUDA ordinal) is the only addition.
+    (lin_reg.py:18-116).  Additions: ``device`` (CUDA ordinal); ``devices`` (several ordinals: the variant blocks are
+    sharded over those GPUs -- contiguous block ranges when the source knows its size, round robin for streams -- the
+    state is replicated once by an NCCL broadcast and the results are gathered in the single-GPU order, bit for bit
+    the same rows); ``options`` (kernel-selection knobs of the C ABI, ``glr_options``; default: the library decides).
 
     Output columns: all columns of ``genotype_df`` except the values column and ``genotypes``,
     then ``effect, stderror, tvalue, pvalue, phenotype`` [+ ``n, sum_x, y_transpose_x`` when
@@ -109,10 +114,15 @@ def linear_regression(genotype_df,
     dof = C.shape[0] - C.shape[1] - 1  # lin_reg.py:159
 
     n_geno = len(genotype_sample_ids) if (intersect_samples and genotype_sample_ids) else phenotype_df.shape[0]
-    _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output, gt_indices_to_drop, n_geno, device)
+    placement = _Placement(device=int(device), devices=None if devices is None else [int(d) for d in devices],
+                           options=options)
+    if not spark_input:
+        # (under Spark the driver needs neither the library nor a GPU: every Python worker builds its own replica
+        # lazily in _linear_regression_inner, once per process)
+        _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output, gt_indices_to_drop, n_geno, placement)
 
     return _generate_linreg_output(genotype_df, np_dt, values_column, Y_state, Y_mask, Y_scale, Q, dof, phenotype_df,
-                                   Y_for_verbose_output, verbose_output, gt_indices_to_drop)
+                                   Y_for_verbose_output, verbose_output, gt_indices_to_drop, placement)
 
 
 def _create_YState(Y, phenotype_df, offset_df, Y_mask, dt, contigs) -> Union[YState, Dict[str, YState]]:
@@ -148,24 +158,53 @@ def _keep_index(n_geno: int, gt_indices_to_drop) -> Optional[np.ndarray]:
     return np.flatnonzero(keep).astype(np.int64)
 
 
-def _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output, gt_indices_to_drop, n_geno, device=0):
-    """Builds the device replica of (Q, Y per contig, mask, scale, dof): what the reference ships to
-    every Spark worker by closure capture (lin_reg.py:277-284)."""
+@dataclass
+class _Placement:
+    """Where the block loop runs: one CUDA ordinal, or several (sharded), plus the kernel knobs.  Travels with the
+    closure to the Spark workers (``spark_worker``): there every Python worker drives ONE GPU -- the one Spark's GPU
+    scheduling assigned to the task if any, else ``devices[partition % len(devices)]``, else ``device``."""
+    device: int = 0
+    devices: Optional[List[int]] = None
+    options: Optional[dict] = None
+    spark_worker: bool = False
+
+    def resolve(self) -> List[int]:
+        if not self.spark_worker:
+            return list(self.devices) if self.devices else [self.device]
+        try:
+            from pyspark import TaskContext
+            ctx = TaskContext.get()
+            res = ctx.resources() if ctx is not None else {}
+            if 'gpu' in res and res['gpu'].addresses:
+                return [int(res['gpu'].addresses[0])]
+            if self.devices and ctx is not None:
+                return [self.devices[ctx.partitionId() % len(self.devices)]]
+        except Exception:  # noqa: BLE001
+            pass
+        return [self.devices[0] if self.devices else self.device]
+
+
+def _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output, gt_indices_to_drop, n_geno, placement=None):
+    """Builds the device replica(s) of (Q, Y per contig, mask, scale, dof): what the reference ships to
+    every Spark worker by closure capture (lin_reg.py:277-284).  ONE state holds every contig's Y."""
+    placement = placement or _Placement()
     states = list(Y_state.values()) if isinstance(Y_state, dict) else [Y_state]
     keep = _keep_index(n_geno, gt_indices_to_drop)
     if keep is not None and keep.size != states[0].Y.shape[0]:
         raise ValueError('after dropping the samples absent from phenotype_df the genotype arrays must have one '
                          'entry per phenotype row')
-    engine = DeviceState(Q=np.asarray(Q, dtype=np.float64),
-                         Y=np.stack([np.asarray(s.Y, dtype=np.float64) for s in states]),
-                         Y_mask=np.asarray(Y_mask, dtype=np.float64),
-                         YdotY=np.stack([np.asarray(s.YdotY, dtype=np.float64) for s in states]),
-                         Y_scale=np.asarray(Y_scale, dtype=np.float64),
-                         dof=int(dof),
-                         Y_raw=None if Y_for_verbose_output is None else np.asarray(Y_for_verbose_output, np.float64),
-                         keep_idx=keep,
-                         n_geno_samples=n_geno,
-                         device=device)
+    kw = dict(Q=np.asarray(Q, dtype=np.float64),
+              Y=np.stack([np.asarray(s.Y, dtype=np.float64) for s in states]),
+              Y_mask=np.asarray(Y_mask, dtype=np.float64),
+              YdotY=np.stack([np.asarray(s.YdotY, dtype=np.float64) for s in states]),
+              Y_scale=np.asarray(Y_scale, dtype=np.float64),
+              dof=int(dof),
+              Y_raw=None if Y_for_verbose_output is None else np.asarray(Y_for_verbose_output, np.float64),
+              keep_idx=keep,
+              n_geno_samples=n_geno,
+              options=placement.options)
+    devs = placement.resolve()
+    engine = DeviceGroup(devs, **kw) if len(devs) > 1 else DeviceState(device=devs[0], **kw)
     for i, s in enumerate(states):
         s._engine = engine
         s._contig_index = i
@@ -209,7 +248,8 @@ def _linear_regression_inner(genotype_pdf: pd.DataFrame, Y_state: YState, Y_mask
         n_drop = 0 if gt_indices_to_drop is None else int(np.size(gt_indices_to_drop))
         _attach_engine(Y_state, Y_mask, Y_scale, Q, dof, Y_for_verbose_output if verbose_output else None,
                        gt_indices_to_drop, n_rows + n_drop)
-    res = Y_state._engine.run(block, Y_state._contig_index)
+    engine = Y_state._engine
+    res = (engine.states[0] if isinstance(engine, DeviceGroup) else engine).run(block, Y_state._contig_index)
     rest = genotype_pdf.drop(columns=[_VALUES_COLUMN_NAME])
     out_dt = np.asarray(Y_scale).dtype
     return _assemble(rest, res, phenotype_names, bool(verbose_output), out_dt)
@@ -223,17 +263,41 @@ def _output_columns(input_columns, verbose_output) -> List[str]:
     return cols + ['effect', 'stderror', 'tvalue', 'pvalue', 'phenotype']
 
 
+_WORKER_ENGINES: Dict[str, Any] = {}  # Spark Python worker: token of a linear_regression call -> its device replica
+
+
 def _generate_linreg_output(genotype_df, np_dt, values_column, Y_state, Y_mask, Y_scale, Q, dof, phenotype_df,
-                            Y_for_verbose_output, verbose_output, gt_indices_to_drop):
+                            Y_for_verbose_output, verbose_output, gt_indices_to_drop, placement=None):
     """lin_reg.py:257-284."""
     phenotype_names = phenotype_df.columns.to_series().astype('str')
     args = (Y_mask, Y_scale, Q, dof, phenotype_names, Y_for_verbose_output, verbose_output, gt_indices_to_drop)
 
-    def map_func(pdf_iterator):
-        for pdf in pdf_iterator:
-            yield gwas_fx._loco_dispatch(pdf, Y_state, _linear_regression_inner, *args)
-
     if gwas_fx._is_spark_df(genotype_df):
+        import uuid
+        token = uuid.uuid4().hex
+        pl = placement or _Placement()
+        worker_placement = _Placement(device=pl.device, devices=pl.devices, options=pl.options, spark_worker=True)
+
+        def map_func(pdf_iterator):
+            # one replica per Python worker process and call: ONE state with every contig's Y, on the GPU of this task
+            first = next(iter(Y_state.values())) if isinstance(Y_state, dict) else Y_state
+            if first._engine is None:
+                cached = _WORKER_ENGINES.get(token)
+                if cached is None:
+                    n_rows = first.Y.shape[0]
+                    n_drop = 0 if gt_indices_to_drop is None else int(np.size(gt_indices_to_drop))
+                    cached = _attach_engine(Y_state, Y_mask, Y_scale, Q, dof,
+                                            Y_for_verbose_output if verbose_output else None, gt_indices_to_drop,
+                                            n_rows + n_drop, worker_placement)
+                    while len(_WORKER_ENGINES) >= 2:
+                        _WORKER_ENGINES.pop(next(iter(_WORKER_ENGINES))).close()
+                    _WORKER_ENGINES[token] = cached
+                else:
+                    for i, s in enumerate(Y_state.values() if isinstance(Y_state, dict) else [Y_state]):
+                        s._engine, s._contig_index = cached, i
+            for pdf in pdf_iterator:
+                yield gwas_fx._loco_dispatch(pdf, Y_state, _linear_regression_inner, *args)
+
         return _spark_map(genotype_df, np_dt, values_column, map_func, verbose_output)
 
     from ..sources import GenotypeSource
@@ -243,53 +307,106 @@ def _generate_linreg_output(genotype_df, np_dt, values_column, Y_state, Y_mask, 
         return _run_arrow(genotype_df, values_column, Y_state, phenotype_names, verbose_output, np_dt)
 
     blocks = [genotype_df] if isinstance(genotype_df, pd.DataFrame) else genotype_df
-    prepared = (gwas_fx._prepare_genotype_pdf(pdf, values_column, np_dt) for pdf in blocks)
-    parts = list(map_func(prepared))
+    return _run_frames(blocks, values_column, Y_state, phenotype_names, verbose_output, np_dt)
+
+
+def _engine_of(Y_state):
+    return (next(iter(Y_state.values())) if isinstance(Y_state, dict) else Y_state)._engine
+
+
+def _split_by_contig(meta: pd.DataFrame, block: GenotypeBlock, Y_state):
+    """_loco_dispatch (functions.py:92-101) for a packed block: one sub-block per contig present, contigs in
+    first-appearance order, each with the index of that contig's Y inside the device state."""
+    if not isinstance(Y_state, dict):
+        yield meta, block, 0
+        return
+    contigs = pd.unique(meta['contigName'])
+    if len(contigs) == 1:  # the usual case (variants sorted by chromosome): no gather, the block goes as is
+        yield meta, block, Y_state[contigs[0]]._contig_index
+        return
+    for contig in contigs:
+        sel = (meta['contigName'] == contig).to_numpy()
+        if not isinstance(block, GenotypeBlock):
+            raise ValueError('a resident block may not span several contigs (ResidentSource splits them at load time)')
+        sub = GenotypeBlock(np.ascontiguousarray(block.data[sel]), block.format, block.missing)
+        yield meta[sel], sub, Y_state[contig]._contig_index
+
+
+def _ordered_columns(out: pd.DataFrame, verbose_output) -> pd.DataFrame:
+    """Exact reference column order: pass-through columns, then results (verbose columns last)."""
+    passthrough = [c for c in out.columns if c not in STAT_NAMES + VERBOSE_NAMES + ('phenotype', )]
+    return out[passthrough + list(STAT_NAMES) + ['phenotype'] + (list(VERBOSE_NAMES) if verbose_output else [])]
+
+
+def _run_work(engine, work, n_work_blocks, phenotype_names, verbose_output, np_dt, shard_ranges=None) -> pd.DataFrame:
+    """Runs (meta, block, contig index) items through the device lanes -- the H2D copy of block i+1 overlaps the kernels
+    of block i -- and assembles the result frames in input order.  ``work(first, last)`` yields the items of the source
+    blocks [first, last).  With several GPUs and a known block count every GPU takes a contiguous range of blocks
+    (SURVEY.md section 8e); otherwise the blocks go round robin.  Either way each block is exactly the block one GPU
+    would have run, so the rows are the same bit for bit."""
+    parts = []
+    if isinstance(engine, DeviceGroup) and len(engine) > 1 and n_work_blocks is not None:
+        n_dev = len(engine)
+        metas = [[] for _ in range(n_dev)]
+
+        ranges = shard_ranges(engine.devices) if shard_ranges else [contiguous_blocks(n_work_blocks, d, n_dev) for d in range(n_dev)]
+
+        def feed(d):
+            for meta, block, ci in work(*ranges[d]):
+                metas[d].append(meta)
+                yield block, ci
+
+        done = [[] for _ in range(n_dev)]
+        for d, seq, res in engine.run_shards([feed(d) for d in range(n_dev)]):
+            done[d].append(_assemble(metas[d][seq], res, phenotype_names, verbose_output, np_dt))
+            metas[d][seq] = None
+        for d in range(n_dev):
+            parts += done[d]
+    else:
+        metas = []
+
+        def feed_all():
+            for meta, block, ci in work(0, None):
+                metas.append(meta)
+                yield block, ci
+
+        for res in engine.run_pipelined(feed_all()):
+            parts.append(_assemble(metas.pop(0), res, phenotype_names, verbose_output, np_dt))
     if not parts:
         return pd.DataFrame(columns=_output_columns([], verbose_output))
     out = pd.concat(parts) if len(parts) > 1 else parts[0]
-    # exact reference column order: pass-through columns, then results (verbose columns last)
-    passthrough = [c for c in out.columns if c not in STAT_NAMES + VERBOSE_NAMES + ('phenotype', )]
-    ordered = passthrough + list(STAT_NAMES) + ['phenotype'] + (list(VERBOSE_NAMES) if verbose_output else [])
-    return out[ordered]
+    return _ordered_columns(out, verbose_output)
+
+
+def _run_frames(blocks, values_column, Y_state, phenotype_names, verbose_output, np_dt) -> pd.DataFrame:
+    """pandas blocks (one frame or a stream of frames): what map_func does at lin_reg.py:277-282, pipelined."""
+    n_blocks = len(blocks) if isinstance(blocks, (list, tuple)) else None
+
+    def work(first, last):
+        import itertools
+        for pdf in itertools.islice(iter(blocks), first, last):
+            pdf = gwas_fx._prepare_genotype_pdf(pdf, values_column, np_dt)
+            values = pdf[_VALUES_COLUMN_NAME]
+            head = values.iloc[0] if len(values) else None
+            block = head if isinstance(head, GenotypeBlock) else as_block(values.array if hasattr(values, 'array') else values,
+                                                                          np_dt)
+            yield from _split_by_contig(pdf.drop(columns=[_VALUES_COLUMN_NAME]), block, Y_state)
+
+    return _run_work(_engine_of(Y_state), work, n_blocks, phenotype_names, verbose_output, np_dt)
 
 
 def _run_source(source, Y_state, phenotype_names, verbose_output, np_dt) -> pd.DataFrame:
-    """Packed blocks (e.g. PLINK 2-bit) pipelined through the device lanes: the H2D copy of block
-    i+1 overlaps the kernels of block i; LOCO blocks are split by contig like _loco_dispatch."""
-    is_loco = isinstance(Y_state, dict)
-    engine = (next(iter(Y_state.values())) if is_loco else Y_state)._engine
+    """Packed blocks (e.g. PLINK 2-bit) straight from a GenotypeSource."""
 
-    def work():
-        for meta, block in source.blocks():
-            if is_loco:
-                contigs = pd.unique(meta['contigName'])
-                if len(contigs) == 1:  # the usual case (variants sorted by chromosome): no gather, the block goes as is
-                    yield meta, block, Y_state[contigs[0]]._contig_index
-                    continue
-                for contig in contigs:
-                    sel = (meta['contigName'] == contig).to_numpy()
-                    sub = GenotypeBlock(np.ascontiguousarray(block.data[sel]), block.format, block.missing)
-                    yield meta[sel], sub, Y_state[contig]._contig_index
-            else:
-                yield meta, block, 0
+    def work(first, last):
+        for meta, block in source.blocks(first, last):
+            yield from _split_by_contig(meta, block, Y_state)
 
-    metas = []
-
-    def feed():
-        for meta, block, ci in work():
-            metas.append(meta)
-            yield block, ci
-
-    parts = []
-    for res in engine.run_pipelined(feed()):
-        meta = metas.pop(0)
-        parts.append(_assemble(meta, res, phenotype_names, verbose_output, np_dt))
-    if not parts:
-        return pd.DataFrame(columns=_output_columns([], verbose_output))
-    out = pd.concat(parts)
-    passthrough = [c for c in out.columns if c not in STAT_NAMES + VERBOSE_NAMES + ('phenotype', )]
-    return out[passthrough + list(STAT_NAMES) + ['phenotype'] + (list(VERBOSE_NAMES) if verbose_output else [])]
+    engine = _engine_of(Y_state)
+    ranges = getattr(source, 'shard_ranges', None)
+    if ranges is not None and not isinstance(engine, DeviceGroup):
+        ranges(getattr(engine, 'devices', [engine.device]))  # a resident source must live on the GPU that runs it
+    return _run_work(engine, work, source.n_blocks(), phenotype_names, verbose_output, np_dt, ranges)
 
 
 def _is_arrow_input(obj) -> bool:
@@ -318,7 +435,7 @@ def _run_arrow(data, values_column, Y_state, phenotype_names, verbose_output, np
     if values_column not in schema.names:
         raise ValueError(f'genotype_df has no column named "{values_column}"')
     is_loco = isinstance(Y_state, dict)
-    engine = (next(iter(Y_state.values())) if is_loco else Y_state)._engine
+    engine = _engine_of(Y_state)
     keep_cols = [n for n in schema.names if n not in (values_column, gwas_fx._GENOTYPES_COLUMN_NAME)]
     P = len(phenotype_names)
     names = np.asarray(list(phenotype_names), dtype=object)

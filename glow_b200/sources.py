@@ -12,7 +12,7 @@ from typing import Iterator, Optional, Sequence, Tuple
 import numpy as np
 import pandas as pd
 
-from .engine import GenotypeBlock
+from .engine import GenotypeBlock, ResidentBlock, contiguous_blocks
 
 PLINK_MAGIC = bytes([0x6c, 0x1b, 0x01])  # PlinkFileFormat.scala:159 (variant-major)
 
@@ -20,8 +20,13 @@ PLINK_MAGIC = bytes([0x6c, 0x1b, 0x01])  # PlinkFileFormat.scala:159 (variant-ma
 class GenotypeSource:
     """Iterable of (metadata frame, GenotypeBlock); the metadata columns pass through to the output."""
 
-    def blocks(self) -> Iterator[Tuple[pd.DataFrame, GenotypeBlock]]:
+    def blocks(self, first_block: int = 0, last_block: Optional[int] = None) -> Iterator[Tuple[pd.DataFrame, GenotypeBlock]]:
+        """Blocks [first_block, last_block) in order (all of them by default)."""
         raise NotImplementedError
+
+    def n_blocks(self) -> Optional[int]:
+        """Number of blocks when it is known up front (lets a multi-GPU run shard contiguous ranges), else None."""
+        return None
 
 
 class ArraySource(GenotypeSource):
@@ -37,9 +42,14 @@ class ArraySource(GenotypeSource):
         self.meta = meta if meta is not None else pd.DataFrame(index=pd.RangeIndex(data.shape[0]))
         self.block_variants = int(block_variants)
 
-    def blocks(self):
+    def n_blocks(self):
+        return -(-self.data.shape[0] // self.block_variants)
+
+    def blocks(self, first_block=0, last_block=None):
         G = self.data.shape[0]
-        for g0 in range(0, G, self.block_variants):
+        last_block = self.n_blocks() if last_block is None else last_block
+        for k in range(first_block, last_block):
+            g0 = k * self.block_variants
             g1 = min(G, g0 + self.block_variants)
             yield self.meta.iloc[g0:g1], GenotypeBlock(np.ascontiguousarray(self.data[g0:g1]), self.format,
                                                        self.missing)
@@ -102,42 +112,51 @@ class PlinkBedSource(GenotypeSource):
             'alternateAllele': bim['alternate'],
         })
 
-    _ring_cache = {}  # (block_variants, row_bytes, n_buffers) -> pinned buffers: page-locking 1 GB costs ~0.4 s
+    def n_blocks(self):
+        return -(-self.packed.shape[0] // self.block_variants)
 
     def _staging_ring(self, n_buffers: int):
-        """Pinned staging buffers, kept for the next call with the same geometry (plain numpy arrays when no CUDA runtime
-        is present, e.g. in CPU-only tests)."""
+        """Pinned staging buffers of THIS source, kept for its next pass (page-locking 1 GB costs ~0.4 s); plain numpy
+        arrays when no CUDA runtime is present (CPU-only tests).  Returns (buffers, pinned?)."""
         shape = (self.block_variants, self.row_bytes)
-        key = shape + (n_buffers, )
-        ring = PlinkBedSource._ring_cache.get(key)
-        if ring is None:
-            try:
-                from . import _capi
-                ring = [_capi.pinned_empty(shape, np.uint8) for _ in range(n_buffers)]
-            except Exception:  # noqa: BLE001 -- no library / no device: the data path still works, just unpinned
-                ring = [np.empty(shape, dtype=np.uint8) for _ in range(n_buffers)]
-            PlinkBedSource._ring_cache.clear()  # one geometry at a time: the buffers are large
-            PlinkBedSource._ring_cache[key] = ring
-        return ring
+        free = self.__dict__.setdefault('_rings', [])
+        for i, (key, ring, pinned) in enumerate(free):
+            if key == shape + (n_buffers, ):
+                free.pop(i)
+                return ring, pinned
+        try:
+            from . import _capi
+            return [_capi.pinned_empty(shape, np.uint8) for _ in range(n_buffers)], True
+        except Exception:  # noqa: BLE001 -- no library / no device: the data path still works, just unpinned
+            return [np.empty(shape, dtype=np.uint8) for _ in range(n_buffers)], False
 
-    def blocks(self):
+    def _release_ring(self, n_buffers, ring, pinned):
+        self.__dict__.setdefault('_rings', []).append(((self.block_variants, self.row_bytes, n_buffers), ring, pinned))
+
+    def blocks(self, first_block=0, last_block=None, ring_depth: int = 3):
+        """``ring_depth``: staging buffers of a streamed file = blocks the consumer may hold at once + 1 (n_lanes + 1)."""
         G = self.packed.shape[0]
+        last_block = self.n_blocks() if last_block is None else last_block
         if self._path is None or G == 0:
-            for g0 in range(0, G, self.block_variants):
+            for k in range(first_block, last_block):
+                g0 = k * self.block_variants
                 g1 = min(G, g0 + self.block_variants)
                 yield self.meta.iloc[g0:g1], GenotypeBlock(np.ascontiguousarray(self.packed[g0:g1]), 'plink2',
                                                            self.missing)
             return
-        # streamed from the file: block k lands in staging buffer k % 3; the consumer (engine.run_pipelined, two
-        # lanes) has finished with block k - 3 before it asks for block k, so the buffer is free again
+        # streamed from the file: block k lands in staging buffer k % depth; the consumer (run_pipelined / run_shards with
+        # depth - 1 lanes) has finished with block k - depth before it asks for block k, so the buffer is free again.
+        # Every live iterator has its own ring (two shards of one file can be streamed at the same time).
         from concurrent.futures import ThreadPoolExecutor
-        ring = self._staging_ring(3)
+        depth = max(2, int(ring_depth))
+        ring, pinned = self._staging_ring(depth)
         fd = os.open(self._path, os.O_RDONLY)
         try:
             with ThreadPoolExecutor(self.read_threads) as pool:
-                for k, g0 in enumerate(range(0, G, self.block_variants)):
+                for i, k in enumerate(range(first_block, last_block)):
+                    g0 = k * self.block_variants
                     g1 = min(G, g0 + self.block_variants)
-                    buf = ring[k % 3][:g1 - g0]
+                    buf = ring[i % depth][:g1 - g0]
                     flat = buf.reshape(-1)
                     nbytes = flat.size
                     base = 3 + g0 * self.row_bytes
@@ -153,6 +172,80 @@ class PlinkBedSource(GenotypeSource):
                             done += got
 
                     list(pool.map(read, range(self.read_threads)))
-                    yield self.meta.iloc[g0:g1], GenotypeBlock(buf, 'plink2', self.missing)
+                    yield self.meta.iloc[g0:g1], GenotypeBlock(buf, 'plink2', self.missing, pinned=pinned)
         finally:
             os.close(fd)
+            self._release_ring(depth, ring, pinned)
+
+
+class ResidentSource(GenotypeSource):
+    """Genotype blocks loaded ONCE into HBM and kept there: every later ``linear_regression(resident, ...)`` call (another
+    phenotype set, another covariate model) reads them at HBM speed instead of paying the PCIe copy of the packed
+    matrix again.  With several devices the source's blocks are placed in contiguous ranges -- the placement the sharded
+    run uses when called with the same device list (``linear_regression(..., devices=...)``).  Blocks that span several
+    contigs are split at load time so that LOCO runs need no gather.  The blocks are uploaded as they are read: nothing
+    but one block at a time is held on the host."""
+
+    def __init__(self, source: GenotypeSource, devices: Sequence[int] = (0, )):
+        import ctypes as C
+        from . import _capi
+        self._lib = _capi.load()
+        self.devices = [int(d) for d in devices]
+        n_src = source.n_blocks()
+        if n_src is None:
+            raise ValueError('ResidentSource needs a source that knows its number of blocks')
+        n_dev = len(self.devices)
+        bounds = [contiguous_blocks(n_src, d, n_dev) for d in range(n_dev)]
+        self._items, self._allocs, self._ranges = [], [], []
+        self.bytes_resident = 0
+        k = 0
+        src_iter = iter(source.blocks())
+        for d, (a, b) in enumerate(bounds):
+            first = len(self._items)
+            dev = self.devices[d]
+            while k < b:
+                meta, block = next(src_iter)
+                k += 1
+                if 'contigName' in meta.columns and meta['contigName'].nunique() > 1:
+                    subs = []
+                    for contig in pd.unique(meta['contigName']):
+                        sel = (meta['contigName'] == contig).to_numpy()
+                        subs.append((meta[sel], np.ascontiguousarray(block.data[sel])))
+                else:
+                    subs = [(meta, np.ascontiguousarray(block.data))]
+                for sub_meta, data in subs:
+                    p = C.c_void_p()
+                    _capi.check(self._lib.glr_device_alloc(dev, data.nbytes, C.byref(p)))
+                    self._allocs.append((dev, p.value))
+                    if data.nbytes:
+                        _capi.check(self._lib.glr_device_upload(dev, p, data.ctypes.data, data.nbytes))
+                    self.bytes_resident += data.nbytes
+                    self._items.append((sub_meta, ResidentBlock(p.value or 0, data.strides[0] if data.shape[0] else 0,
+                                                                int(data.shape[0]), block.format, block.missing, dev)))
+            self._ranges.append((first, len(self._items)))
+
+    def n_blocks(self):
+        return len(self._items)
+
+    def shard_ranges(self, devices: Sequence[int]):
+        """Item ranges per device of a sharded run; it must use the devices the blocks were placed on."""
+        if [int(d) for d in devices] != self.devices:
+            raise ValueError(f'the blocks are resident on GPUs {self.devices}, the run was asked for GPUs {list(devices)}')
+        return list(self._ranges)
+
+    def blocks(self, first_block=0, last_block=None):
+        last_block = len(self._items) if last_block is None else last_block
+        for k in range(first_block, last_block):
+            yield self._items[k]
+
+    def close(self):
+        for dev, addr in getattr(self, '_allocs', []):
+            try:
+                self._lib.glr_device_free(dev, addr)
+            except Exception:  # noqa: BLE001
+                pass
+        self._allocs = []
+        self._items = []
+
+    def __del__(self):
+        self.close()

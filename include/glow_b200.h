@@ -175,6 +175,18 @@ int glr_state_destroy(glr_state* st);
  * fully observed, the masked pass is skipped). */
 int glr_state_unique_masks(glr_state* st);
 
+/* Multi-GPU inside one process.  The reference parallelises over Spark partitions of variant rows
+ * and ships the state to every worker by closure capture (lin_reg.py:277-284); here variants shard across the devices
+ * of the communicator and the state is replicated ONCE: glr_comm_broadcast_state builds it on devices[0] and sends every
+ * packed array to the other devices in one grouped ncclBroadcast (NCCL loaded at run time; cudaMemcpyPeerAsync when it
+ * is absent -- glr_comm_transport says which).  out_states[i] lives on devices[i]; each is driven and destroyed like a
+ * state from glr_state_create.  There is no collective in the block loop. */
+int glr_comm_init(const int32_t* devices, int32_t n_devices, glr_comm** out);
+int glr_comm_destroy(glr_comm* comm);
+int glr_comm_size(glr_comm* comm);
+const char* glr_comm_transport(glr_comm* comm); /* "nccl" | "p2p" */
+int glr_comm_broadcast_state(glr_comm* comm, const glr_state_desc* desc, glr_state** out_states /* [n_devices] */);
+
 /* Replaces one call of _linear_regression_inner (lin_reg.py:203-254).  Synchronous:
  * submit on lane 0 + wait. */
 int glr_run_block(glr_state* st, const glr_block_desc* blk, const glr_block_out* out);
@@ -191,6 +203,14 @@ int glr_lane_stream(glr_state* st, int lane, void** stream);
 /* Pinned host memory for block staging. */
 int glr_host_alloc(size_t bytes, void** ptr);
 int glr_host_free(void* ptr);
+
+/* Device memory for genotype blocks that stay RESIDENT in HBM across calls (one shard of the genotype matrix is loaded
+ * once -- 15.6 GB per GPU for the UK-Biobank shape on 8 GPUs -- and many phenotype sets are then regressed against it
+ * with glr_block_desc.memspace = GLR_MEM_DEVICE, so that the steady state is not bound by the PCIe copy of 125 kB per
+ * variant).  glr_device_upload is synchronous. */
+int glr_device_alloc(int device, size_t bytes, void** ptr);
+int glr_device_free(int device, void* ptr);
+int glr_device_upload(int device, void* dst, const void* src_host, size_t bytes);
 
 /* Standalone A6: p = 2 * t.sf(|t|, dof) (lin_reg.py:245) for n device-computed values; host in/out.
  * Exposed so the special-function kernel can be tested against scipy/mpmath directly. */
