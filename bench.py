@@ -5,8 +5,9 @@ variant x phenotype tests/sec, device-timed).
 Workload (config.workload): BASELINE.json configs[2], the configuration the metric is quoted on --
 UK-Biobank shape, N = 500 000 samples, 16 covariates + intercept (K = 17), P = 1 phenotype,
 PLINK 2-bit packed genotypes (125 000 B per variant, 1 % missing calls, mean-imputed inside the
-decode).  One step = one batch of G_step variants per GPU (4.7 GB packed at the default 37 888);
-variants are independent, so N GPUs each take their own batch (weak scaling, no data-path
+decode).  One batch = 37 888 variants per GPU (4.7 GB packed, far beyond L2); one STEP = `--batches-per-step`
+batches back to back (default 16: 20 steps are a 0.9 s timed region, long enough for the board to settle at its
+power-capped clock).  Variants are independent, so N GPUs each take their own batches (weak scaling, no data-path
 collective; the state is replicated with one NCCL broadcast before the timed region).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -15,9 +16,17 @@ collective; the state is replicated with one NCCL broadcast before the timed reg
            the kernels are launched on, max over ranks.
 `e2e`    : tests/s through the C-ABI block call with PINNED HOST buffers -- H2D copy of the packed
            batch and D2H copy of the four result arrays inside the timed region, sub-blocks
-           pipelined over the library's lanes.
-`roofline`: the DMMA contraction kernel against the FP64 tensor peak measured in this run with a
-           cuBLAS DGEMM (MEASURED_PEAKS.json has no fp64 entry; HBM peak is taken from it).
+           pipelined over the library's lanes (`--e2e-batches-per-step` batches per step).  `e2e.h2d_ceiling`
+           is what bare cudaMemcpyAsync copies of the same buffers reach on this box at this GPU count: the
+           number the e2e path is bounded by.
+`e2e_resident`: the same call with the batch already resident in HBM (glow_b200.ResidentSource) and
+           the results copied to pinned host memory: the steady state of many phenotype sets against one
+           loaded genotype shard.
+`e2e_api`: the public API on a .bed FILE in tmpfs: glow_b200.gwas.linear_regression(PlinkBedSource(path)).
+`roofline`: the dominant kernel (split8_kernel, int8 tensor cores) against the tcgen05.mma issue rate measured in
+           this run; `traffic` comes from the committed ncu capture named in `traffic_source`.
+`configs`: device-timed tests/s and the dominant kernel's roofline fraction for the other BASELINE.json configs
+           (N = 1 only).
 `cpu_baseline` / --impl reference: the oracle port of the reference's _linear_regression_inner
            (numpy + BLAS on all host cores) on a bounded sample of the same workload.
 """
@@ -44,8 +53,12 @@ SEED = 20261019
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batches-per-step', type=int, default=16)
+    ap.add_argument('--e2e-batches-per-step', type=int, default=4)
+    ap.add_argument('--skip-configs', action='store_true', help='do not measure the other BASELINE configs')
+    ap.add_argument('--skip-e2e-api', action='store_true')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--variants-per-step', type=int, default=148 * 256)
     ap.add_argument('--samples', type=int, default=N_SAMPLES)
@@ -237,7 +250,7 @@ def run_reference_impl(args):
         'vs_baseline': None,
         'dtype': 'f64',
         'data': 'synthetic',
-        'config': workload_config(args, bv),
+        'config': dict(workload_config(args, bv), batches_per_step=1, variants_per_step_per_gpu=bv),
         'cpu_baseline': {
             'value': value,
             'unit': 'tests/s',
@@ -253,18 +266,175 @@ def run_reference_impl(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, variants_per_step):
+def workload_config(args, variants_per_batch):
     return {
         'workload': 'BASELINE.json configs[2]: UK-Biobank shape, PLINK 2-bit genotypes, variant-sharded',
         'n_samples': args.samples,
         'n_covariates': N_COV,
         'n_phenotypes': N_PHENO,
-        'variants_per_step_per_gpu': variants_per_step,
+        'variants_per_batch_per_gpu': variants_per_batch,
+        'batches_per_step': args.batches_per_step,
+        'variants_per_step_per_gpu': variants_per_batch * args.batches_per_step,
         'missing_call_rate': MISSING_RATE,
         'imputation': 'mean_substitute fused into the decode',
-        'cache': 'inputs larger than L2 (packed batch >> 126 MB); no L2 flush',
+        'cache': 'inputs larger than L2 (packed batch 4.7 GB >> 126 MB); no L2 flush',
         'parallelism': f'variant-sharded x{args.gpus}, state replicated by one NCCL broadcast'
     }
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernels from the committed ncu --set full captures (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+# --------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (device-timed, N = 1): tests/s + roofline fraction of the dominant kernel
+# --------------------------------------------------------------------------------------------------
+def _prep_state(rg, N, K_cov, P, missing=0.0, n_contigs=1):
+    C = np.hstack([np.ones((N, 1)), rg.standard_normal((N, K_cov))])
+    Q = np.linalg.qr(C)[0]
+    Y = rg.standard_normal((N, P))
+    mask = np.ones((N, P))
+    if missing:
+        mask = (rg.random((N, P), dtype=np.float32) >= missing).astype(np.float64)
+        Y *= mask
+    Y -= Y.mean(axis=0)
+    Y = (Y - Q @ (Q.T @ Y)) * mask
+    scale = np.sqrt(np.sum(Y**2, axis=0) / (mask.sum(axis=0) - Q.shape[1]))
+    Y /= scale[None, :]
+    Ys, ydys = [], []
+    for _ in range(n_contigs):
+        Yc = Y if n_contigs == 1 else (Y - 0.1 * rg.standard_normal((N, P))) * mask
+        Ys.append(Yc)
+        ydys.append(np.sum(Yc * Yc, axis=0))
+    return Q, np.stack(Ys), mask, np.stack(ydys), scale, N - C.shape[1] - 1
+
+
+def run_config(torch, dev, name, label, N, K_cov, P, G, fmt, hbm_peak, i8_peak, missing=0.0, n_contigs=1, call_missing=MISSING_RATE,
+               min_seconds=0.3):
+    from glow_b200 import _capi
+    from glow_b200.engine import DeviceState
+    rg = np.random.default_rng(11)
+    Q, Y, mask, ydy, scale, dof = _prep_state(rg, N, K_cov, P, missing, n_contigs)
+    st = DeviceState(Q=Q, Y=Y, Y_mask=mask, YdotY=ydy, Y_scale=scale, dof=dof, device=dev.index)
+    del Y, mask
+    if fmt == 'plink2':
+        global MISSING_RATE
+        keep, MISSING_RATE = MISSING_RATE, call_missing
+        X = gen_packed_device(torch, G, N, 5, dev)
+        MISSING_RATE = keep
+        stride = X.shape[1]
+    else:
+        X = torch.empty((G, N), dtype=torch.float64, device=dev)
+        for g0 in range(0, G, 4096):
+            g1 = min(G, g0 + 4096)
+            f = torch.rand((g1 - g0, 1), device=dev) * 0.49 + 0.01
+            u = torch.rand((g1 - g0, N), device=dev)
+            X[g0:g1] = (u > (1 - f)**2).double() + (u > (1 - f)**2 + 2 * f * (1 - f)).double() + 0.1 * torch.rand(
+                (g1 - g0, N), device=dev).double()
+        stride = N * 8
+    outs = {k: torch.empty((P, G), dtype=torch.float64, device=dev) for k in ('effect', 'stderror', 'tvalue', 'pvalue')}
+    addrs = {k: v.data_ptr() for k, v in outs.items()}
+    torch.cuda.synchronize()
+    for _ in range(3):
+        st.run_device(fmt, X.data_ptr(), stride, G, addrs, contig=0, missing='mean')
+    acc, reps, t0 = {}, 0, time.perf_counter()
+    while reps < 3 or time.perf_counter() - t0 < min_seconds:
+        st.run_device(fmt, X.data_ptr(), stride, G, addrs, contig=0, missing='mean')
+        t = st.timing(0)
+        for k, v in t.items():
+            acc[k] = acc.get(k, 0.0) + v
+        path = t['path']
+        reps += 1
+    for k in acc:
+        acc[k] /= reps
+    K = K_cov + 1
+    U = st.unique_masks
+    cols = (K - 1) + P
+    line = dict(config=label, N=N, K=K, P=P, variants_per_block=G, format=fmt, unique_masks=U, missing_call_rate=call_missing if fmt == 'plink2' else 0.0,
+                tests_per_s=P * G / (acc['total_ms'] / 1e3), block_ms=acc['total_ms'], blocks_timed=reps,
+                stage_ms={k: round(acc[k], 4) for k in ('prepass_ms', 'gram_ms', 'masked_ms', 'epilogue_ms')}, path_flags=int(path),
+                finite=float(torch.isfinite(outs['pvalue']).double().mean().item()))
+    gram_s = acc['gram_ms'] / 1e3
+    if path & _capi.PATH_SPLIT8:
+        operands = 1 if path & _capi.PATH_OPTIMISTIC else 2
+        ops = 2.0 * N * (7 * cols) * operands * G
+        line['roofline'] = dict(kernel='split8_kernel' + (' (optimistic form: no missing-call operand)' if operands == 1 else ''),
+                                bound='tensor', achieved=ops / gram_s / 1e12, peak=i8_peak, unit='TFLOP/s',
+                                frac=ops / gram_s / 1e12 / i8_peak if i8_peak == i8_peak else None,
+                                op_type='int8 tensor-core operations, algorithmic digit rows', share_of_block=acc['gram_ms'] / acc['total_ms'],
+                                fp64_equivalent_tflops=2.0 * N * cols * G / gram_s / 1e12)
+        if U and acc['masked_ms'] > 0:
+            line['masked_pass'] = dict(ms=acc['masked_ms'], form='int8' if path & _capi.PATH_MASK_INT8 else
+                                       ('sparse' if path & _capi.PATH_MASK_SPARSE else 'dmma'))
+    else:
+        nbytes = float(G) * stride + 4 * 8 * P * G
+        line['roofline'] = dict(kernel='gram_kernel (FP64 DMMA, dosage rows streamed once)', bound='hbm', achieved=nbytes / gram_s / 1e9,
+                                peak=hbm_peak, unit='GB/s', frac=nbytes / gram_s / 1e9 / hbm_peak, share_of_block=acc['gram_ms'] / acc['total_ms'],
+                                executed_tflops=2.0 * N * (K - 1 + P) * G / gram_s / 1e12)
+    st.close()
+    del X, outs
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_other_configs(torch, dev, hbm_peak, i8_peak):
+    out = []
+    cfgs = [
+        ('cfg1', 'BASELINE.json configs[1]: dense fp64 dosages 10k samples x 100k variants x 10 phenotypes x 10 covariates',
+         dict(N=10_000, K_cov=10, P=10, G=100_000, fmt='f64')),
+        ('cfg3', 'BASELINE.json configs[3]: 50k samples x 2 000 phenotypes, 10 % missing each (2 000 distinct masks), 2-bit; one block of 8 192 variants',
+         dict(N=50_000, K_cov=10, P=2_000, G=8_192, fmt='plink2', missing=0.1)),
+        ('cfg4', 'BASELINE.json configs[4]: 200k samples x 20 phenotypes, LOCO offsets (2 of the 22 contig states built), 2-bit',
+         dict(N=200_000, K_cov=16, P=20, G=37_888, fmt='plink2', n_contigs=2)),
+        ('cfg2_fully_called', 'configs[2] shape with fully called genotypes (imputed hard calls): the optimistic form without the missing-call operand',
+         dict(N=500_000, K_cov=16, P=1, G=37_888, fmt='plink2', call_missing=0.0)),
+        ('cfg2_missing_phenotype', 'configs[2] shape with 2 % of the phenotype values unobserved (masked second pass)',
+         dict(N=500_000, K_cov=16, P=1, G=37_888, fmt='plink2', missing=0.02)),
+        ('cfg2_spark_batch', 'configs[2] shape in blocks of 10 000 variants (Spark default Arrow batch, lin_reg.py:277-282): sample range split across CTAs',
+         dict(N=500_000, K_cov=16, P=1, G=10_000, fmt='plink2')),
+    ]
+    for name, label, kw in cfgs:
+        try:
+            out.append(run_config(torch, dev, name, label, hbm_peak=hbm_peak, i8_peak=i8_peak, **kw))
+        except Exception as exc:  # noqa: BLE001
+            out.append(dict(config=label, error=f'{type(exc).__name__}: {exc}'))
+    return out
+
+
+def run_e2e_api(torch, dev, n_variants=16_384, block_variants=8_192):
+    """Public API on a .bed FILE in tmpfs: everything a user waits for (file -> pinned staging -> H2D -> kernels -> D2H ->
+    pandas frame), state creation included."""
+    import pandas as pd
+    import glow_b200
+    N = N_SAMPLES
+    packed = gen_packed_device(torch, n_variants, N, 5, dev).cpu().numpy()
+    path = '/dev/shm/glow_b200_stream.bed' if os.path.isdir('/dev/shm') else '/tmp/glow_b200_stream.bed'
+    with open(path, 'wb') as f:
+        f.write(bytes([0x6c, 0x1b, 0x01]))
+        f.write(packed.tobytes())
+    del packed
+    rg = np.random.default_rng(3)
+    cov = pd.DataFrame(rg.standard_normal((N, N_COV)))
+    phe = pd.DataFrame(rg.standard_normal((N, 1)), columns=['trait'])
+    meta = pd.DataFrame({'idx': np.arange(n_variants)})
+    times = []
+    try:
+        src = glow_b200.PlinkBedSource(path, N, meta, block_variants=block_variants)
+        for _ in range(3):
+            t0 = time.perf_counter()
+            out = glow_b200.gwas.linear_regression(src, phe, cov, device=dev.index)
+            times.append(time.perf_counter() - t0)
+    finally:
+        os.unlink(path)
+    best = min(times[1:])
+    return {'value': n_variants / best, 'unit': 'tests/s', 'seconds': times, 'n_variants': n_variants,
+            'file_gb_per_s': n_variants * ((N + 3) // 4) / best / 1e9, 'rows': int(len(out)),
+            'call': 'glow_b200.gwas.linear_regression(PlinkBedSource(<.bed in tmpfs>), phenotype_df, covariate_df): includes the '
+                    'host-side state preparation (QR of 500k x 17), state packing, the file read and the pandas result frame'}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -277,7 +447,7 @@ def main():
     import torch
     import torch.distributed as dist
     from glow_b200 import _capi
-    from glow_b200.engine import DeviceState, GenotypeBlock
+    from glow_b200.engine import DeviceState, GenotypeBlock, ResidentBlock
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -293,6 +463,7 @@ def main():
 
     n, K, P = args.samples, N_COV + 1, N_PHENO
     G = args.variants_per_step
+    B = max(1, args.batches_per_step)
 
     # ---- state: rank 0 prepares it on the host, ONE NCCL broadcast replicates it ----
     from glow_b200 import dist as gdist
@@ -317,16 +488,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(st, sample_clocks):
-        """W warm-up steps, then K timed steps on the lane stream of `st` (CUDA events, max over ranks)."""
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(st, sample_clocks, batches):
+        """W warm-up steps, then K timed steps of `batches` batches each on the lane stream of `st` (CUDA events around the
+        whole timed region, max over ranks)."""
         lane_stream = torch.cuda.ExternalStream(st.lane_stream(0), device=dev)
 
         def step_device():
-            st.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=False)
+            for _ in range(batches):
+                st.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=True)
 
         for _ in range(args.warmup):
             step_device()
-            st.wait_device(0)
         barrier()
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
@@ -336,36 +514,31 @@ def main():
         launches = 0
         ev0.record(lane_stream)
         for _ in range(args.steps):
-            step_device()
-            st.wait_device(0)
-            t = st.timing(0)
-            for k in stage:
-                stage[k] += t[k]
-            launches += t['kernel_launches']
+            for _ in range(batches):
+                st.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=True)
+                t = st.timing(0)
+                for k in stage:
+                    stage[k] += t[k]
+                launches += t['kernel_launches']
         ev1.record(lane_stream)
         barrier()
         clocks = sampler.stop() if sampler else None
-        ms_total = ev0.elapsed_time(ev1)
-        t_max = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-        ms_step = float(t_max.item()) / args.steps
+        ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
         for k in stage:
-            stage[k] /= args.steps
-        return ms_step, stage, launches, clocks
+            stage[k] /= args.steps * batches   # per batch
+        return ms_step, stage, launches, clocks, st.timing(0)['path']
 
     # primary arm: the library's default path (2-bit genotypes -> exact int8 digit-split GEMM on tcgen05)
-    ms_step, stage, launches, clocks = measure(state, True)
-    value = world * G * P / (ms_step / 1e3)
+    ms_step, stage, launches, clocks, path = measure(state, True, B)
+    value = world * G * B * P / (ms_step / 1e3)
     t_primary = outs['tvalue'].clone()
 
-    # secondary arm in the same run: the FP64 tensor-core (DMMA) path forced for the same batch
+    # secondary arm in the same run: the FP64 tensor-core (DMMA) path forced for the same batch (2 batches per step)
     ms_dmma, stage_dmma, paths_agree = None, None, None
     if not args.skip_dmma_arm:
-        os.environ['GLR_SPLIT8'] = '0'
-        state_dmma = gdist.device_state_from_flat(flat, header, local_rank, n_lanes=1)
-        os.environ.pop('GLR_SPLIT8', None)
-        ms_dmma, stage_dmma, _, _ = measure(state_dmma, False)
+        from glow_b200.dist import state_layout
+        state_dmma = gdist.device_state_from_flat(flat, header, local_rank, n_lanes=1, options={'split8': 'off'})
+        ms_dmma, stage_dmma, _, _, _ = measure(state_dmma, False, 1)
         paths_agree = bool(torch.allclose(outs['tvalue'], t_primary, rtol=1e-9, atol=1e-12, equal_nan=True))
         state_dmma.close()
         state.run_device('plink2', packed.data_ptr(), row_bytes, G, out_addrs, missing='mean', lane=0, wait=True)
@@ -375,62 +548,99 @@ def main():
     frac_finite = float(torch.isfinite(pv).double().mean().item())
 
     # ---- e2e: pinned host buffers through the C-ABI block call, lanes pipelined ----
-    e2e = None
+    e2e, e2e_res = None, None
+    names = ('effect', 'stderror', 'tvalue', 'pvalue')
     if not args.skip_e2e:
+        Be = max(1, args.e2e_batches_per_step)
         nsub = max(1, args.e2e_subblocks)
         gs = G // nsub
         host_packed = torch.empty((G, row_bytes), dtype=torch.uint8, pin_memory=True)
         host_packed.copy_(packed)
         hp = host_packed.numpy()
-        names = ('effect', 'stderror', 'tvalue', 'pvalue')
         host_out = [{k: torch.empty((P, gs), dtype=torch.float64, pin_memory=True).numpy() for k in names}
                     for _ in range(nsub)]
         torch.cuda.synchronize()
 
         def step_e2e():
             inflight = []
-            for i in range(nsub):
-                lane = i % state.n_lanes
-                if len(inflight) == state.n_lanes:
-                    state.wait(inflight.pop(0))
-                state.submit(lane, GenotypeBlock(hp[i * gs:(i + 1) * gs], 'plink2', 'mean'), 0, out=host_out[i])
-                inflight.append(lane)
+            for _ in range(Be):
+                for i in range(nsub):
+                    lane = i % state.n_lanes
+                    if len(inflight) == state.n_lanes:
+                        state.wait(inflight.pop(0))
+                    state.submit(lane, GenotypeBlock(hp[i * gs:(i + 1) * gs], 'plink2', 'mean', pinned=True), 0, out=host_out[i])
+                    inflight.append(lane)
             while inflight:
                 state.wait(inflight.pop(0))
 
         for _ in range(max(1, args.warmup - 1)):
             step_e2e()
         barrier()
-        e2e_launches = 0
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step_e2e()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e_val = world * gs * nsub * P * args.steps / float(t_e.item())
-        # the device-resident and host paths must agree bit for bit
-        # the host path (smaller sub-blocks, split reduction order) must agree with the resident path
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e_val = world * gs * nsub * Be * P * args.steps / dt
+        # the host path (smaller sub-blocks) must agree with the resident path
         same = bool(np.allclose(host_out[0]['tvalue'], outs['tvalue'][:, :gs].cpu().numpy(), rtol=1e-9, atol=1e-12,
                                 equal_nan=True))
+        # what the platform gives: the same pinned sub-blocks copied with bare cudaMemcpyAsync on two streams, all ranks at once
+        barrier()
+        scratch = torch.empty((2, gs, row_bytes), dtype=torch.uint8, device=dev)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        reps = max(2, min(args.steps, 6)) * Be
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for i in range(nsub):
+                with torch.cuda.stream(streams[i % 2]):
+                    scratch[i % 2].copy_(host_packed[i * gs:(i + 1) * gs], non_blocking=True)
+        torch.cuda.synchronize()
+        dt_c = max_over_ranks(time.perf_counter() - t0)
+        ceiling_gbs = world * reps * gs * nsub * row_bytes / dt_c / 1e9
+        del scratch
+        h2d = int(gs * nsub * row_bytes) * Be
         e2e = {
             'value': e2e_val,
             'unit': 'tests/s',
-            'h2d_bytes_per_step': int(gs * nsub * row_bytes),
-            'd2h_bytes_per_step': int(4 * 8 * P * gs * nsub),
+            'h2d_bytes_per_step': h2d,
+            'd2h_bytes_per_step': int(4 * 8 * P * gs * nsub) * Be,
+            'batches_per_step': Be,
+            'seconds_timed': dt,
             'subblocks': nsub,
             'lanes': state.n_lanes,
             'timer': 'host wall clock around submit..wait of every sub-block (copies inside), max over ranks',
-            'matches_device_path': same
+            'matches_device_path': same,
+            'h2d_gbs': world * h2d * args.steps / dt / 1e9,
+            'h2d_ceiling': {'gbs': ceiling_gbs, 'frac': (world * h2d * args.steps / dt / 1e9) / ceiling_gbs,
+                            'how': 'bare cudaMemcpyAsync of the same pinned sub-blocks on two streams, every rank at once, no kernels'},
+            'note': 'bound by the host-to-device copy of 125 kB per test: compare h2d_gbs with h2d_ceiling.gbs (whole job)'
         }
+        # resident genotypes: the batch stays in HBM (glow_b200.ResidentSource), only the results cross PCIe
+        rblk = ResidentBlock(packed.data_ptr(), row_bytes, G, 'plink2', 'mean', local_rank)
+        pin_out = {k: torch.empty((P, G), dtype=torch.float64, pin_memory=True).numpy() for k in names}
+        for _ in range(2):
+            state.submit(0, rblk, 0, out=pin_out)
+            state.wait(0)
+        barrier()
+        t0 = time.perf_counter()
+        nres = args.steps * Be
+        for _ in range(nres):
+            state.submit(0, rblk, 0, out=pin_out)
+            state.wait(0)
+        dt_r = max_over_ranks(time.perf_counter() - t0)
+        e2e_res = {'value': world * G * P * nres / dt_r, 'unit': 'tests/s', 'h2d_bytes_per_step': 0,
+                   'd2h_bytes_per_step': int(4 * 8 * P * G) * Be, 'seconds_timed': dt_r,
+                   'note': 'genotype shard loaded into HBM once (glow_b200.ResidentSource), every later phenotype set runs against '
+                           'it: C-ABI call with a device-resident block, results copied to pinned host memory inside the timed region'}
         del host_packed
 
     # ---- rooflines ----
     roof = None
     dmma = None
     cpu = None
+    configs = None
+    e2e_api = None
     if rank == 0:
         peaks = {}
         try:
@@ -439,6 +649,7 @@ def main():
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         hbm_src = 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+        traffic = load_traffic()
 
         def best_of(fn, n=7, skip=2):
             best = 1e9
@@ -460,8 +671,6 @@ def main():
             b = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
             fp64_peak = 2 * 8192**3 / (best_of(lambda: torch.matmul(a, b)) / 1e3) / 1e12
             del a, b
-            # INT8 tensor peak: cuBLASLt int8 GEMM 8192^3 through torch._int_mm; if that is not available the
-            # rate of back-to-back tcgen05.mma kind::i8 (benchmarks/micro/umma_i8_rate.cu, 4.28 Pop/s) is used
             try:
                 a8 = torch.randint(-127, 127, (8192, 8192), dtype=torch.int8, device=dev)
                 b8 = torch.randint(-127, 127, (8192, 8192), dtype=torch.int8, device=dev)
@@ -469,20 +678,19 @@ def main():
                 int8_src = 'cuBLASLt int8 GEMM 8192^3 via torch._int_mm, best of 5, measured in this run'
                 del a8, b8
             except Exception as exc:  # noqa: BLE001
-                int8_peak = 4280.0
-                int8_src = f'tcgen05.mma kind::i8 issue-rate microbenchmark (torch._int_mm unavailable: {type(exc).__name__})'
+                int8_src = f'torch._int_mm unavailable: {type(exc).__name__}'
         # what the int8 tensor pipe does on this box right now: back-to-back tcgen05.mma with resident operands on every
         # SM, ~6 ms (long enough for the clocks to settle), through the library's own probe
         issue_rate, issue_src = 4340.0, 'benchmarks/micro/umma_i8_ts.cu (0.6 ms burst, measured earlier on this pool)'
         if not args.skip_peak:
             try:
                 import ctypes as C
-                from glow_b200 import _capi
                 r = C.c_double()
                 _capi.check(_capi.load().glr_tensor_i8_issue_rate(local_rank, 6.0, C.byref(r)))
                 issue_rate, issue_src = float(r.value), 'glr_tensor_i8_issue_rate: 6 ms of back-to-back tcgen05.mma kind::i8, measured in this run'
             except Exception as exc:  # noqa: BLE001
                 issue_src += f' (live probe failed: {type(exc).__name__})'
+        bf16 = peaks.get('bf16_tflops')
         # Executed formulation: S = [Q(:,1:) | Ytilde]^T X.  The intercept column of Q is constant, so its product
         # with x is q0 * sum(x) and comes from the genotype counts: its flops are NOT executed and not counted.
         cols = (K - 1) + P
@@ -495,6 +703,7 @@ def main():
         nc_rows = -(-(7 * -(-cols // n_cb) + 1) // 16) * 16       # digit rows per block incl. the row of ones = MMA N
         ops_int8_issued = 2.0 * (-(-n // 128) * 128) * nc_rows * n_cb * 2 * (-(-G // 128) * 128)
         achieved = ops_int8 / gram_s / 1e12
+        default_shape = n == N_SAMPLES and G == 148 * 256
         roof = {
             'kernel': 'split8_kernel (tcgen05.mma.cta_group::2 kind::i8 on CTA pairs, A = decoded genotypes of 2 x 128 '
                       'variants in TMEM, B = digit rows split over the pair\'s shared memory, M256 N128 K32, accumulators in '
@@ -504,26 +713,30 @@ def main():
             'achieved': achieved,
             'peak': issue_rate,
             'unit': 'TFLOP/s',
-            'op_type': 'int8 tensor-core operations (2 per multiply-accumulate), algorithmic = digit rows actually needed',
+            'op_type': 'int8 tensor-core operations (2 per multiply-accumulate), algorithmic = digit rows actually needed; half of '
+                       'them multiply the missing-call indicator (1 % dense): see configs.cfg2_fully_called for the form without it',
             'frac': achieved / issue_rate,
-            # dram bytes of one launch at the default shape, ncu --set full, profiles/r01_split8_full.txt
-            'traffic': 4.876e9 if (n == N_SAMPLES and G == 148 * 256) else None,
+            'traffic': traffic.get('split8_kernel', {}).get('dram_bytes_per_launch') if default_shape else None,
+            'traffic_source': traffic.get('split8_kernel', {}).get('source', 'no capture committed') +
+                              ' (ncu --set full capture of one launch at this shape: a constant of the build, not measured in this run)',
             'peak_source': issue_src,
-            # back-to-back tcgen05.mma kind::i8 from one thread per SM, operands resident: 64 clk per M128 N128 K32; a
-            # library GEMM and this kernel both run below it
-            'library_int8_gemm_tops': int8_peak,
-            'library_int8_gemm_source': int8_src,
-            'frac_of_library_int8_gemm': achieved / int8_peak,
+            'peak_alternatives': {
+                'library_int8_gemm_tops': int8_peak,
+                'library_int8_gemm_source': int8_src,
+                'frac_of_library_int8_gemm': achieved / int8_peak,
+                'twice_MEASURED_PEAKS_bf16_burst_tops': 2 * bf16 if bf16 else None,
+                'frac_of_twice_bf16_burst': achieved / (2 * bf16) if bf16 else None,
+            },
             'note': 'peak = the int8 tensor pipe fed back to back with constant resident operands on every SM (it holds '
-                    '~1.9 GHz); a library int8 GEMM on random data (as MEASURED_PEAKS.json measures bf16: 1625 TFLOP/s burst, '
-                    'i.e. 3250 TOP/s for int8 on the same pipe) runs BELOW this kernel: under a real load the board sits at '
-                    'its power cap and the SM clock drops (ncu: 1.59 GHz with the tensor pipe 97.5 % active for this kernel)',
+                    '~1.9 GHz); MEASURED_PEAKS.json has no int8 entry -- 2 x its bf16 burst figure is given beside it. Under a real '
+                    'load the board sits at its power cap and the SM clock drops (see clocks)',
             'ops_per_launch_algorithmic': ops_int8,
             'issued_tops_incl_padding': ops_int8_issued / gram_s / 1e12,
             'fp64_equivalent_tflops': flops_f64_equiv / gram_s / 1e12,
             'reference_equivalent_tflops': flops_ref / gram_s / 1e12,
             'algorithmic_bytes_per_launch': float(G) * row_bytes + 7.0 * n * cols,
             'avg_launch_ms': stage['gram_ms'],
+            'launches_timed': args.steps * B,
             'share_of_step': stage['gram_ms'] / max(stage['total_ms'], 1e-9),
             'stages': {
                 'genotype_read_inside_kernel': {
@@ -544,11 +757,10 @@ def main():
         dmma_cols = (cols // 8) * 8 if 1 <= cols % 8 <= 3 and cols // 8 >= 1 else ((cols + 7) // 8) * 8
         d_s = stage_dmma['gram_ms'] / 1e3 if stage_dmma else float('nan')
         dmma = None if stage_dmma is None else {
-            'note': 'same batch through the FP64 tensor-core path (GLR_SPLIT8=0): what float / dosage input, verbose '
-                    'states and small blocks use',
+            'note': 'same batch through the FP64 tensor-core path (options split8=off): what float / dosage input uses',
             'value': world * G * P / (ms_dmma / 1e3),
             'unit': 'tests/s',
-            'ms_per_step': ms_dmma,
+            'ms_per_batch': ms_dmma,
             'stage_ms': stage_dmma,
             'agrees_with_primary_path_rel_1e-9': paths_agree,
             'roofline': {
@@ -559,8 +771,8 @@ def main():
                 'peak': fp64_peak,
                 'unit': 'TFLOP/s',
                 'frac': flops_f64_equiv / d_s / 1e12 / fp64_peak,
-                # dram bytes of one launch at the default shape, ncu --set full, profiles/r01_gram_full.txt
-                'traffic': 4.818e9 if (n == N_SAMPLES and G == 148 * 256) else None,
+                'traffic': traffic.get('gram_kernel_plink2', {}).get('dram_bytes_per_launch') if default_shape else None,
+                'traffic_source': traffic.get('gram_kernel_plink2', {}).get('source', 'no capture committed'),
                 'algorithmic_bytes_per_launch': float(G) * row_bytes + 8.0 * n * cols,
                 'peak_source': 'cuBLAS DGEMM 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json has no fp64 entry)',
                 'issued_tflops_incl_padding': 2.0 * n * max(dmma_cols, cols) * G / d_s / 1e12,
@@ -588,6 +800,19 @@ def main():
                           'decode + mean substitution not timed',
                 'block_seconds': times
             }
+    # the other configs and the public-API run use the whole GPU: only at N = 1, after the main measurement
+    if world == 1:
+        del packed, outs
+        state.close()
+        del flat
+        torch.cuda.empty_cache()
+        if not args.skip_configs:
+            configs = run_other_configs(torch, dev, hbm_peak, issue_rate)
+        if not args.skip_e2e_api:
+            try:
+                e2e_api = run_e2e_api(torch, dev)
+            except Exception as exc:  # noqa: BLE001
+                e2e_api = {'error': f'{type(exc).__name__}: {exc}'}
 
     if rank == 0:
         line = {
@@ -598,6 +823,8 @@ def main():
             'steps': args.steps,
             'warmup': args.warmup,
             'ms_per_step': ms_step,
+            'ms_per_batch': ms_step / B,
+            'seconds_timed': ms_step * args.steps / 1e3,
             'higher_is_better': True,
             'scaling': 'weak',
             'vs_baseline': None,
@@ -609,11 +836,15 @@ def main():
             'config': workload_config(args, G),
             'clocks': clocks,
             'e2e': e2e,
+            'e2e_resident': e2e_res,
+            'e2e_api': e2e_api,
             'gpu_launches': launches,
+            'path_flags': int(path),
             'roofline': roof,
             'dmma_f64_path': dmma,
+            'configs': configs,
             'cpu_baseline': cpu,
-            'stage_ms': stage,
+            'stage_ms_per_batch': stage,
             'finite_fraction': frac_finite
         }
         print(json.dumps(line), flush=True)

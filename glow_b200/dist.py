@@ -89,7 +89,8 @@ def broadcast_state(state: Optional[dict], src: int = 0, device=None):
     return flat, header
 
 
-def device_state_from_flat(flat, header, device_index: int, n_lanes: int = 2, keep_idx=None, n_geno_samples=None):
+def device_state_from_flat(flat, header, device_index: int, n_lanes: int = 2, keep_idx=None, n_geno_samples=None,
+                           options=None):
     """Builds this rank's DeviceState straight from the broadcast buffer (CUDA tensor)."""
     from . import _capi
     from .engine import DeviceState
@@ -100,4 +101,4 @@ def device_state_from_flat(flat, header, device_index: int, n_lanes: int = 2, ke
     return DeviceState(Q=addr('Q'), Y=addr('Y'), Y_mask=addr('Y_mask'), YdotY=addr('YdotY'), Y_scale=addr('Y_scale'),
                        Y_raw=addr('Y_raw') if verbose else None, dof=dof, keep_idx=keep_idx,
                        n_geno_samples=n_geno_samples, device=device_index, n_lanes=n_lanes,
-                       memspace=_capi.MEM_DEVICE, dims=(N, K, P, C))
+                       memspace=_capi.MEM_DEVICE, dims=(N, K, P, C), options=options)

@@ -186,7 +186,9 @@ class ResidentSource(GenotypeSource):
     contigs are split at load time so that LOCO runs need no gather.  The blocks are uploaded as they are read: nothing
     but one block at a time is held on the host."""
 
-    def __init__(self, source: GenotypeSource, devices: Sequence[int] = (0, )):
+    def __init__(self, source: GenotypeSource, devices: Sequence[int] = (0, ), split_contigs: bool = True):
+        """``split_contigs=False`` keeps the source's blocks whole (rows then come out in exactly the source's block
+        order; only for runs without LOCO offsets)."""
         import ctypes as C
         from . import _capi
         self._lib = _capi.load()
@@ -206,7 +208,7 @@ class ResidentSource(GenotypeSource):
             while k < b:
                 meta, block = next(src_iter)
                 k += 1
-                if 'contigName' in meta.columns and meta['contigName'].nunique() > 1:
+                if split_contigs and 'contigName' in meta.columns and meta['contigName'].nunique() > 1:
                     subs = []
                     for contig in pd.unique(meta['contigName']):
                         sel = (meta['contigName'] == contig).to_numpy()

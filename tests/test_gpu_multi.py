@@ -86,7 +86,8 @@ def test_sharded_result_is_bit_identical_to_single_gpu(rg, loco, tmp_path):
     many_f = glow_b200.gwas.linear_regression(iter(frames), phe, cov, offs, devices=list(range(n)))
     _frames_identical(one_f, many_f)
     # (c) resident genotypes: loaded once into the HBM of the GPUs, then run against two phenotype sets
-    res = glow_b200.ResidentSource(glow_b200.PlinkBedSource(str(path), N, meta, block_variants=128), devices=list(range(n)))
+    res = glow_b200.ResidentSource(glow_b200.PlinkBedSource(str(path), N, meta, block_variants=128), devices=list(range(n)),
+                                   split_contigs=loco)
     many_r = glow_b200.gwas.linear_regression(res, phe, cov, offs, devices=list(range(n)))
     _frames_identical(one, many_r)
     phe2 = phe * 2.0 + 1.0
