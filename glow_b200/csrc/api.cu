@@ -755,7 +755,7 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   gp.s_slab = Mpad * ldS;
   gp.mom_part = (float_fmt && n_split > 1) ? L.mom_part.as<double>() : L.mom.as<double>();
   if (use_split8) {
-    Split8Params sp;
+    Split8Params sp{};
     sp.x = x;
     sp.w8 = st->w8 + (int64_t)b->contig * st->s8_contig_bytes;
     sp.scale = st->s8_scale + (int64_t)b->contig * st->s8_cols;
@@ -819,7 +819,7 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
     n_parts = std::max(1, std::min(n_parts, 64));
     if (n_parts > 1)
       if (int rc = L.d_part.ensure((size_t)n_parts * U * ldS * 8)) return rc;
-    SparseMaskedParams sp;
+    SparseMaskedParams sp{};
     sp.x = x;
     sp.A = L.s_red.as<double>();
     sp.ldS = ldS;

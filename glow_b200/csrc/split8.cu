@@ -682,14 +682,21 @@ Split8Plan split8_plan(int n_variants, int n_cb, int64_t n_stages, int sm_count,
     double best_cost = 1e300;
     for (int ns = 1; ns <= max_split; ++ns) {
       if (force_split > 0 && ns != std::min(force_split, max_split)) continue;
-      const int per = (int)round_up(ceil_div(n_stages, ns), 2);
-      const int eff = (int)std::max<int64_t>(1, n_stages / per);  // ranges in use (the last one takes the remainder)
-      const int64_t longest = n_stages - (int64_t)(eff - 1) * per;
-      const double waves = (double)ceil_div((int64_t)items * eff, units);
-      const double cost = waves * (double)(longest + kOverhead);
+      // ns ranges of `per` stages (even), the last one shorter: n_stages - (ns - 1) per >= 2
+      const int per = ns == 1 ? (int)n_stages : (int)round_up(ceil_div(n_stages, ns), 2);
+      if (ns > 1 && (int64_t)(ns - 1) * per + 2 > n_stages) {
+        if (force_split > 0) {  // forced but not feasible: fall back to the unsplit form
+          ns_out = 1;
+          per_out = (int)n_stages;
+          best_cost = (double)ceil_div((int64_t)items, units) * (double)(n_stages + kOverhead);
+        }
+        continue;
+      }
+      const double waves = (double)ceil_div((int64_t)items * ns, units);
+      const double cost = waves * (double)(per + kOverhead);
       if (cost < best_cost * (ns > 1 ? 0.98 : 1.0)) {  // prefer fewer ranges unless clearly better
         best_cost = cost;
-        ns_out = eff;
+        ns_out = ns;
         per_out = per;
       }
       if (items >= 8 * units && force_split <= 0) break;  // many items per unit: the tail is negligible

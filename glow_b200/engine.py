@@ -236,7 +236,7 @@ class DeviceState:
         st = self._stage.setdefault(lane, {})
         buf = st.get(key)
         if buf is None or buf.size < nbytes:
-            st[key] = buf = _capi.pinned_empty((max(nbytes + nbytes // 4, 4096), ), np.uint8)
+            st[key] = buf = _capi.pinned_empty((-(-max(nbytes + nbytes // 4, 4096) // 64) * 64, ), np.uint8)
         return buf
 
     def submit(self, lane: int, block: GenotypeBlock, contig: int = 0, out: Optional[Dict[str, np.ndarray]] = None,
@@ -256,7 +256,7 @@ class DeviceState:
         staged_out = out is None
         if staged_out:
             n = self.P * G
-            flat = self._pinned(lane, 'out', 8 * n * len(names)).view(np.float64)
+            flat = self._pinned(lane, 'out', 8 * n * len(names))[:8 * n * len(names)].view(np.float64)
             out = {k: flat[i * n:(i + 1) * n].reshape(self.P, G) for i, k in enumerate(names)}
         if resident:
             bd = self._block_desc(fmt, block.addr if G else None, block.stride, G, contig, block.missing, _capi.MEM_DEVICE)
