@@ -435,7 +435,7 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   // integer tensor-core operand (split8.cu): any number of columns (blocks of up to 18)
   double* d_colmax = nullptr;
   const int split8_mode = tri_knob(d->opt.split8, "GLR_SPLIT8");
-  if (split8_mode != GLR_OFF && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 128) {
+  if (split8_mode != GLR_OFF && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 3 * 128) {  // >= 4 stages: one per issuer warp
     st->s8_cols = st->Mcols;
     split8_geometry(st->s8_cols, &st->s8_ncb, &st->s8_cpb, &st->s8_NC);
     st->s8_stages = ceil_div(Ng, 128);

@@ -37,12 +37,15 @@
 // the L2 and shared-memory traffic.  The leader (rank 0) issues the MMAs; the barriers it waits on collect arrivals from
 // both CTAs (remote mbarrier arrives), and tcgen05.commit multicasts the completions to both.
 //
-// CTA roles (384 threads, 1 CTA/SM, persistent over (128-variant tile, column block) work items):
-//   warp 0    : lane 0 streams the packed digit operand (pre-swizzled image, one bulk copy per stage)
-//   warps 1, 3: issue tcgen05.mma for alternate stages (converged warps, one elected lane); one tcgen05.commit per
-//               stage frees the stage's buffers, a second one after the last stage publishes the accumulators
-//               (in the non-leader CTA of a pair they forward "my half of the digit stage has landed" instead)
-//   warp 2    : TMEM allocation / deallocation
+// CTA roles (416 threads, 1 CTA/SM, persistent over (128-variant tile, column block[, sample range]) work items):
+//   warps 0-3 : issue tcgen05.mma, stage g by warp g % 4 (converged warps, one elected lane); one tcgen05.commit per
+//               stage frees the stage's buffers, a second one after the warp's last stage of the item publishes the
+//               accumulators (in the non-leader CTA of a pair they forward "my half of the digit stage has landed"
+//               instead).  One iteration of an issuer (three barrier waits, fence, election, 4-8 MMAs, commit) has a
+//               latency of several hundred cycles: two issuers sustained one stage per ~470 cycles, enough for the full
+//               form (512 cycles of MMAs per stage) but not for the optimistic one (256)
+//   warp 12   : TMEM allocation / deallocation; lane 0 streams the packed digit operand (pre-swizzled image, one bulk
+//               copy per stage)
 //   warps 4-11: decode.  Warp w owns TMEM lanes 32 (w % 4) ..; warps 4-7 take the even stages, warps
 //               8-11 the odd ones; a thread turns 32 bytes of its variant's row (128 samples) into 32 + 32
 //               TMEM words per stage.  All 8 warps run the epilogue (tcgen05.ld of the variant's digit
@@ -62,11 +65,21 @@ constexpr int kS8TileV = 128;  // variants per tile = TMEM lanes
 constexpr int kS8Digits = 7;
 constexpr int kS8DecodeWarps = 8;
 constexpr int kS8FirstDecodeWarp = 4;
-constexpr int kS8Issuers = 2;
-constexpr int kS8Threads = (kS8FirstDecodeWarp + kS8DecodeWarps) * 32;
+#ifndef GLR_S8_ISSUERS
+#define GLR_S8_ISSUERS 4
+#endif
+constexpr int kS8Issuers = GLR_S8_ISSUERS;  // warps 0-3 (or 0-1): stage g is issued by warp g % kS8Issuers
+constexpr int kS8ProducerWarp = kS8FirstDecodeWarp + kS8DecodeWarps;  // warp 12: digit-operand producer, TMEM allocation
+constexpr int kS8Threads = (kS8ProducerWarp + 1) * 32;
 constexpr int kS8Words = 8;  // 32-bit words (16 samples each) per decode thread per stage
 constexpr int kS8WRing = 8;  // digit-operand stages in shared memory (also the depth of the completion barriers)
-constexpr int kS8ARing = 4;  // genotype-operand stages in TMEM: 4 x (32 + 32) columns
+constexpr int kS8WRingMax = 16;  // CTA pairs in the optimistic form: a stage takes half as long, so twice as many digit stages
+                                 // (8 KB each) must be in flight to cover the L2 latency of the bulk copies
+constexpr int kS8ARing = 4;  // genotype-operand stages in TMEM: 4 x (32 + 32) columns (full form)
+constexpr int kS8ARingNoE = 8;  // optimistic form (no indicator operand): 8 x 32 columns -- its MMAs take half as long, and
+                                // with 4 slots the round trip MMA done -> TMEM store -> arrive -> issue bounded the kernel
+                                // (ncu: tensor pipe 52 %, decode warps stalled on the slot barrier)
+constexpr int kS8ARingMax = 8;
 constexpr uint32_t kS8ColDe = 128, kS8ColA = 256;
 
 __device__ __forceinline__ uint64_t s8_desc(uint32_t saddr) {
@@ -84,6 +97,13 @@ __device__ __forceinline__ void s8_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
       "}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// byte permute with the table in both source registers.  (__byte_perm masks the selector with 0x7777 first; the selectors
+// here are already masked, and the extra LOP3 per permute was a fifth of the decode's instructions.)
+__device__ __forceinline__ uint32_t s8_prmt(uint32_t table, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %1, %2;\n" : "=r"(r) : "r"(table), "r"(sel));
+  return r;
 }
 __device__ __forceinline__ uint32_t s8_and(uint32_t a, uint32_t m) {
   uint32_t r;
@@ -174,13 +194,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 
 struct Split8Smem {
-  uint64_t full_w[kS8WRing];  // bulk copy of a digit stage has landed
-  uint64_t done[kS8WRing];    // the MMAs of a stage have completed (stage g -> barrier g % 8, parity (g / 8) & 1)
-  uint64_t full_a[kS8ARing];  // the 4 decode warps of a stage have written its genotype operand
+  uint64_t full_w[kS8WRingMax];  // bulk copy of a digit stage has landed
+  uint64_t done[kS8WRingMax];    // the MMAs of a stage have completed (stage g -> barrier g % 8, parity (g / 8) & 1)
+  uint64_t full_a[kS8ARingMax];  // the 4 decode warps of a stage have written its genotype operand
   uint64_t tmem_full;
   uint64_t tmem_empty;
   uint64_t tile_started;
-  uint64_t peer_w[kS8WRing];  // pair mode, leader: the peer CTA's half of a digit stage has landed
+  uint64_t peer_w[kS8WRingMax];  // pair mode, leader: the peer CTA's half of a digit stage has landed
   uint32_t tmem_base;
   uint32_t pad;
   int32_t n00[2][kS8TileV];  // per stage-parity group: homozygous-alternate (code 00) count per variant
@@ -199,7 +219,7 @@ __device__ __forceinline__ void s8_item(int item, int n_tiles, int n_cb, int& ti
 }
 
 // Sample-range split (small blocks: fewer (tile, column block) items than SMs).  Item = (tile, column block, z); split z
-// covers the stages [z per, (z + 1) per), the last one up to n_stages (per is even and every range has >= 2 stages, so both
+// covers the stages [z per, (z + 1) per), the last one up to n_stages (per is even and every range has >= 4 stages, so all
 // MMA issuers and both decode groups take part in every item).  The partial digit sums are int32: they are added into a
 // zeroed workspace with integer atomics (exact, any order gives the same bits) and split8_finalize_kernel recombines.
 __device__ __forceinline__ void s8_item_split(int item, int n_tiles, int n_cb, int n_split, int per, int n_st, int& tile, int& cb,
@@ -217,20 +237,23 @@ __device__ __forceinline__ void s8_item_split(int item, int n_tiles, int n_cb, i
 #ifdef GLR_S8_PROFILE
 __device__ long long g_s8_prof[160][3][8];  // [cta][issuer 0 / issuer 1 / decode warp 4][phase] clock64 sums
 #define S8_T(var) const long long var = clock64()
-#define S8_ACC(role, slot, t1, t0) g_s8_prof[blockIdx.x][role][slot] += (t1) - (t0)
+#define S8_ACC(role, slot, t1, t0) g_s8_prof[blockIdx.x][(role) > 2 ? 1 : (role)][slot] += (t1) - (t0)
 #else
 #define S8_T(var)
 #define S8_ACC(role, slot, t1, t0)
 #endif
 
-// kAligned: every row starts on a 4-byte boundary (base and stride multiples of 4): no funnel shifts.
+// kAlign: 8 = every row starts on an 8-byte boundary (base and stride multiples of 8): the 32 bytes of a stage are four 64-bit
+// loads -- the row segments of a warp's 32 variants are 32 different cache lines, so every load instruction costs the L1 data
+// pipe a dozen wavefronts, and with 32-bit loads that pipe was 85 % busy (ncu, round 1), co-limiting the kernel;
+// 4 = 4-byte boundary: eight 32-bit loads; 0 = any alignment: nine 32-bit loads and funnel shifts.
 // kPair: CTA pairs (cluster of 2, cta_group::2): a pair works on 256 variants and shares one copy of every digit
 // stage (each CTA loads and holds half of the rows), which halves the shared-memory and L2 traffic of the digit stream.
 // Only the leader (rank 0) issues MMAs; barriers the leader waits on collect arrivals from both CTAs, and the MMA
 // completion is multicast to both.
 // kNoE: "optimistic" form for blocks expected to have no missing call: no indicator operand, no De MMAs (half the tensor
 // work).  The decode still checks every code; a missing call raises *p.flags and the host re-runs the block in the full form.
-template <bool kAligned, bool kPair, bool kNoE>
+template <int kAlign, bool kPair, bool kNoE>
 __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NC = p.NC;
@@ -238,22 +261,25 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
   const uint32_t w_stage_bytes = (uint32_t)NC * kS8K;                   // a whole digit stage in the packed image
   const uint32_t w_bytes = kPair ? w_stage_bytes / 2 : w_stage_bytes;   // what this CTA holds of it
   unsigned char* w_ring = smem_raw;  // 1024-byte aligned operand buffers first, bookkeeping after
-  Split8Smem* sm = reinterpret_cast<Split8Smem*>(w_ring + (size_t)kS8WRing * w_bytes);
+  constexpr int kWR = (kNoE && kPair) ? kS8WRingMax : kS8WRing, kWRLog = (kNoE && kPair) ? 4 : 3;
+  Split8Smem* sm = reinterpret_cast<Split8Smem*>(w_ring + (size_t)kWR * w_bytes);
 
+  // genotype-operand ring in TMEM: depth, log2(depth), columns per slot
+  constexpr int kAR = kNoE ? kS8ARingNoE : kS8ARing, kARLog = kNoE ? 3 : 2, kASlot = kNoE ? 32 : 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < kS8WRing; ++s) {
+    for (int s = 0; s < kS8WRingMax; ++s) {
       mbar_init(&sm->full_w[s], 1);
       mbar_init(&sm->done[s], 1);
     }
-    for (int s = 0; s < kS8WRing; ++s) mbar_init(&sm->peer_w[s], 1);
-    for (int s = 0; s < kS8ARing; ++s) mbar_init(&sm->full_a[s], (kPair ? 2 : 1) * kS8DecodeWarps / 2);
+    for (int s = 0; s < kS8WRingMax; ++s) mbar_init(&sm->peer_w[s], 1);
+    for (int s = 0; s < kS8ARingMax; ++s) mbar_init(&sm->full_a[s], (kPair ? 2 : 1) * kS8DecodeWarps / 2);
     mbar_init(&sm->tmem_full, kS8Issuers);  // every MMA issuer thread commits its last stage of the item
     mbar_init(&sm->tmem_empty, (kPair ? 2 : 1) * kS8DecodeWarps);
     mbar_init(&sm->tile_started, 1);
     mbar_fence_init();
   }
-  if (warp == 2) {
+  if (warp == kS8ProducerWarp) {
     if (kPair) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sm->tmem_base)),
                    "n"(512));
@@ -280,7 +306,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
 
   // Every role walks the same sequence of stages; g = running ("global") stage index of this CTA.  Ring slots and
   // barrier parities are functions of g (power-of-two depths: masks and shifts only).
-  if (warp == 0) {
+  if (warp == kS8ProducerWarp) {
     // ---- digit-operand producer ----
     if (lane == 0) {
       uint32_t g = 0;
@@ -290,38 +316,38 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         // pair: rows [rank NC/2, ..)
         const int8_t* src = p.w8 + ((int64_t)cb * n_st_all + kbeg) * w_stage_bytes + rank * w_bytes;
         for (int64_t k = 0; k < kcnt; ++k, ++g) {
-          const uint32_t s = g & (kS8WRing - 1);
-          if (g >= (uint32_t)kS8WRing) mbar_wait_backoff(&sm->done[s], ((g >> 3) & 1u) ^ 1u);  // stage g - 8 consumed
+          const uint32_t s = g & (kWR - 1);
+          if (g >= (uint32_t)kWR) mbar_wait_backoff(&sm->done[s], ((g >> kWRLog) & 1u) ^ 1u);  // stage g - ring depth consumed
           mbar_expect_tx(&sm->full_w[s], w_bytes);
           bulk_g2s(w_ring + (size_t)s * w_bytes, src + k * w_stage_bytes, w_bytes, &sm->full_w[s]);
         }
       }
     }
-  } else if (warp == 1 || warp == 3) {
-    // ---- MMA issuers: two warps take alternate stages, so that one is issuing while the other is
-    // committing / waiting for the next stage's operands.  Integer accumulation is order independent; the only
+  } else if (warp < kS8Issuers) {
+    // ---- MMA issuers: four warps take the stages round robin, so that one is issuing while the others are
+    // committing / waiting for their next stage's operands.  Integer accumulation is order independent; the only
     // ordering needed is that the stage that OVERWRITES the accumulators (first stage of an item) is issued
     // before the other thread's first stage of that item. ----
     // The whole warp runs the loop CONVERGED (warp-uniform indices, addresses and barrier polls live in uniform
     // registers); only the tcgen05 instructions themselves are issued by one elected lane.
     if (kPair && rank != 0) {
       // peer CTA of a pair: no MMAs to issue; these two warps forward "my half of digit stage g has landed" to the leader
-      const uint32_t j = __shfl_sync(0xffffffffu, warp, 0) == 1 ? 0u : 1u;
+      const uint32_t j = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);
       uint32_t g0 = 0;
       for (int item = first_item; item < n_items; item += item_stride) {
         int tile_, cb_, kbeg_, n_st32;
         s8_item_split(item, n_tiles, p.n_cb, n_split, per, n_st_all, tile_, cb_, kbeg_, n_st32);
-        for (int k = (int)((j ^ g0) & 1u); k < n_st32; k += kS8Issuers) {
+        for (int k = (int)((j - g0) & (uint32_t)(kS8Issuers - 1)); k < n_st32; k += kS8Issuers) {
           const uint32_t g = g0 + (uint32_t)k;
-          const uint32_t sw = g & (kS8WRing - 1);
-          mbar_wait(&sm->full_w[sw], (g >> 3) & 1u);
+          const uint32_t sw = g & (kWR - 1);
+          mbar_wait(&sm->full_w[sw], (g >> kWRLog) & 1u);
           if (lane == 0) s8_arrive_cta(&sm->peer_w[sw], 0);
           __syncwarp();
         }
         g0 += (uint32_t)n_st32;
       }
     } else {
-      const uint32_t j = __shfl_sync(0xffffffffu, warp, 0) == 1 ? 0u : 1u;
+      const uint32_t j = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);
       // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
       const uint32_t idesc =
           (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)((kPair ? 2 : 1) * kS8TileV >> 4) << 24);
@@ -332,7 +358,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       for (int item = first_item; item < n_items; item += item_stride, ++icount) {
         int tile_, cb_, kbeg_, n_st32;
         s8_item_split(item, n_tiles, p.n_cb, n_split, per, n_st_all, tile_, cb_, kbeg_, n_st32);
-        for (int k = (int)((j ^ g0) & 1u); k < n_st32; k += kS8Issuers) {
+        for (int k = (int)((j - g0) & (uint32_t)(kS8Issuers - 1)); k < n_st32; k += kS8Issuers) {
           const uint32_t g = g0 + (uint32_t)k;
           S8_T(t0);
           if (k == 0) {
@@ -344,18 +370,18 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           } else if (k < kS8Issuers) {
             mbar_wait(&sm->tile_started, (uint32_t)(icount & 1));  // stage 0 (overwrite) has been issued
           }
-          const uint32_t sw = g & (kS8WRing - 1), sa = g & (kS8ARing - 1);
+          const uint32_t sw = g & (kWR - 1), sa = g & (kAR - 1);
           S8_T(t1);
-          mbar_wait(&sm->full_w[sw], (g >> 3) & 1u);
-          if (kPair) s8_wait_cluster(&sm->peer_w[sw], (g >> 3) & 1u);
+          mbar_wait(&sm->full_w[sw], (g >> kWRLog) & 1u);
+          if (kPair) s8_wait_cluster(&sm->peer_w[sw], (g >> kWRLog) & 1u);
           S8_T(t2);
-          if (kPair) s8_wait_cluster(&sm->full_a[sa], (g >> 2) & 1u);
-          else mbar_wait(&sm->full_a[sa], (g >> 2) & 1u);
+          if (kPair) s8_wait_cluster(&sm->full_a[sa], (g >> kARLog) & 1u);
+          else mbar_wait(&sm->full_a[sa], (g >> kARLog) & 1u);
           S8_T(t3);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           // descriptor of the stage's digit rows: only the start-address field changes (units of 16 bytes)
           const uint64_t db0 = s8_desc(w_ring_addr + sw * w_bytes);
-          const uint32_t a_x = tmem + kS8ColA + sa * 64, a_e = a_x + 32;
+          const uint32_t a_x = tmem + kS8ColA + sa * kASlot, a_e = a_x + 32;
           if (s8_elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < kS8K / 32; ++kk) {
@@ -423,12 +449,24 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         const int64_t b0 = k * 32;
         if (b0 + 4 * kS8Words + 3 <= full_bytes) {  // every word touched lies inside the whole bytes of the row
           const uint8_t* q8 = row + b0;
-          const uint32_t a = kAligned ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(q8) & 3);
-          const uint32_t* qw = reinterpret_cast<const uint32_t*>(q8 - a);
+          if (kAlign == 8) {
+            const uint2* q2 = reinterpret_cast<const uint2*>(q8);
 #pragma unroll
-          for (int i = 0; i < kS8Words; ++i) nxt[i] = __ldg(qw + i);
-          nxt[kS8Words] = a ? __ldg(qw + kS8Words) : 0u;
-          sh_nxt = a * 8;
+            for (int i = 0; i < kS8Words / 2; ++i) {
+              const uint2 t = __ldg(q2 + i);
+              nxt[2 * i] = t.x;
+              nxt[2 * i + 1] = t.y;
+            }
+            nxt[kS8Words] = 0u;
+            sh_nxt = 0;
+          } else {
+            const uint32_t a = kAlign ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(q8) & 3);
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(q8 - a);
+#pragma unroll
+            for (int i = 0; i < kS8Words; ++i) nxt[i] = __ldg(qw + i);
+            nxt[kS8Words] = a ? __ldg(qw + kS8Words) : 0u;
+            sh_nxt = a * 8;
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < kS8Words; ++i) {
@@ -464,7 +502,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         S8_T(d0);
         uint32_t w[kS8Words];
 #pragma unroll
-        for (int i = 0; i < kS8Words; ++i) w[i] = kAligned ? nxt[i] : __funnelshift_r(nxt[i], nxt[i + 1], sh_nxt);
+        for (int i = 0; i < kS8Words; ++i) w[i] = kAlign ? nxt[i] : __funnelshift_r(nxt[i], nxt[i + 1], sh_nxt);
         if (k + 2 < kcnt) load(ka + 2);
         if ((ka & 3) == 0 && (ka + 16) * 32 < row_bytes)
           asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (ka + 16) * 32));
@@ -475,7 +513,8 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         for (int i = 0; i < kS8Words; ++i) {
           const uint32_t ww = w[i];
           n00 += __popc(~(ww | (ww << 1)) & 0xAAAAAAAAu);  // both bits of a code clear (left shift: FMA pipe, not ALU)
-          if (kNoE) miss_seen |= ww & ~(ww >> 1) & 0x55555555u;  // code 01: the optimistic form does not apply to this block
+          // code 01 (low bit set, high bit clear) at the even bit positions; the odd ones are masked once, at the end
+          if (kNoE) miss_seen |= ww & ~(ww >> 1);
           // PRMT selectors: nibble n of `ev` = code 2n (bit 2 is a stray bit of the neighbouring code: the table
           // is passed in both source registers, so it does not matter; bit 3 must be clear), of `od` = code 2n+1.
           // Sample order inside a 16-sample group is therefore 0,2,4,6 | 8,10,12,14 | 1,3,5,7 | 9,11,13,15;
@@ -484,29 +523,29 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           const uint32_t ev = s8_and(ww, 0x77777777u), od = s8_and(ww >> 2, 0x77777777u);
           const uint32_t ev_hi = ev >> 16, od_hi = od >> 16;
           // code 00 -> 2, 01 -> 0 (missing), 10 -> 1, 11 -> 0;  e: code 01 -> 1
-          xs[4 * i + 0] = __byte_perm(0x00010002u, 0x00010002u, ev);
-          xs[4 * i + 1] = __byte_perm(0x00010002u, 0x00010002u, ev_hi);
-          xs[4 * i + 2] = __byte_perm(0x00010002u, 0x00010002u, od);
-          xs[4 * i + 3] = __byte_perm(0x00010002u, 0x00010002u, od_hi);
+          xs[4 * i + 0] = s8_prmt(0x00010002u, ev);
+          xs[4 * i + 1] = s8_prmt(0x00010002u, ev_hi);
+          xs[4 * i + 2] = s8_prmt(0x00010002u, od);
+          xs[4 * i + 3] = s8_prmt(0x00010002u, od_hi);
           if (!kNoE) {
-            es[4 * i + 0] = __byte_perm(0x00000100u, 0x00000100u, ev);
-            es[4 * i + 1] = __byte_perm(0x00000100u, 0x00000100u, ev_hi);
-            es[4 * i + 2] = __byte_perm(0x00000100u, 0x00000100u, od);
-            es[4 * i + 3] = __byte_perm(0x00000100u, 0x00000100u, od_hi);
+            es[4 * i + 0] = s8_prmt(0x00000100u, ev);
+            es[4 * i + 1] = s8_prmt(0x00000100u, ev_hi);
+            es[4 * i + 2] = s8_prmt(0x00000100u, od);
+            es[4 * i + 3] = s8_prmt(0x00000100u, od_hi);
           }
         }
-        const uint32_t sa = g & (kS8ARing - 1);
+        const uint32_t sa = g & (kAR - 1);
         S8_T(d1);
-        // the MMAs that read this TMEM slot last (stage g - 4) must have completed
-        if (g >= (uint32_t)kS8ARing) {
-          uint64_t* bar = &sm->done[(g - kS8ARing) & (kS8WRing - 1)];
-          const uint32_t par = ((g - kS8ARing) >> 3) & 1u;
+        // the MMAs that read this TMEM slot last (stage g - ring depth) must have completed
+        if (g >= (uint32_t)kAR) {
+          uint64_t* bar = &sm->done[(g - kAR) & (kWR - 1)];
+          const uint32_t par = ((g - kAR) >> kWRLog) & 1u;
           if constexpr (kNoE) s8_wait_keep1(bar, par, xs);
           else s8_wait_keep(bar, par, xs, es);
         }
         S8_T(d2);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t a_x = lane_addr + kS8ColA + sa * 64, a_e = a_x + 32;
+        const uint32_t a_x = lane_addr + kS8ColA + sa * kASlot, a_e = a_x + 32;
         tmem_st16(a_x, xs);
         tmem_st16(a_x + 16, xs + 16);
         if constexpr (!kNoE) {
@@ -613,12 +652,12 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       g0 += (uint32_t)kcnt;
     }
     if (kNoE) {
-      if (__any_sync(0xffffffffu, miss_seen != 0) && lane == 0) atomicOr(p.flags, 1);
+      if (__any_sync(0xffffffffu, (miss_seen & 0x55555555u) != 0) && lane == 0) atomicOr(p.flags, 1);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   if (kPair) s8_cluster_sync(); else __syncthreads();
-  if (warp == 2) {
+  if (warp == kS8ProducerWarp) {
     if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
   }
@@ -682,9 +721,10 @@ Split8Plan split8_plan(int n_variants, int n_cb, int64_t n_stages, int sm_count,
     double best_cost = 1e300;
     for (int ns = 1; ns <= max_split; ++ns) {
       if (force_split > 0 && ns != std::min(force_split, max_split)) continue;
-      // ns ranges of `per` stages (even), the last one shorter: n_stages - (ns - 1) per >= 2
+      // ns ranges of `per` stages (even), the last one shorter but with a stage for every issuer warp:
+      // n_stages - (ns - 1) per >= kS8Issuers
       const int per = ns == 1 ? (int)n_stages : (int)round_up(ceil_div(n_stages, ns), 2);
-      if (ns > 1 && (int64_t)(ns - 1) * per + 2 > n_stages) {
+      if (ns > 1 && (int64_t)(ns - 1) * per + kS8Issuers > n_stages) {
         if (force_split > 0) {  // forced but not feasible: fall back to the unsplit form
           ns_out = 1;
           per_out = (int)n_stages;
@@ -719,7 +759,8 @@ size_t split8_ws_bytes(int n_cb, int NC, int64_t ldS) { return (size_t)n_cb * 2 
 
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;
-  const bool aligned = (reinterpret_cast<uintptr_t>(p.x.base) & 3) == 0 && (p.x.stride & 3) == 0;
+  const uintptr_t misal = reinterpret_cast<uintptr_t>(p.x.base) | (uintptr_t)p.x.stride;
+  const int align = (misal & 7) == 0 ? 8 : ((misal & 3) == 0 ? 4 : 0);
   const int n_items1 = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb * p.n_split;
   const int n_items2 = (p.x.n_variants + 2 * kS8TileV - 1) / (2 * kS8TileV) * p.n_cb * p.n_split;
   bool pair = p.pair != 0;
@@ -733,9 +774,9 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   cudaMemcpyToSymbol(g_s8_prof, zero, sizeof(zero));
 #endif
   if (pair) {
-    const size_t smem = (size_t)kS8WRing * (p.NC / 2) * kS8K + sizeof(Split8Smem) + 64;
-    auto kern = no_e ? (aligned ? split8_kernel<true, true, true> : split8_kernel<false, true, true>)
-                     : (aligned ? split8_kernel<true, true, false> : split8_kernel<false, true, false>);
+    const size_t smem = (size_t)(no_e ? kS8WRingMax : kS8WRing) * (p.NC / 2) * kS8K + sizeof(Split8Smem) + 64;
+    auto kern = no_e ? (align == 8 ? split8_kernel<8, true, true> : (align ? split8_kernel<4, true, true> : split8_kernel<0, true, true>))
+                     : (align == 8 ? split8_kernel<8, true, false> : (align ? split8_kernel<4, true, false> : split8_kernel<0, true, false>));
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * std::min(n_items2, sm_count / 2));
@@ -756,8 +797,8 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   }
   if (!pair) {
     const size_t smem = (size_t)kS8WRing * p.NC * kS8K + sizeof(Split8Smem) + 64;
-    auto kern = no_e ? (aligned ? split8_kernel<true, false, true> : split8_kernel<false, false, true>)
-                     : (aligned ? split8_kernel<true, false, false> : split8_kernel<false, false, false>);
+    auto kern = no_e ? (align == 8 ? split8_kernel<8, false, true> : (align ? split8_kernel<4, false, true> : split8_kernel<0, false, true>))
+                     : (align == 8 ? split8_kernel<8, false, false> : (align ? split8_kernel<4, false, false> : split8_kernel<0, false, false>));
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<std::min(n_items1, sm_count), kS8Threads, smem, st>>>(p);
   }
