@@ -67,6 +67,13 @@ class BlockOut(C.Structure):
                 ('y_transpose_x', C.c_void_p)]
 
 
+class LogRegDesc(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('device', C.c_int32), ('n_samples', C.c_int64), ('n_geno_samples', C.c_int64),
+                ('n_covariates', C.c_int32), ('n_phenotypes', C.c_int32), ('n_contigs', C.c_int32), ('reserved', C.c_int32),
+                ('C', C.c_void_p), ('gamma', C.c_void_p), ('Y_res', C.c_void_p), ('inv_CtGammaC', C.c_void_p),
+                ('keep_idx', C.c_void_p)]
+
+
 class Timing(C.Structure):
     _fields_ = [('total_ms', C.c_float), ('prepass_ms', C.c_float), ('gram_ms', C.c_float), ('masked_ms', C.c_float),
                 ('epilogue_ms', C.c_float), ('kernel_launches', C.c_int32), ('path', C.c_int32)]
@@ -90,6 +97,9 @@ SYMBOLS = {
     'glr_t_two_sided_pvalues': (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     'glr_decode_block': (C.c_int, [C.c_int, C.POINTER(BlockDesc), C.c_int64, C.c_void_p]),
     'glr_tensor_i8_issue_rate': (C.c_int, [C.c_int, C.c_double, C.POINTER(C.c_double)]),
+    'glr_logreg_state_create': (C.c_int, [C.POINTER(LogRegDesc), C.POINTER(C.c_void_p)]),
+    'glr_logreg_state_destroy': (C.c_int, [C.c_void_p]),
+    'glr_logreg_run_block': (C.c_int, [C.c_void_p, C.POINTER(BlockDesc), C.c_void_p, C.c_void_p]),
     'glr_device_alloc': (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
     'glr_device_free': (C.c_int, [C.c_int, C.c_void_p]),
     'glr_device_upload': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),

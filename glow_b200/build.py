@@ -11,7 +11,7 @@ OBJ = os.path.join(PKG, 'build')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB = os.path.join(LIB_DIR, 'libglow_b200.so')
 
-SOURCES = ['api.cu', 'aux.cu', 'gram_f64.cu', 'gram_f32.cu', 'gram_i8.cu', 'gram_p2.cu', 'split8.cu', 'mask8.cu', 'masked_sparse.cu']
+SOURCES = ['api.cu', 'aux.cu', 'gram_f64.cu', 'gram_f32.cu', 'gram_i8.cu', 'gram_p2.cu', 'split8.cu', 'mask8.cu', 'masked_sparse.cu', 'logreg.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
     '--expt-relaxed-constexpr'

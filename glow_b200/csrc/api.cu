@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/glow_b200.h"
+#include "api_internal.h"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -1016,6 +1017,13 @@ int glr_host_free(void* ptr) {
   if (ptr) CU(cudaFreeHost(ptr));
   return 0;
 }
+
+}  // extern "C"
+namespace glr {
+int api_fail(int code, const std::string& msg) { return fail(code, msg); }
+int api_check_device(int device) { return check_device(device); }
+}  // namespace glr
+extern "C" {
 
 int glr_device_alloc(int device, size_t bytes, void** ptr) {
   if (!ptr) return fail(GLR_ERR_INVALID, "null argument");

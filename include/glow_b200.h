@@ -175,6 +175,33 @@ int glr_state_destroy(glr_state* st);
  * fully observed, the masked pass is skipped). */
 int glr_state_unique_masks(glr_state* st);
 
+/* ---- logistic-regression score test --------------------------------------------------
+ * The block kernel _logistic_regression_inner of python/glow/gwas/log_reg.py:278-350 with correction = 'none':
+ * genotypes residualised against the null-model fit (log_reg.py:263-275: X - C (C^T Gamma C)^-1 C^T Gamma X), score
+ * statistic chisq = (sum X_res Y_res)^2 / (sum X_res^2 gamma) (log_reg.py:316-321), pvalue = chi2.sf(chisq, 1).  The
+ * null-model fit (log_reg.py:160-200) stays on the host like the QR of the linear path; its results are the state. */
+typedef struct glr_logreg_state glr_logreg_state; /* opaque */
+typedef struct glr_logreg_desc {
+  int32_t abi_version;       /* GLR_ABI_VERSION */
+  int32_t device;
+  int64_t n_samples;         /* N */
+  int64_t n_geno_samples;    /* length of each genotype array (>= N) */
+  int32_t n_covariates;      /* K = columns of C (covariates + intercept), log_reg.py:126-128 */
+  int32_t n_phenotypes;      /* P */
+  int32_t n_contigs;         /* LogRegState per contig with LOCO offsets, else 1 */
+  int32_t reserved;
+  const double* C;           /* [N x K] covariate matrix (NOT orthogonalised) */
+  const double* gamma;       /* [contigs][N x P]  LogRegState.gamma = yhat (1 - yhat), 0 where the phenotype is missing */
+  const double* Y_res;       /* [contigs][N x P]  LogRegState.Y_res = y - yhat, 0 where missing */
+  const double* inv_CtGammaC;/* [contigs][P][K x K] LogRegState.inv_CtGammaC */
+  const int64_t* keep_idx;   /* [N] genotype-array index of each phenotype row (np.delete, log_reg.py:303-304) or NULL */
+} glr_logreg_desc;
+int glr_logreg_state_create(const glr_logreg_desc* desc, glr_logreg_state** out);
+int glr_logreg_state_destroy(glr_logreg_state* st);
+/* One block (same glr_block_desc as the linear path; synchronous): chisq and pvalue are [P x G_b] host arrays,
+ * phenotype-major like the reference's np.ravel (log_reg.py:322-328). */
+int glr_logreg_run_block(glr_logreg_state* st, const glr_block_desc* blk, double* chisq, double* pvalue);
+
 /* Multi-GPU inside one process.  The reference parallelises over Spark partitions of variant rows
  * and ships the state to every worker by closure capture (lin_reg.py:277-284); here variants shard across the devices
  * of the communicator and the state is replicated ONCE: glr_comm_broadcast_state builds it on devices[0] and sends every

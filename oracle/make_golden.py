@@ -348,8 +348,53 @@ def golden_regenie():
     np.savez_compressed(os.path.join(OUT, 'regenie.npz'), **arrays)
 
 
+def golden_logreg():
+    """Logistic score test (log_reg.py, correction='none'): randomised cases in the style of
+    python/glow/gwas/tests/test_log_reg.py (test_multiple, test_multiple_missing, test_spector_no_intercept,
+    test_simple_offset), run through the UNMODIFIED reference block kernel via the reference tests' own
+    ``run_score_test`` recipe (oracle/refshim.py::reference_score_test).  The null-model GLM fit is the restated IRLS
+    (statsmodels is absent from this image)."""
+    rg = np.random.default_rng(20261020)
+    arrays = {}
+    cases = {
+        'multiple': dict(N=50, G=5, P=5, K=3, missing=0.0, intercept=True, offset=False),
+        'multiple_missing': dict(N=60, G=5, P=5, K=3, missing=0.1, intercept=True, offset=False),
+        'no_intercept': dict(N=64, G=6, P=2, K=2, missing=0.1, intercept=False, offset=False),
+        'simple_offset': dict(N=80, G=9, P=3, K=3, missing=0.05, intercept=True, offset=True),
+        'hardcalls': dict(N=400, G=40, P=2, K=4, missing=0.05, intercept=True, offset=False, hardcalls=True),
+    }
+    for name, c in cases.items():
+        N, G, P, K = c['N'], c['G'], c['P'], c['K']
+        if c.get('hardcalls'):
+            X = rg.binomial(2, rg.uniform(0.1, 0.5, (G, 1)), (G, N)).astype(np.float64)
+        else:
+            X = rg.random((G, N))
+        cov = pd.DataFrame(rg.random((N, K)))
+        Y = rg.integers(0, 2, (N, P)).astype(np.float64)
+        if c['missing']:
+            Y[rg.random((N, P)) < c['missing']] = np.nan
+        phe = pd.DataFrame(Y, columns=[f't{i}' for i in range(P)])
+        off = pd.DataFrame(0.5 * rg.standard_normal((N, P)), columns=phe.columns) if c['offset'] else None
+        out, _ = refshim.reference_score_test(X, phe, cov, add_intercept=c['intercept'], offset_df=off)
+        arrays[f'{name}/X'] = X
+        arrays[f'{name}/phenotypes'] = Y
+        arrays[f'{name}/covariates'] = cov.to_numpy(np.float64)
+        arrays[f'{name}/intercept'] = np.array(int(c['intercept']))
+        if off is not None:
+            arrays[f'{name}/offsets'] = off.to_numpy(np.float64)
+        arrays[f'{name}/ref_chisq'] = out['chisq'].to_numpy(np.float64).reshape(P, G)
+        arrays[f'{name}/ref_pvalue'] = out['pvalue'].to_numpy(np.float64).reshape(P, G)
+        assert list(out['phenotype'][:G]) == ['t0'] * G
+    np.savez_compressed(os.path.join(OUT, 'logreg_cases.npz'), **arrays)
+    print('logreg golden cases:', ', '.join(cases))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'logreg':
+        golden_logreg()
+        sys.exit(0)
+    golden_logreg()
     golden_regenie()
     golden_docs()
     golden_doctest()

@@ -53,7 +53,7 @@ def _stub_modules():
                     **{
                         n: _dummy_class(n)
                         for n in ('StringType', 'StructField', 'IntegerType', 'StructType', 'FloatType',
-                                  'DoubleType', 'ArrayType')
+                                  'DoubleType', 'ArrayType', 'BooleanType', 'DataType')
                     })
     sql_functions = mod('pyspark.sql.functions')
     sql = mod('pyspark.sql',
@@ -66,7 +66,9 @@ def _stub_modules():
     # nptyping: annotations only
     mod('nptyping', **{n: _dummy_class(n) for n in ('Float', 'NDArray', 'Int32', 'Int', 'Shape', 'Bool')})
     # opt_einsum (python/setup.py:32 `opt_einsum>=3.2.0`, un-vendored)
-    mod('opt_einsum', contract=lambda s, *ops, **kw: np.einsum(s, *ops, optimize=True))
+    import contextlib
+    mod('opt_einsum', contract=lambda s, *ops, **kw: np.einsum(s, *ops, optimize=True),
+        shared_intermediates=contextlib.nullcontext)  # (a cache of intermediates: no effect on the values)
 
     # bare glow packages so glow/__init__.py (py4j, JVM) is never executed
     def _assert_all_present(df, col_name, df_name):
@@ -229,3 +231,113 @@ def reference_linear_regression(genotype_pdf,
             parts.append(lr._linear_regression_inner(sub, Y_state[c], *args))
         return pd.concat(parts)
     return lr._linear_regression_inner(pdf, Y_state, *args)
+
+
+# ----------------------------------------------------------------------------------------------
+# logistic regression (python/glow/gwas/log_reg.py), score test
+# ----------------------------------------------------------------------------------------------
+_loaded_logreg = None
+
+
+def _statsmodels_stub():
+    """``statsmodels.api`` as far as log_reg.py uses it (log_reg.py:160-175): GLM(y, X, family=Binomial(), offset=...,
+    missing='ignore').fit() and model.predict(params).  The fit is the restated IRLS of oracle/logreg_oracle.py
+    (statsmodels itself is absent from this image)."""
+    from oracle import logreg_oracle as lo
+
+    class _Binomial:
+        pass
+
+    class _Fit:
+        def __init__(self, params):
+            self.params = params
+
+    class GLM:
+        def __init__(self, endog, exog, family=None, offset=None, missing='none'):
+            self.y = np.asarray(endog, dtype=np.float64)
+            self.X = np.asarray(exog, dtype=np.float64)
+            self.offset = None if offset is None else np.asarray(offset, dtype=np.float64)
+
+        def fit(self):
+            self._params, self._mu = lo.glm_binomial_fit(self.y, self.X, self.offset)
+            return _Fit(self._params)
+
+        def predict(self, params):
+            eta = self.X @ params + (0.0 if self.offset is None else self.offset)
+            return 1.0 / (1.0 + np.exp(-eta))
+
+    api = types.ModuleType('statsmodels.api')
+    api.GLM = GLM
+    api.families = types.SimpleNamespace(Binomial=_Binomial)
+    sm = types.ModuleType('statsmodels')
+    sm.api = api
+    return {'statsmodels': sm, 'statsmodels.api': api}
+
+
+def load_logreg():
+    """Returns the reference's ``log_reg`` module, executed unmodified (with approx_firth.py beside it)."""
+    global _loaded_logreg
+    if _loaded_logreg is not None:
+        return _loaded_logreg
+    fx, _ = load()
+    stubs = _stub_modules()
+    stubs.update(_statsmodels_stub())
+    stubs['glow.wgr.wgr_functions'].reshape_for_gwas = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError('Spark'))
+    try:
+        import typeguard  # noqa: F401
+    except Exception:  # noqa: BLE001
+        tg = types.ModuleType('typeguard')
+        tg.typechecked = lambda f: f
+        stubs['typeguard'] = tg
+    saved = {}
+    for name, m in stubs.items():
+        saved[name] = sys.modules.get(name)
+        sys.modules[name] = m
+    sys.modules['glow.gwas.functions'] = fx
+    setattr(sys.modules['glow.gwas'], 'functions', fx)
+    saved.setdefault('glow.gwas.functions', None)
+    try:
+        mods = {}
+        for short in ('approx_firth', 'log_reg'):
+            full = f'glow.gwas.{short}'
+            spec = importlib.util.spec_from_file_location(full, os.path.join(_GWAS_DIR, short + '.py'))
+            module = importlib.util.module_from_spec(spec)
+            sys.modules[full] = module
+            saved.setdefault(full, None)
+            spec.loader.exec_module(module)
+            setattr(sys.modules['glow.gwas'], short, module)
+            mods[short] = module
+        _loaded_logreg = mods['log_reg']
+    finally:
+        for name, old in saved.items():
+            if old is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = old
+    return _loaded_logreg
+
+
+def reference_score_test(genotype_matrix, phenotype_df, covariate_df, add_intercept=True, offset_df=None):
+    """The reference's own ``run_score_test`` recipe (python/glow/gwas/tests/test_log_reg.py:10-32): state rows from
+    ``_prepare_one_phenotype``, ``_pdf_to_log_reg_state``, then ONE block through ``_logistic_regression_inner``.
+    genotype_matrix: [G, N].  Returns the reference's output frame."""
+    import pandas as pd
+    fx, _ = load()
+    lr = load_logreg()
+    C = covariate_df.to_numpy(copy=True)
+    if add_intercept:
+        C = fx._add_intercept(C, phenotype_df.shape[0])
+    Y = phenotype_df.to_numpy(copy=True)
+    Y_mask = ~np.isnan(Y)
+    Y[~Y_mask] = 0
+    rows = []
+    for p in phenotype_df:
+        d = {'label': p, 'values': phenotype_df[p].to_numpy(copy=True)}
+        if offset_df is not None:
+            d['offset'] = offset_df[p].to_numpy(copy=True)
+        rows.append(lr._prepare_one_phenotype(C, pd.Series(d), lr.correction_none, add_intercept))
+    names = phenotype_df.columns.to_series().astype('str')
+    state = lr._pdf_to_log_reg_state(pd.DataFrame(rows), names, C.shape[1])
+    values_df = pd.DataFrame({fx._VALUES_COLUMN_NAME: list(np.asarray(genotype_matrix, dtype=np.float64))})
+    out = lr._logistic_regression_inner(values_df, state, C, Y, Y_mask, None, lr.correction_none, 0.05, names, None)
+    return out, state

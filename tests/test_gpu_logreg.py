@@ -1,0 +1,119 @@
+"""Logistic-regression score test on the GPU against the oracle and the fixtures the
+unmodified reference generated: every genotype format, missing phenotype values, offsets (single and LOCO),
+intersect_samples, no intercept, many covariates, ragged sizes.  Tolerances: the north-star's rel 1e-9 on the
+statistic and rel 1e-6 (abs 1e-300) on the p-value."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from gpu_utils import pack_plink
+from oracle import logreg_oracle as lo
+from oracle import linreg_oracle as orc
+from test_logreg_oracle_pins import case_frames, load_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, ref, label, rtol=1e-9):
+    for k, rt, at in (('chisq', rtol, 1e-13), ('pvalue', max(rtol, 1e-6), 1e-300)):
+        g, r = np.asarray(got[k], dtype=np.float64), np.asarray(ref[k], dtype=np.float64)
+        assert g.shape == r.shape, (label, k)
+        assert np.array_equal(np.isnan(g), np.isnan(r)), (label, k, 'NaN pattern')
+        ok = ~np.isnan(r)
+        err = np.abs(g[ok] - r[ok])
+        tol = at + rt * np.abs(r[ok])
+        assert (err <= tol).all(), f'{label} {k}: worst rel {np.max(err / np.maximum(np.abs(r[ok]), 1e-300)):.3e}'
+
+
+@pytest.mark.parametrize('name', ['multiple', 'multiple_missing', 'no_intercept', 'simple_offset', 'hardcalls'])
+def test_reference_fixtures(name):
+    import glow_b200
+    c = load_cases()[name]
+    phe, cov, off, icpt = case_frames(c)
+    G, P = c['X'].shape[0], phe.shape[1]
+    pdf = pd.DataFrame({'values': list(c['X']), 'idx': np.arange(G)})
+    out = glow_b200.gwas.logistic_regression(pdf, phe, cov, off if off is not None else pd.DataFrame({}), correction='none',
+                                             add_intercept=icpt)
+    assert out.columns.tolist() == ['idx', 'chisq', 'pvalue', 'phenotype']
+    assert out['phenotype'].tolist() == [p for p in phe.columns for _ in range(G)]
+    assert out['idx'].tolist() == list(range(G)) * P
+    _close({k: out[k].to_numpy().reshape(P, G) for k in ('chisq', 'pvalue')}, {'chisq': c['ref_chisq'], 'pvalue': c['ref_pvalue']},
+           f'fixture {name}')
+
+
+@pytest.mark.parametrize('N,G,P,K', [(200, 33, 3, 4), (1000, 300, 1, 16), (515, 129, 11, 3), (4099, 260, 20, 16), (130, 9, 2, 40)])
+def test_all_formats_against_oracle(rg, N, G, P, K):
+    from glow_b200.gwas.log_reg import LogRegDeviceState
+    from glow_b200.engine import GenotypeBlock
+    states = rg.binomial(2, rg.uniform(0.05, 0.5, (G, 1)), (G, N)).astype(np.int64)
+    states[:, 0] = [g % 3 for g in range(G)]
+    miss = states.copy()
+    miss[rg.random((G, N)) < 0.02] = -1
+    cov = pd.DataFrame(rg.standard_normal((N, K)) * 0.3)
+    Y = (rg.random((N, P)) < 0.4).astype(np.float64)
+    Y[rg.random((N, P)) < 0.07] = np.nan
+    phe = pd.DataFrame(Y)
+    C, mask, st = lo.prepare_state(phe, cov)
+    eng = LogRegDeviceState(C, [st])
+    X = states.astype(np.float64) + 0.25 * rg.random((G, N))
+    _close(eng.run(GenotypeBlock(X, 'f64')), lo.block_score_test(X, C, mask, st), 'f64')
+    X32 = X.astype(np.float32)
+    _close(eng.run(GenotypeBlock(X32, 'f32')), lo.block_score_test(X32.astype(np.float64), C, mask, st), 'f32')
+    Xm = orc.mean_substitute(miss.astype(np.float64))
+    ref_mean, ref_raw = lo.block_score_test(Xm, C, mask, st), lo.block_score_test(miss.astype(np.float64), C, mask, st)
+    _close(eng.run(GenotypeBlock(pack_plink(miss), 'plink2', 'mean')), ref_mean, 'plink2 mean')
+    _close(eng.run(GenotypeBlock(pack_plink(miss), 'plink2', 'minus_one')), ref_raw, 'plink2 raw')
+    _close(eng.run(GenotypeBlock(miss.astype(np.int8), 'i8', 'mean')), ref_mean, 'i8 mean')
+    eng.close()
+
+
+def test_loco_offsets_intersect_and_sources(rg):
+    import glow_b200
+    N, G, P, K = 320, 60, 2, 3
+    samples = [f's{i}' for i in range(N)]
+    states = rg.integers(0, 3, (G, N))
+    states[rg.random((G, N)) < 0.03] = -1
+    keep = [i for i in range(N) if i % 9 != 4]
+    Y = (rg.random((N, P)) < 0.5).astype(np.float64)
+    Y[rg.random((N, P)) < 0.05] = np.nan
+    phe = pd.DataFrame(Y, index=samples, columns=['y1', 'y2']).iloc[keep]
+    cov = pd.DataFrame(rg.standard_normal((N, K)), index=samples)
+    contigs = ['1', '2']
+    off = pd.DataFrame(0.3 * rg.standard_normal((len(keep) * 2, P)), index=pd.MultiIndex.from_product([phe.index, contigs]),
+                       columns=phe.columns)
+    meta = pd.DataFrame({'contigName': [contigs[(g // 7) % 2] for g in range(G)], 'idx': np.arange(G)})
+    src = glow_b200.PlinkBedSource(bytes([0x6c, 0x1b, 0x01]) + pack_plink(states).tobytes(), N, meta, mean_substitute=True,
+                                   block_variants=25)
+    out = glow_b200.gwas.logistic_regression(src, phe, cov, off, correction='none', intersect_samples=True,
+                                             genotype_sample_ids=samples)
+    X = orc.mean_substitute(states.astype(np.float64))
+    C, mask, st = lo.prepare_state(phe, cov.loc[phe.index], off)
+    Xk = X[:, keep]
+    for c in contigs:
+        sel = (meta['contigName'] == c).to_numpy()
+        ref = lo.block_score_test(Xk[sel], C, mask, st[c])
+        for p, name in enumerate(phe.columns):
+            rows = out[(out['contigName'] == c) & (out['phenotype'] == name)].sort_values('idx')
+            assert rows['idx'].tolist() == meta['idx'][sel].tolist()
+            _close({'chisq': rows['chisq'].to_numpy(), 'pvalue': rows['pvalue'].to_numpy()},
+                   {'chisq': ref['chisq'][p], 'pvalue': ref['pvalue'][p]}, f'LOCO contig {c} {name}')
+    # the same through pandas blocks (float64 arrays, the reference's own input shape)
+    pdf = meta.copy()
+    pdf['values'] = list(X)
+    out2 = glow_b200.gwas.logistic_regression(iter([pdf.iloc[:31], pdf.iloc[31:]]), phe, cov, off, correction='none',
+                                              intersect_samples=True, genotype_sample_ids=samples)
+    key = lambda d: d.sort_values(['phenotype', 'idx'], kind='stable').reset_index(drop=True)
+    a, b = key(out), key(out2)
+    _close({k: a[k].to_numpy() for k in ('chisq', 'pvalue')}, {k: b[k].to_numpy() for k in ('chisq', 'pvalue')}, 'bed vs pandas')
+
+
+def test_c_abi_logreg_errors(rg):
+    import ctypes as C
+    from glow_b200 import _capi
+    lib = _capi.load()
+    h = C.c_void_p()
+    d = _capi.LogRegDesc(abi_version=_capi.GLR_ABI_VERSION, device=0, n_samples=10, n_geno_samples=10, n_covariates=0, n_phenotypes=1,
+                         n_contigs=1)
+    assert lib.glr_logreg_state_create(C.byref(d), C.byref(h)) == _capi.ERR_INVALID
+    assert b'dimensions' in lib.glr_last_error()
+    assert lib.glr_logreg_state_destroy(None) == 0
