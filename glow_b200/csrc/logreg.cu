@@ -276,7 +276,8 @@ int glr_logreg_run_block(glr_logreg_state* st, const glr_block_desc* b, double* 
   const bool float_fmt = b->format == GLR_FMT_F64 || b->format == GLR_FMT_F32;
   const bool scrub = float_fmt && st->n_drop > 0;
 
-  const int nt = 2, warps = 8;
+  // (the 2-bit kernels are instantiated as 16 consumer warps up to 4 m-tiles, 8 beyond: gram_p2.cu)
+  const int nt = 2, warps = (b->format == GLR_FMT_PLINK2 && st->MT <= 4) ? 16 : 8;
   const int tile = gram_tile_variants(nt, warps);
   const int64_t ldS = std::max(round_up(round_up(G, tile), 8), round_up(G, 256));
   auto split_for = [&](int64_t ctas) {
