@@ -8,8 +8,8 @@ The block loop runs in hand-written sm_100a CUDA behind the C ABI in include/glo
 """
 from . import gwas
 from .engine import DeviceGroup, DeviceState, GenotypeBlock
-from .sources import ArraySource, GenotypeSource, PlinkBedSource, ResidentSource
+from .sources import ArraySource, BgenSource, GenotypeSource, PlinkBedSource, ResidentSource
 
-__all__ = ['gwas', 'DeviceGroup', 'DeviceState', 'GenotypeBlock', 'ArraySource', 'GenotypeSource', 'PlinkBedSource',
+__all__ = ['gwas', 'DeviceGroup', 'DeviceState', 'GenotypeBlock', 'ArraySource', 'BgenSource', 'GenotypeSource', 'PlinkBedSource',
            'ResidentSource']
 __version__ = '0.1.0'

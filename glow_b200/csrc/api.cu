@@ -1044,6 +1044,30 @@ int glr_device_upload(int device, void* dst, const void* src_host, size_t bytes)
   return 0;
 }
 
+int glr_bgen_to_plink2(int device, const void* probs_host, const uint8_t* ploidy_host, int32_t n_variants, int64_t n_samples,
+                       int32_t bits, double hard_call_threshold, void* out_device, int64_t out_stride_bytes) {
+  if (n_variants < 0 || n_samples <= 0 || (bits != 8 && bits != 16 && bits != 32)) return fail(GLR_ERR_INVALID, "bad arguments");
+  if (n_variants == 0) return 0;
+  if (!probs_host || !ploidy_host || !out_device || out_stride_bytes < (n_samples + 3) / 4)
+    return fail(GLR_ERR_INVALID, "missing buffer or output stride smaller than a row");
+  if (int rc = check_device(device)) return rc;
+  const size_t pbytes = (size_t)n_variants * 2 * n_samples * (bits / 8), lbytes = (size_t)n_variants * n_samples;
+  void *dp = nullptr, *dl = nullptr;
+  CU(cudaMalloc(&dp, pbytes));
+  cudaError_t e = cudaMalloc(&dl, lbytes);
+  if (e == cudaSuccess) e = cudaMemcpy(dp, probs_host, pbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dl, ploidy_host, lbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    launch_bgen_to_plink2(dp, (const uint8_t*)dl, n_variants, n_samples, bits, hard_call_threshold, (uint8_t*)out_device,
+                          out_stride_bytes, nullptr);
+    e = cudaDeviceSynchronize();
+  }
+  cudaFree(dp);
+  if (dl) cudaFree(dl);
+  if (e != cudaSuccess) return fail(GLR_ERR_CUDA, std::string("glr_bgen_to_plink2: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 int glr_tensor_i8_issue_rate(int device, double milliseconds, double* tops) {
   if (!tops || !(milliseconds > 0.0)) return fail(GLR_ERR_INVALID, "bad arguments");
   int rc = check_device(device);

@@ -271,6 +271,58 @@ void launch_zero_dropped(const uint8_t* base, int64_t stride, int G, int format,
                                                                        format == GLR_FMT_F64 ? 8 : 4, drop_idx, n_drop);
 }
 
+// ------------------------------------------------------------------------------------------------
+// BGEN v1.2 layout-2 probability blocks (unphased, diploid, biallelic) -> Glow hard calls -> PLINK 2-bit rows on the
+// device.  Semantics of the reference's BGEN datasource + hard_calls + genotype_states
+// (core/.../bgen/BgenFileIterator.scala, BgenSchemaInferrer.scala:42 hardCallThreshold = 0.9,
+// core/.../sql/expressions/VariantUtilExprs.scala:37-59): p = stored integer / (2^bits - 1); the call is the most
+// probable genotype if its probability reaches the threshold, else missing; a sample flagged missing (top bit of its
+// ploidy byte) is missing; state = number of alternate alleles.  Thread = 4 samples of a variant = one output byte
+// (state 0 -> code 11, 1 -> 10, 2 -> 00, missing -> 01: PlinkRowToInternalRowConverter.scala:40-47 inverted).
+template <typename T>
+__global__ void bgen_to_plink2_kernel(const T* probs, const uint8_t* ploidy, int G, int64_t N, double denom, double threshold,
+                                      uint8_t* out, int64_t out_stride) {
+  const int64_t row_bytes = (N + 3) >> 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)G * row_bytes) return;
+  const int64_t g = idx / row_bytes, bpos = idx - g * row_bytes;
+  const T* pr = probs + g * 2 * N;
+  const uint8_t* pl = ploidy + g * N;
+  uint32_t byte = 0;
+  for (int k = 0; k < 4; ++k) {
+    const int64_t s = bpos * 4 + k;
+    uint32_t code = 0;  // padding bits of the last byte stay 0, as in a .bed file
+    if (s < N) {
+      const double p_aa = (double)pr[2 * s] / denom, p_ab = (double)pr[2 * s + 1] / denom;
+      const double p_bb = 1.0 - p_aa - p_ab;
+      int best = 0;
+      double pmax = p_aa;
+      if (p_ab > pmax) {
+        pmax = p_ab;
+        best = 1;
+      }
+      if (p_bb > pmax) {
+        pmax = p_bb;
+        best = 2;
+      }
+      const bool called = pmax >= threshold && !(pl[s] & 0x80);
+      code = !called ? 1u : (best == 0 ? 3u : (best == 1 ? 2u : 0u));
+    }
+    byte |= code << (2 * k);
+  }
+  out[g * out_stride + bpos] = (uint8_t)byte;
+}
+void launch_bgen_to_plink2(const void* probs, const uint8_t* ploidy, int G, int64_t N, int bits, double threshold, uint8_t* out,
+                           int64_t out_stride, cudaStream_t st) {
+  if (G <= 0) return;
+  const int64_t total = (int64_t)G * ((N + 3) >> 2);
+  const unsigned grid = (unsigned)ceil_div(total, 256);
+  const double denom = std::ldexp(1.0, bits) - 1.0;
+  if (bits == 8) bgen_to_plink2_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)probs, ploidy, G, N, denom, threshold, out, out_stride);
+  else if (bits == 16) bgen_to_plink2_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)probs, ploidy, G, N, denom, threshold, out, out_stride);
+  else bgen_to_plink2_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)probs, ploidy, G, N, denom, threshold, out, out_stride);
+}
+
 __global__ void intercept_row_kernel(const double* sum_x, double q0, double* row0, int G) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < G) row0[v] = q0 * sum_x[v];

@@ -171,6 +171,9 @@ void launch_dropped_moments(const BlockView& x, const int64_t* drop_idx, int64_t
 // zeroes the listed (dropped) samples of a STAGED float block (base is library-owned memory)
 void launch_zero_dropped(const uint8_t* base, int64_t stride, int G, int format, const int64_t* drop_idx, int64_t n_drop,
                          cudaStream_t st);
+// BGEN layout-2 probability pairs (bits = 8 | 16 | 32 per probability) + ploidy bytes -> PLINK 2-bit rows (device buffers)
+void launch_bgen_to_plink2(const void* probs, const uint8_t* ploidy, int G, int64_t N, int bits, double threshold, uint8_t* out,
+                           int64_t out_stride, cudaStream_t st);
 // S row of an intercept column that is not in the GEMM: row0[v] = q0 * sum_x[v]
 void launch_intercept_row(const double* sum_x, double q0, double* row0, int G, cudaStream_t st);
 

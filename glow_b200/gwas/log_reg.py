@@ -18,7 +18,7 @@ import pandas as pd
 from . import functions as gwas_fx
 from .functions import _VALUES_COLUMN_NAME, _get_indices_to_drop
 from .. import _capi
-from ..engine import FORMATS, GenotypeBlock, as_block
+from ..engine import FORMATS, GenotypeBlock, ResidentBlock, as_block
 
 __all__ = ['logistic_regression']
 
@@ -129,16 +129,23 @@ class LogRegDeviceState:
                              keep_idx=None if keep_idx is None else keep_idx.ctypes.data)
         _capi.check(self._lib.glr_logreg_state_create(C_.byref(d), C_.byref(self._handle)))
 
-    def run(self, block: GenotypeBlock, contig: int = 0):
-        data = block.data
-        G = int(data.shape[0])
+    def run(self, block, contig: int = 0):
+        resident = isinstance(block, ResidentBlock)
+        if resident and block.device != self.device:
+            raise ValueError(f'resident block lives on GPU {block.device}, this state on GPU {self.device}')
+        G = int(block.n_variants) if resident else int(block.data.shape[0])
         chisq = np.empty((self.P, G), dtype=np.float64)
         pvalue = np.empty((self.P, G), dtype=np.float64)
         if G:
-            if data.ndim != 2 or not data.flags['C_CONTIGUOUS']:
-                raise ValueError('genotype block must be a C-contiguous 2-D array')
-            bd = _capi.BlockDesc(format=FORMATS[block.format], memspace=_capi.MEM_HOST, genotypes=data.ctypes.data,
-                                 row_stride_bytes=data.strides[0], n_variants=G, contig=contig,
+            if resident:
+                addr, stride, space = block.addr, block.stride, _capi.MEM_DEVICE
+            else:
+                data = block.data
+                if data.ndim != 2 or not data.flags['C_CONTIGUOUS']:
+                    raise ValueError('genotype block must be a C-contiguous 2-D array')
+                addr, stride, space = data.ctypes.data, data.strides[0], _capi.MEM_HOST
+            bd = _capi.BlockDesc(format=FORMATS[block.format], memspace=space, genotypes=addr,
+                                 row_stride_bytes=stride, n_variants=G, contig=contig,
                                  missing_policy=_capi.MISSING_MEAN if block.missing == 'mean' else _capi.MISSING_AS_MINUS_ONE)
             _capi.check(self._lib.glr_logreg_run_block(self._handle, C_.byref(bd), chisq.ctypes.data, pvalue.ctypes.data))
         return {'chisq': chisq, 'pvalue': pvalue}
@@ -240,7 +247,12 @@ def logistic_regression(genotype_df,
                 groups = []
                 for contig in pd.unique(meta['contigName']):
                     sel = (meta['contigName'] == contig).to_numpy()
-                    sub = block if sel.all() else GenotypeBlock(np.ascontiguousarray(block.data[sel]), block.format, block.missing)
+                    if sel.all():
+                        sub = block
+                    elif isinstance(block, ResidentBlock):
+                        raise ValueError('a resident block may not span several contigs')
+                    else:
+                        sub = GenotypeBlock(np.ascontiguousarray(block.data[sel]), block.format, block.missing)
                     groups.append((meta[sel], sub, contig_index[contig]))
             for m, blk, ci in groups:
                 res = engine.run(blk, ci)

@@ -251,3 +251,123 @@ class ResidentSource(GenotypeSource):
 
     def __del__(self):
         self.close()
+
+
+class BgenSource(GenotypeSource):
+    """BGEN v1.2 (layout 2, zlib or uncompressed) file -> hard-call blocks on the device.
+
+    The reference reads BGEN through its Spark datasource (core/.../bgen/BgenFileIterator.scala) into probability
+    arrays, turns them into calls with ``hardCallThreshold`` (0.9, BgenSchemaInferrer.scala:42) and the regression
+    sees ``genotype_states`` of those calls.  Here the host only parses the variant records and inflates the probability
+    blocks; the stored 8/16/32-bit probabilities go to the GPU as they are, where ``glr_bgen_to_plink2`` turns them into
+    2-bit rows in HBM -- exact small integers, so a BGEN file takes the int8 tensor-core path of the regression.
+    Supported: unphased, diploid, biallelic blocks (what Glow's ``genotype_states`` path is defined for)."""
+
+    def __init__(self, path, hard_call_threshold: float = 0.9, mean_substitute: bool = True, block_variants: int = 2048,
+                 device: int = 0):
+        import struct
+        self._path = os.fspath(path)
+        self.threshold = float(hard_call_threshold)
+        self.missing = 'mean' if mean_substitute else 'minus_one'
+        self.block_variants = int(block_variants)
+        self.device = int(device)
+        with open(self._path, 'rb') as f:
+            head = f.read(16)
+            offset, hlen, M, N = struct.unpack('<IIII', head)
+            rest = f.read(hlen - 12)
+            if rest[:4] not in (b'bgen', b'\0\0\0\0'):
+                raise ValueError('not a BGEN file (bad magic)')
+            flags, = struct.unpack('<I', rest[-4:])
+            self._compression, layout = flags & 3, (flags >> 2) & 15
+            if layout != 2 or self._compression not in (0, 1):
+                raise ValueError(f'only BGEN v1.2 layout 2 with zlib or no compression is supported (layout {layout}, '
+                                 f'compression {self._compression})')
+            self.n_samples, self.n_variants = int(N), int(M)
+            # one pass over the variant records: identifiers and the byte range of every probability block
+            f.seek(4 + offset)
+            contigs, rsids, starts, ends, refs, alts, spans = [], [], [], [], [], [], []
+            for _ in range(M):
+                lid, = struct.unpack('<H', f.read(2))
+                f.seek(lid, 1)
+                lrs, = struct.unpack('<H', f.read(2))
+                rsids.append(f.read(lrs).decode())
+                lchr, = struct.unpack('<H', f.read(2))
+                contigs.append(f.read(lchr).decode())
+                vpos, nall = struct.unpack('<IH', f.read(6))
+                alleles = []
+                for _a in range(nall):
+                    la, = struct.unpack('<I', f.read(4))
+                    alleles.append(f.read(la).decode())
+                if nall != 2:
+                    raise ValueError('only biallelic BGEN variants are supported')
+                clen, = struct.unpack('<I', f.read(4))
+                spans.append((f.tell(), clen))
+                f.seek(clen, 1)
+                starts.append(vpos - 1)
+                ends.append(vpos - 1 + len(alleles[0]))
+                refs.append(alleles[0])
+                alts.append(alleles[1])
+        self._spans = spans
+        self.meta = pd.DataFrame({'contigName': contigs, 'names': rsids, 'start': np.asarray(starts, dtype=np.int64),
+                                  'end': np.asarray(ends, dtype=np.int64), 'referenceAllele': refs, 'alternateAllele': alts})
+        self.row_bytes = (self.n_samples + 3) // 4
+        self._ring = []  # device buffers [(addr, bytes)], one per block in flight
+
+    def n_blocks(self):
+        return -(-self.n_variants // self.block_variants)
+
+    def _read_block(self, g0, g1):
+        """-> (probs [g, 2 N] uint8/16/32, ploidy [g, N] uint8, bits)"""
+        import struct
+        import zlib
+        N = self.n_samples
+        probs, ploidy, bits_all = [], [], None
+        with open(self._path, 'rb') as f:
+            for g in range(g0, g1):
+                pos, clen = self._spans[g]
+                f.seek(pos)
+                raw = f.read(clen)
+                block = zlib.decompress(raw[4:]) if self._compression == 1 else raw
+                n, k, pmin, pmax = struct.unpack_from('<IHBB', block, 0)
+                if n != N or k != 2 or pmin != 2 or pmax != 2:
+                    raise ValueError('only diploid biallelic BGEN probability blocks are supported')
+                phased, bits = struct.unpack_from('<BB', block, 8 + n)
+                if phased != 0 or bits not in (8, 16, 32):
+                    raise ValueError(f'unsupported BGEN block (phased={phased}, bits={bits})')
+                if bits_all is None:
+                    bits_all = bits
+                elif bits != bits_all:
+                    raise ValueError('mixed probability precisions inside one block of variants')
+                ploidy.append(np.frombuffer(block, dtype=np.uint8, count=n, offset=8))
+                probs.append(np.frombuffer(block, dtype={8: np.uint8, 16: '<u2', 32: '<u4'}[bits], count=2 * n, offset=10 + n))
+        return np.ascontiguousarray(np.stack(probs)), np.ascontiguousarray(np.stack(ploidy)), bits_all
+
+    def blocks(self, first_block=0, last_block=None, ring_depth: int = 3):
+        import ctypes as C
+        from . import _capi
+        lib = _capi.load()
+        last_block = self.n_blocks() if last_block is None else last_block
+        nbytes = self.block_variants * self.row_bytes
+        ring = []
+        try:
+            for _ in range(max(2, ring_depth)):
+                p = C.c_void_p()
+                _capi.check(lib.glr_device_alloc(self.device, nbytes, C.byref(p)))
+                ring.append(p.value)
+            for i, k in enumerate(range(first_block, last_block)):
+                g0, g1 = k * self.block_variants, min(self.n_variants, (k + 1) * self.block_variants)
+                probs, ploidy, bits = self._read_block(g0, g1)
+                addr = ring[i % len(ring)]
+                _capi.check(lib.glr_bgen_to_plink2(self.device, probs.ctypes.data, ploidy.ctypes.data, g1 - g0, self.n_samples, bits,
+                                                   self.threshold, addr, self.row_bytes))
+                meta = self.meta.iloc[g0:g1]
+                # a block is handed out in runs of one contig (LOCO runs take a different Y per contig; a run is just a
+                # row range of the device buffer)
+                names = meta['contigName'].to_numpy()
+                cuts = [0] + [j for j in range(1, len(names)) if names[j] != names[j - 1]] + [len(names)]
+                for r0, r1 in zip(cuts, cuts[1:]):
+                    yield meta.iloc[r0:r1], ResidentBlock(addr + r0 * self.row_bytes, self.row_bytes, r1 - r0, 'plink2',
+                                                          self.missing, self.device)
+        finally:
+            for addr in ring:
+                lib.glr_device_free(self.device, addr)

@@ -239,6 +239,16 @@ int glr_device_alloc(int device, size_t bytes, void** ptr);
 int glr_device_free(int device, void* ptr);
 int glr_device_upload(int device, void* dst, const void* src_host, size_t bytes);
 
+/* BGEN v1.2 layout-2 probability blocks -> Glow hard calls -> PLINK 2-bit rows in device memory (SURVEY.md section 8f
+ * row N2; reference: core/.../bgen/BgenFileIterator.scala, hardCallThreshold BgenSchemaInferrer.scala:42, genotype_states
+ * VariantUtilExprs.scala:37-59).  probs_host: [n_variants][n_samples][2] stored probabilities P(hom ref), P(het) of
+ * `bits` bits each (unphased, diploid, biallelic, as inflated from the file); ploidy_host: [n_variants][n_samples] ploidy
+ * bytes (top bit = missing).  The rows land at out_device + g * out_stride_bytes and are then run like any
+ * GLR_FMT_PLINK2 block with memspace = GLR_MEM_DEVICE: hard calls are exact small integers, so BGEN input takes the
+ * int8 tensor-core path.  Synchronous. */
+int glr_bgen_to_plink2(int device, const void* probs_host, const uint8_t* ploidy_host, int32_t n_variants, int64_t n_samples,
+                       int32_t bits, double hard_call_threshold, void* out_device, int64_t out_stride_bytes);
+
 /* Standalone A6: p = 2 * t.sf(|t|, dof) (lin_reg.py:245) for n device-computed values; host in/out.
  * Exposed so the special-function kernel can be tested against scipy/mpmath directly. */
 int glr_t_two_sided_pvalues(int device, const double* tvalues, int64_t n, double dof, double* pvalues);

@@ -60,3 +60,34 @@ def unpack_states(packed_rows, n_samples):
     for j in range(4):
         codes[:, j::4] = (packed_rows >> (2 * j)) & 3
     return lut[codes[:, :n_samples]]
+
+
+def write_bgen(path, probs, missing=None, compress=True, bits=8, contig='1'):
+    """Minimal BGEN v1.2 layout-2 writer for tests: probs integer [G, N, 2] = stored P(hom ref), P(het) (unphased, diploid,
+    biallelic); missing: bool [G, N] or None."""
+    import struct
+    import zlib
+    G, N, _ = probs.shape
+    dt = {8: np.uint8, 16: '<u2', 32: '<u4'}[bits]
+    body = b''
+    for g in range(G):
+        ident = f'id{g}'.encode()
+        rs = f'rs{g}'.encode()
+        ch = contig.encode() if isinstance(contig, str) else str(contig[g]).encode()
+        rec = struct.pack('<H', len(ident)) + ident + struct.pack('<H', len(rs)) + rs + struct.pack('<H', len(ch)) + ch
+        rec += struct.pack('<IH', 1000 + g, 2) + struct.pack('<I', 1) + b'A' + struct.pack('<I', 1) + b'G'
+        ploidy = np.full(N, 2, dtype=np.uint8)
+        if missing is not None:
+            ploidy[missing[g]] |= 0x80
+        block = struct.pack('<IHBB', N, 2, 2, 2) + ploidy.tobytes() + struct.pack('<BB', 0, bits) + \
+            np.ascontiguousarray(probs[g], dtype=dt).tobytes()
+        if compress:
+            z = zlib.compress(block)
+            rec += struct.pack('<I', len(z) + 4) + struct.pack('<I', len(block)) + z
+        else:
+            rec += struct.pack('<I', len(block)) + block
+        body += rec
+    flags = (1 if compress else 0) | (2 << 2)
+    header = struct.pack('<III', 20, G, N) + b'bgen' + struct.pack('<I', flags)
+    with open(path, 'wb') as f:
+        f.write(struct.pack('<I', 20) + header + body)

@@ -295,3 +295,42 @@ def test_assemble_matches_reference_layout():
     ref['phenotype'] = pd.Series(['a', 'b']).repeat(3).tolist()
     pd.testing.assert_frame_equal(out, ref, check_dtype=False)
     assert out.index.tolist() == [10, 11, 12, 10, 11, 12]
+
+
+def test_bgen_source_parses_layout2_records(tmp_path):
+    """Host half of the BGEN source: variant records and inflated probability blocks, checked
+    against the oracle-side reader on synthetic files and, in the build container, on the reference's own fixture."""
+    import glow_b200
+    from gpu_utils import write_bgen
+    from oracle import bgen as obgen
+    rg = np.random.default_rng(2)
+    G, N = 23, 101
+    for bits, compress in ((8, True), (16, True), (8, False)):
+        hi = 2**bits - 1
+        a = rg.integers(0, hi + 1, (G, N))
+        b = np.minimum(rg.integers(0, hi + 1, (G, N)), hi - a)
+        sure = rg.random((G, N)) < 0.7  # most genotypes are confident calls
+        pick = rg.integers(0, 3, (G, N))
+        a = np.where(sure, np.where(pick == 0, hi, 0), a)
+        b = np.where(sure, np.where(pick == 1, hi, 0), b)
+        probs = np.stack([a, b], axis=2)
+        missing = rg.random((G, N)) < 0.05
+        path = tmp_path / f'x{bits}{int(compress)}.bgen'
+        write_bgen(str(path), probs, missing, compress=compress, bits=bits)
+        src = glow_b200.BgenSource(str(path), block_variants=7)
+        assert (src.n_samples, src.n_variants, src.n_blocks()) == (N, G, 4)
+        assert src.meta['names'].tolist() == [f'rs{g}' for g in range(G)] and src.meta['start'].tolist() == [999 + g for g in range(G)]
+        pr, pl, got_bits = src._read_block(3, 11)
+        assert got_bits == bits and np.array_equal(pr.reshape(8, N, 2), probs[3:11]) and np.array_equal((pl & 0x80) != 0, missing[3:11])
+        _, _, _, states = obgen.read_bgen_states(str(path))
+        p = probs / hi
+        pa, pb = p[:, :, 0], p[:, :, 1]
+        P3 = np.stack([pa, pb, 1.0 - pa - pb], axis=2)
+        want = np.where((P3.max(axis=2) >= 0.9) & ~missing, P3.argmax(axis=2), -1)
+        assert np.array_equal(states, want)
+    ref = '/root/reference/test-data/regenie/example.bgen'
+    if os.path.exists(ref):
+        src = glow_b200.BgenSource(ref)
+        contigs, pos, rsids, _ = obgen.read_bgen_states(ref)
+        assert src.meta['names'].tolist() == rsids and src.meta['contigName'].tolist() == contigs
+        assert (src.meta['start'].to_numpy() == pos - 1).all()

@@ -327,3 +327,48 @@ def test_int8_split_path_with_dropped_samples_and_loco(rg, monkeypatch):
     ref = orc.block_frame(pdf, 'values', st)
     assert out['idx'].tolist() == ref['idx'].tolist()
     assert_stats_close({k: out[k].to_numpy() for k in STATS}, {k: ref[k].to_numpy() for k in STATS}, label='split8 drop+loco')
+
+
+@pytest.mark.parametrize('bits,compress', [(8, True), (16, True), (8, False)])
+def test_bgen_source_runs_on_the_device(rg, tmp_path, bits, compress):
+    """BGEN file -> inflated probabilities -> glr_bgen_to_plink2 on the device -> 2-bit blocks in HBM -> regression on
+    the int8 tensor path, against the oracle fed with the oracle-side reader's hard calls (Glow's threshold 0.9)."""
+    import glow_b200
+    from glow_b200 import _capi
+    from gpu_utils import write_bgen
+    from oracle import bgen as obgen
+    G, N, P, K = 300, 1003, 2, 3
+    hi = 2**bits - 1
+    pick = rg.integers(0, 3, (G, N))
+    a = np.where(pick == 0, hi, 0)
+    b = np.where(pick == 1, hi, 0)
+    fuzzy = rg.random((G, N)) < 0.1  # uncertain genotypes: some clear the threshold, some do not
+    fa = rg.integers(0, hi + 1, (G, N))
+    fb = np.minimum(rg.integers(0, hi + 1, (G, N)), hi - fa)
+    probs = np.stack([np.where(fuzzy, fa, a), np.where(fuzzy, fb, b)], axis=2)
+    missing = rg.random((G, N)) < 0.02
+    path = tmp_path / 'g.bgen'
+    write_bgen(str(path), probs, missing, compress=compress, bits=bits, contig=[1 + g // 150 for g in range(G)])
+    _, _, _, states = obgen.read_bgen_states(str(path))
+    assert (states == -1).any() and (states == 2).any()
+    phe = pd.DataFrame(rg.standard_normal((N, P)) + 0.1 * np.maximum(states[:P], 0).T, columns=['a', 'b'])
+    cov = pd.DataFrame(rg.standard_normal((N, K)))
+    contigs = ['1', '2']
+    off = pd.DataFrame(0.1 * rg.standard_normal((N * 2, P)), index=pd.MultiIndex.from_product([phe.index, contigs]), columns=phe.columns)
+    for o in (pd.DataFrame({}), off):
+        src = glow_b200.BgenSource(str(path), block_variants=128)
+        out = glow_b200.gwas.linear_regression(src, phe, cov, o, options={'split8': 'force'})
+        st = orc.prepare_state(phe, cov, o if not o.empty else None)
+        pdf = src.meta.copy()
+        pdf['values'] = list(orc.mean_substitute(states.astype(np.float64)))
+        ref = pd.concat([orc.block_frame(pdf.iloc[g0:g0 + 128], 'values', st) for g0 in range(0, G, 128)])
+        assert out['names'].tolist() == ref['names'].tolist() and out['phenotype'].tolist() == ref['phenotype'].tolist()
+        assert_stats_close({k: out[k].to_numpy() for k in STATS}, {k: ref[k].to_numpy() for k in STATS}, label=f'bgen {bits} bits')
+    # logistic score test from the same file
+    yb = pd.DataFrame((rg.random((N, P)) < 0.4).astype(np.float64), columns=['a', 'b'])
+    lo_out = glow_b200.gwas.logistic_regression(glow_b200.BgenSource(str(path), block_variants=128), yb, cov, correction='none')
+    from oracle import logreg_oracle as lo
+    C, mask, lst = lo.prepare_state(yb, cov)
+    want = lo.block_score_test(orc.mean_substitute(states.astype(np.float64)), C, mask, lst)
+    got = lo_out.sort_values(['phenotype', 'start'], kind='stable')
+    np.testing.assert_allclose(got['chisq'].to_numpy(), want['chisq'].ravel(), rtol=1e-9, atol=1e-13)
