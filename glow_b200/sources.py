@@ -264,8 +264,11 @@ class BgenSource(GenotypeSource):
     Supported: unphased, diploid, biallelic blocks (what Glow's ``genotype_states`` path is defined for)."""
 
     def __init__(self, path, hard_call_threshold: float = 0.9, mean_substitute: bool = True, block_variants: int = 2048,
-                 device: int = 0):
+                 device: int = 0, split_contigs: bool = True):
+        """``split_contigs``: hand a block out in runs of one contig (needed for LOCO offsets; a run is a row range of the
+        device buffer).  With False the rows of the result follow the file's blocks exactly."""
         import struct
+        self.split_contigs = bool(split_contigs)
         self._path = os.fspath(path)
         self.threshold = float(hard_call_threshold)
         self.missing = 'mean' if mean_substitute else 'minus_one'
@@ -364,7 +367,7 @@ class BgenSource(GenotypeSource):
                 # a block is handed out in runs of one contig (LOCO runs take a different Y per contig; a run is just a
                 # row range of the device buffer)
                 names = meta['contigName'].to_numpy()
-                cuts = [0] + [j for j in range(1, len(names)) if names[j] != names[j - 1]] + [len(names)]
+                cuts = [0] + [j for j in range(1, len(names)) if self.split_contigs and names[j] != names[j - 1]] + [len(names)]
                 for r0, r1 in zip(cuts, cuts[1:]):
                     yield meta.iloc[r0:r1], ResidentBlock(addr + r0 * self.row_bytes, self.row_bytes, r1 - r0, 'plink2',
                                                           self.missing, self.device)

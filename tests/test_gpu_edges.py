@@ -356,7 +356,7 @@ def test_bgen_source_runs_on_the_device(rg, tmp_path, bits, compress):
     contigs = ['1', '2']
     off = pd.DataFrame(0.1 * rg.standard_normal((N * 2, P)), index=pd.MultiIndex.from_product([phe.index, contigs]), columns=phe.columns)
     for o in (pd.DataFrame({}), off):
-        src = glow_b200.BgenSource(str(path), block_variants=128)
+        src = glow_b200.BgenSource(str(path), block_variants=128, split_contigs=not o.empty)
         out = glow_b200.gwas.linear_regression(src, phe, cov, o, options={'split8': 'force'})
         st = orc.prepare_state(phe, cov, o if not o.empty else None)
         pdf = src.meta.copy()
