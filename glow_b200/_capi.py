@@ -105,6 +105,8 @@ SYMBOLS = {
     'glr_device_upload': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     'glr_bgen_to_plink2': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_double, C.c_void_p,
                                      C.c_int64]),
+    'glr_loco_predict': (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'glr_comm_init': (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
     'glr_comm_destroy': (C.c_int, [C.c_void_p]),
     'glr_comm_size': (C.c_int, [C.c_void_p]),

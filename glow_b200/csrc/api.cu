@@ -1068,6 +1068,62 @@ int glr_bgen_to_plink2(int device, const void* probs_host, const uint8_t* ploidy
   return 0;
 }
 
+int glr_loco_predict(int device, int64_t n_samples, int32_t n_headers, int32_t n_sample_blocks, int32_t n_chromosomes,
+                     const double* X_raw, const double* mu, const double* sig, const double* B, const int32_t* header_chromosome,
+                     const int32_t* sample_block, const double* cov, int32_t n_cov, const double* B_cov, double* out) {
+  if (n_samples <= 0 || n_headers < 0 || n_sample_blocks <= 0 || n_chromosomes <= 0 || n_cov < 0)
+    return fail(GLR_ERR_INVALID, "bad dimensions");
+  if ((n_headers > 0 && (!X_raw || !mu || !sig || !B || !header_chromosome)) || !sample_block || !out || (n_cov > 0 && (!cov || !B_cov)))
+    return fail(GLR_ERR_INVALID, "missing array");
+  const int64_t N = n_samples;
+  const int H = n_headers, C = n_chromosomes;
+  // headers grouped by chromosome (stable: the order inside a chromosome is the caller's)
+  std::vector<int32_t> perm, seg(C + 1, 0);
+  for (int h = 0; h < H; ++h) {
+    if (header_chromosome[h] < 0 || header_chromosome[h] >= C) return fail(GLR_ERR_INVALID, "header chromosome index out of range");
+    if (sig[h] == 0.0) return fail(GLR_ERR_INVALID, "Standard deviation cannot be 0.");  // model_functions.py:140-141
+    ++seg[header_chromosome[h] + 1];
+  }
+  for (int c = 0; c < C; ++c) seg[c + 1] += seg[c];
+  perm.resize(std::max(H, 1));
+  {
+    std::vector<int32_t> fill(seg.begin(), seg.end() - 1);
+    for (int h = 0; h < H; ++h) perm[fill[header_chromosome[h]]++] = h;
+  }
+  for (int64_t s = 0; s < N; ++s)
+    if (sample_block[s] < 0 || sample_block[s] >= n_sample_blocks) return fail(GLR_ERR_INVALID, "sample block index out of range");
+  if (int rc = check_device(device)) return rc;
+  struct Tmp {
+    std::vector<void*> v;
+    ~Tmp() { for (void* p : v) if (p) cudaFree(p); }
+    cudaError_t up(const void* src, size_t bytes, void** dst) {
+      cudaError_t e = cudaMalloc(dst, bytes ? bytes : 1);
+      if (e != cudaSuccess) return e;
+      v.push_back(*dst);
+      return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    }
+  } tmp;
+  void *dX, *dmu, *dsig, *dB, *dperm, *dseg, *dsb, *dcov = nullptr, *dBc = nullptr, *dout;
+  CU(tmp.up(X_raw, (size_t)N * H * 8, &dX));
+  CU(tmp.up(mu, (size_t)H * 8, &dmu));
+  CU(tmp.up(sig, (size_t)H * 8, &dsig));
+  CU(tmp.up(B, (size_t)n_sample_blocks * H * 8, &dB));
+  CU(tmp.up(perm.data(), (size_t)H * 4, &dperm));
+  CU(tmp.up(seg.data(), (size_t)(C + 1) * 4, &dseg));
+  CU(tmp.up(sample_block, (size_t)N * 4, &dsb));
+  if (n_cov > 0) {
+    CU(tmp.up(cov, (size_t)N * n_cov * 8, &dcov));
+    CU(tmp.up(B_cov, (size_t)n_sample_blocks * n_cov * 8, &dBc));
+  }
+  CU(cudaMalloc(&dout, (size_t)C * N * 8));
+  tmp.v.push_back(dout);
+  launch_loco_predict((const double*)dX, N, H, (const double*)dmu, (const double*)dsig, (const double*)dB, (const int32_t*)dperm,
+                      (const int32_t*)dseg, C, (const int32_t*)dsb, (const double*)dcov, n_cov, (const double*)dBc, (double*)dout, nullptr);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dout, (size_t)C * N * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int glr_tensor_i8_issue_rate(int device, double milliseconds, double* tops) {
   if (!tops || !(milliseconds > 0.0)) return fail(GLR_ERR_INVALID, "bad arguments");
   int rc = check_device(device);

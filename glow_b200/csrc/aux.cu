@@ -323,6 +323,57 @@ void launch_bgen_to_plink2(const void* probs, const uint8_t* ploidy, int G, int6
   else bgen_to_plink2_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)probs, ploidy, G, N, denom, threshold, out, out_stride);
 }
 
+// ------------------------------------------------------------------------------------------------
+// GloWGR LOCO apply step: RidgeRegression.transform_loco (python/glow/wgr/
+// ridge_regression.py:199-234) applies the fitted model with the headers of one chromosome removed, once per
+// chromosome; per (sample block, label) the apply step is apply_model (python/glow/wgr/ridge_udfs.py:259-347):
+// X = [covariates | (X_raw - mu) / sig] (assemble_block, model_functions.py:118-158), prediction = X @ B.
+// Warp = one sample.  The headers are visited chromosome by chromosome (perm = header indices grouped by chromosome,
+// seg = group boundaries); the per-chromosome partial sums are then combined so that offsets[c] = covariate term +
+// sum of the partials of every OTHER chromosome.
+__global__ void __launch_bounds__(256) loco_predict_kernel(const double* X, int64_t N, int H, const double* mu, const double* sig,
+                                                           const double* B, const int32_t* perm, const int32_t* seg, int n_chr,
+                                                           const int32_t* sample_block, const double* cov, int Kc,
+                                                           const double* Bcov, double* out) {
+  extern __shared__ double part_s[];  // [warps][n_chr]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (s >= N) return;
+  const int sb = sample_block[s];
+  const double* xr = X + s * H;
+  const double* br = B + (int64_t)sb * H;
+  double* part = part_s + warp * n_chr;
+  for (int c = 0; c < n_chr; ++c) {
+    double acc = 0.0;
+    for (int i = seg[c] + lane; i < seg[c + 1]; i += 32) {
+      const int h = perm[i];
+      acc = fma((xr[h] - mu[h]) / sig[h], br[h], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) part[c] = acc;
+  }
+  double cterm = 0.0;
+  for (int k = lane; k < Kc; k += 32) cterm = fma(cov[s * Kc + k], Bcov[(int64_t)sb * Kc + k], cterm);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cterm += __shfl_xor_sync(0xffffffffu, cterm, o);
+  __syncwarp();
+  for (int c = lane; c < n_chr; c += 32) {
+    double acc = cterm;
+    for (int c2 = 0; c2 < n_chr; ++c2)
+      if (c2 != c) acc += part[c2];
+    out[(int64_t)c * N + s] = acc;
+  }
+}
+void launch_loco_predict(const double* X, int64_t N, int H, const double* mu, const double* sig, const double* B, const int32_t* perm,
+                         const int32_t* seg, int n_chr, const int32_t* sample_block, const double* cov, int Kc, const double* Bcov,
+                         double* out, cudaStream_t st) {
+  if (N <= 0 || n_chr <= 0) return;
+  const int warps = 8;
+  loco_predict_kernel<<<(unsigned)ceil_div(N, warps), warps * 32, (size_t)warps * n_chr * sizeof(double), st>>>(
+      X, N, H, mu, sig, B, perm, seg, n_chr, sample_block, cov, Kc, Bcov, out);
+}
+
 __global__ void intercept_row_kernel(const double* sum_x, double q0, double* row0, int G) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v < G) row0[v] = q0 * sum_x[v];

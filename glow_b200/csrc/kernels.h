@@ -174,6 +174,11 @@ void launch_zero_dropped(const uint8_t* base, int64_t stride, int G, int format,
 // BGEN layout-2 probability pairs (bits = 8 | 16 | 32 per probability) + ploidy bytes -> PLINK 2-bit rows (device buffers)
 void launch_bgen_to_plink2(const void* probs, const uint8_t* ploidy, int G, int64_t N, int bits, double threshold, uint8_t* out,
                            int64_t out_stride, cudaStream_t st);
+// GloWGR LOCO apply step: out[c][s] = cov[s] . Bcov[block(s)] + sum over headers h of chromosomes != c of
+// (X[s][h] - mu[h]) / sig[h] * B[block(s)][h]; perm/seg = header indices grouped by chromosome (device arrays)
+void launch_loco_predict(const double* X, int64_t N, int H, const double* mu, const double* sig, const double* B, const int32_t* perm,
+                         const int32_t* seg, int n_chr, const int32_t* sample_block, const double* cov, int Kc, const double* Bcov,
+                         double* out, cudaStream_t st);
 // S row of an intercept column that is not in the GEMM: row0[v] = q0 * sum_x[v]
 void launch_intercept_row(const double* sum_x, double q0, double* row0, int G, cudaStream_t st);
 

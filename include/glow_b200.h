@@ -249,6 +249,21 @@ int glr_device_upload(int device, void* dst, const void* src_host, size_t bytes)
 int glr_bgen_to_plink2(int device, const void* probs_host, const uint8_t* ploidy_host, int32_t n_variants, int64_t n_samples,
                        int32_t bits, double hard_call_threshold, void* out_device, int64_t out_stride_bytes);
 
+/* GloWGR LOCO apply step for ONE label: the offsets RidgeRegression.transform_loco
+ * (python/glow/wgr/ridge_regression.py:199-234) produces by applying the fitted model with the headers of one
+ * chromosome removed, once per chromosome.  Per (sample block, label) the reference's apply_model
+ * (python/glow/wgr/ridge_udfs.py:259-347) computes X @ B with X = [covariates | (X_raw - mu) / sig]
+ * (assemble_block, model_functions.py:118-158).  Here
+ *   out[c][s] = cov[s] . B_cov[block(s)] + sum over headers h with header_chromosome[h] != c of
+ *               (X_raw[s][h] - mu[h]) / sig[h] * B[block(s)][h]
+ * X_raw [n_samples x n_headers] row-major (the reduced block matrix of this label, samples in label order),
+ * B [n_sample_blocks x n_headers] (coefficients of the chosen alpha for the model that excludes each sample block),
+ * sample_block [n_samples], cov [n_samples x n_cov] / B_cov [n_sample_blocks x n_cov] (optional), out
+ * [n_chromosomes x n_samples].  Host in / host out, synchronous.  sig == 0 is an error as in the reference. */
+int glr_loco_predict(int device, int64_t n_samples, int32_t n_headers, int32_t n_sample_blocks, int32_t n_chromosomes,
+                     const double* X_raw, const double* mu, const double* sig, const double* B, const int32_t* header_chromosome,
+                     const int32_t* sample_block, const double* cov, int32_t n_cov, const double* B_cov, double* out);
+
 /* Standalone A6: p = 2 * t.sf(|t|, dof) (lin_reg.py:245) for n device-computed values; host in/out.
  * Exposed so the special-function kernel can be tested against scipy/mpmath directly. */
 int glr_t_two_sided_pvalues(int device, const double* tvalues, int64_t n, double dof, double* pvalues);

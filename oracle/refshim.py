@@ -341,3 +341,50 @@ def reference_score_test(genotype_matrix, phenotype_df, covariate_df, add_interc
     values_df = pd.DataFrame({fx._VALUES_COLUMN_NAME: list(np.asarray(genotype_matrix, dtype=np.float64))})
     out = lr._logistic_regression_inner(values_df, state, C, Y, Y_mask, None, lr.correction_none, 0.05, names, None)
     return out, state
+
+
+# ----------------------------------------------------------------------------------------------
+# GloWGR apply step (python/glow/wgr/ridge_udfs.py::apply_model, model_functions.py)
+# ----------------------------------------------------------------------------------------------
+_loaded_wgr = None
+
+
+def load_wgr():
+    """Returns the reference's ``glow.wgr.ridge_udfs`` module (with ``model_functions`` behind it), executed unmodified.
+    Stubs: pyspark (type/SQL-function names only, none is called by apply_model), nptyping, typeguard (identity
+    decorator: the nptyping stand-ins are not real types)."""
+    global _loaded_wgr
+    if _loaded_wgr is not None:
+        return _loaded_wgr
+    if not available():
+        raise RuntimeError(f'reference tree not found under {REFERENCE_ROOT}')
+    stubs = _stub_modules()
+    stubs['pyspark.sql'].Row = _dummy_class('Row')
+    stubs['pyspark.sql.window'] = types.ModuleType('pyspark.sql.window')
+    stubs['pyspark.sql.window'].Window = _dummy_class('Window')
+    tg = types.ModuleType('typeguard')
+    tg.typechecked = lambda f=None, **kw: f if f is not None else (lambda g: g)
+    stubs['typeguard'] = tg
+    wgr_dir = os.path.join(REFERENCE_ROOT, 'python', 'glow', 'wgr')
+    saved = {}
+    for name, m in stubs.items():
+        saved[name] = sys.modules.get(name)
+        sys.modules[name] = m
+    try:
+        mods = {}
+        for short in ('model_functions', 'ridge_udfs'):
+            full = f'glow.wgr.{short}'
+            spec = importlib.util.spec_from_file_location(full, os.path.join(wgr_dir, short + '.py'))
+            module = importlib.util.module_from_spec(spec)
+            saved.setdefault(full, sys.modules.get(full))
+            sys.modules[full] = module
+            spec.loader.exec_module(module)
+            mods[short] = module
+        _loaded_wgr = mods['ridge_udfs']
+    finally:
+        for name, old in saved.items():
+            if old is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = old
+    return _loaded_wgr
