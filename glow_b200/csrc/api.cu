@@ -415,8 +415,9 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   const int n_mtiles = (int)ceil_div(st->Mcols, 8);
   const int full_tiles = st->Mcols / 8, rem_cols = st->Mcols % 8;
   const bool no_tail = flag_knob(d->opt.no_tail, "GLR_NO_TAIL");
-  if (!no_tail && full_tiles >= 1 && full_tiles <= 4 && rem_cols >= 1 && rem_cols <= 3) {
-    // 8*MT + 1..3 columns: the remainder goes through FP64 FMAs instead of a zero-padded m-tile
+  if (!no_tail && full_tiles >= 1 && full_tiles <= 4 && rem_cols >= 1 && rem_cols <= 4) {
+    // 8*MT + 1..4 columns: the remainder goes through FP64 FMAs instead of a zero-padded m-tile (an FMA column costs
+    // the FP64 datapath what a DMMA column costs, so up to half a tile it is cheaper than padding to 8)
     st->MT = full_tiles;
     st->tail = rem_cols;
     st->n_groups = 1;
@@ -659,6 +660,18 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   if (ctas < st->sm_count) {
     n_split = (int)std::min<int64_t>(ceil_div(2 * st->sm_count, ctas), std::max<int64_t>(1, st->n_chunks / 8));
     n_split = std::max(1, std::min(n_split, 64));
+  } else if (ctas < 12 * (int64_t)st->sm_count) {
+    // a few waves: the last, partly filled one costs a whole wave.  Splitting the sample range in 2..4 makes the waves
+    // shorter (5.3 waves of work run as 6 whole ones, but as 11 halves = 5.5); partial sums are reduced in fixed order
+    double best = (double)ceil_div(ctas, st->sm_count);
+    for (int ns = 2; ns <= 4; ++ns) {
+      if (st->n_chunks / ns < 16) break;
+      const double t = (double)ceil_div(ctas * ns, st->sm_count) / ns + 0.03 * ns;  // + reduce pass and shorter pipelines
+      if (t < best) {
+        best = t;
+        n_split = ns;
+      }
+    }
   }
   if (st->force_split > 0) n_split = (int)std::min<int64_t>(st->force_split, st->n_chunks);
   const int64_t Mpad = st->s_rows;

@@ -294,12 +294,13 @@ struct XLoaderFloatAsync {
 
 // loader of the first pass: the cp.async ring for float formats, the plain loaders otherwise.  The ring depth is what
 // fits next to the W ring (8 warps x 4 KB per unit for f64; the W ring is 8 stages deep up to 4 m-tiles, 4 beyond).
-template <int FMT, int NT, int MT>
+// (16 consumer warps -- float blocks with few columns -- have half the ring per warp: 3 units of 32 samples in flight)
+template <int FMT, int NT, int MT, int WARPS = kWarps>
 struct GramLoader : XLoader<FMT, NT> {};
-template <int NT, int MT>
-struct GramLoader<GLR_FMT_F64, NT, MT> : XLoaderFloatAsync<double, NT, (MT <= 2 ? 4 : (MT == 4 ? 2 : 3))> {};
-template <int NT, int MT>
-struct GramLoader<GLR_FMT_F32, NT, MT> : XLoaderFloatAsync<float, NT, (MT <= 2 ? 4 : (MT == 4 ? 2 : 3))> {};
+template <int NT, int MT, int WARPS>
+struct GramLoader<GLR_FMT_F64, NT, MT, WARPS> : XLoaderFloatAsync<double, NT, (WARPS > 8 ? 3 : (MT <= 2 ? 4 : (MT == 4 ? 2 : 3)))> {};
+template <int NT, int MT, int WARPS>
+struct GramLoader<GLR_FMT_F32, NT, MT, WARPS> : XLoaderFloatAsync<float, NT, (WARPS > 8 ? 3 : (MT <= 2 ? 4 : (MT == 4 ? 2 : 3)))> {};
 
 template <int NT>
 struct XLoader<GLR_FMT_F64, NT> : XLoaderFloat<double, NT> {};
@@ -376,7 +377,7 @@ struct Ring {
 // ------------------------------------------------------------------------------------------------
 // pass 1
 // ------------------------------------------------------------------------------------------------
-// TAIL = 0..3 extra columns beyond the MT m-tiles, accumulated with plain FP64 FMAs on the lane's
+// TAIL = 0..4 extra columns beyond the MT m-tiles, accumulated with plain FP64 FMAs on the lane's
 // own two samples (then reduced over the 4 lanes that share a variant): a column count of 8*MT + 1..3
 // does not pay for a whole zero-padded m-tile of DMMAs.
 template <int FMT, int MT, int NT, int TAIL, int WARPS>
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kStageDoubles = kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup);
   constexpr uint32_t kStageBytes = kStageDoubles * 8;
-  using Loader = GramLoader<FMT, NT, MT>;
+  using Loader = GramLoader<FMT, NT, MT, WARPS>;
   constexpr int UG = Loader::UG;
   constexpr int UPC = kChunkGroups / UG;  // units per chunk
 
@@ -695,7 +696,7 @@ void launch_gram_inst(const GramParams& p, cudaStream_t st) {
   const int tile = WARPS * NT * 8;
   dim3 grid((unsigned)ceil_div(p.x.n_variants, tile), (unsigned)p.n_groups, (unsigned)p.n_split);
   const size_t smem = kBarBytes + (size_t)(MT <= 4 ? kMaxStages : kStages) * kChunkGroups * (MT * kAtomDoubles + TAIL * kGroup) * 8 +
-                      (size_t)WARPS * GramLoader<FMT, NT, MT>::kLutDoublesPerWarp * 8;
+                      (size_t)WARPS * GramLoader<FMT, NT, MT, WARPS>::kLutDoublesPerWarp * 8;
   auto kern = gram_kernel<FMT, MT, NT, TAIL, WARPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<grid, (WARPS + 1) * 32, smem, st>>>(p);
@@ -709,6 +710,7 @@ void launch_gram_tail(const GramParams& p, cudaStream_t st) {
       case 1: launch_gram_inst<FMT, MT, NT, 1, WARPS>(p, st); return;
       case 2: launch_gram_inst<FMT, MT, NT, 2, WARPS>(p, st); return;
       case 3: launch_gram_inst<FMT, MT, NT, 3, WARPS>(p, st); return;
+      case 4: launch_gram_inst<FMT, MT, NT, 4, WARPS>(p, st); return;
       default: break;
     }
   }
