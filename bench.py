@@ -405,7 +405,7 @@ def run_other_configs(torch, dev, hbm_peak, i8_peak):
     return out
 
 
-def run_e2e_api(torch, dev, n_variants=16_384, block_variants=8_192):
+def run_e2e_api(torch, dev, n_variants=65_536, block_variants=8_192):
     """Public API on a .bed FILE in tmpfs: everything a user waits for (file -> pinned staging -> H2D -> kernels -> D2H ->
     pandas frame), state creation included."""
     import pandas as pd

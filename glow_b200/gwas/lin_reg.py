@@ -100,7 +100,7 @@ def linear_regression(genotype_df,
         C = gwas_fx._add_intercept(C, phenotype_df.shape[0]).astype(np_dt, copy=False)
 
     # covariate basis and phenotype residuals (lin_reg.py:146-155)
-    Q = np.linalg.qr(C)[0]
+    Q = _thin_q(C)
     Y = phenotype_df.to_numpy(np_dt, copy=True)
     Y_mask = (~np.isnan(Y)).astype(np_dt)
     Y = np.nan_to_num(Y, copy=False)
@@ -123,6 +123,30 @@ def linear_regression(genotype_df,
 
     return _generate_linreg_output(genotype_df, np_dt, values_column, Y_state, Y_mask, Y_scale, Q, dof, phenotype_df,
                                    Y_for_verbose_output, verbose_output, gt_indices_to_drop, placement)
+
+
+def _thin_q(C: np.ndarray) -> np.ndarray:
+    """``np.linalg.qr(C)[0]`` (lin_reg.py:147).  For tall matrices (UK-Biobank shape: 500 000 x 17, 0.22 s in LAPACK's
+    panel factorisation on one core) the same Householder QR is done as a TSQR: row chunks factorised in parallel
+    threads, then the stacked R factors; Q = blockdiag(Q_i) Q2.  Q spans the same space with orthonormal columns (the
+    columns may differ from numpy's in sign, which no quantity of the regression depends on: Q only enters as Q Q^T)."""
+    n, k = C.shape
+    if n < 100_000 or k == 0 or n < 64 * k:
+        return np.linalg.qr(C)[0]
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    parts = min(16, max(2, os.cpu_count() or 2))
+    bounds = [(n * i) // parts for i in range(parts + 1)]
+    with ThreadPoolExecutor(parts) as pool:
+        qs, rs = zip(*pool.map(lambda i: np.linalg.qr(C[bounds[i]:bounds[i + 1]]), range(parts)))
+        q2 = np.linalg.qr(np.vstack(rs))[0]
+        Q = np.empty_like(C)
+
+        def fill(i):
+            np.matmul(qs[i], q2[i * k:(i + 1) * k], out=Q[bounds[i]:bounds[i + 1]])
+
+        list(pool.map(fill, range(parts)))
+    return Q
 
 
 def _create_YState(Y, phenotype_df, offset_df, Y_mask, dt, contigs) -> Union[YState, Dict[str, YState]]:

@@ -148,12 +148,13 @@ class PlinkBedSource(GenotypeSource):
         # depth - 1 lanes) has finished with block k - depth before it asks for block k, so the buffer is free again.
         # Every live iterator has its own ring (two shards of one file can be streamed at the same time).
         from concurrent.futures import ThreadPoolExecutor
-        depth = max(2, int(ring_depth))
+        depth = max(2, int(ring_depth)) + 1  # + 1: the NEXT block is read while the consumer works on this one
         ring, pinned = self._staging_ring(depth)
         fd = os.open(self._path, os.O_RDONLY)
         try:
             with ThreadPoolExecutor(self.read_threads) as pool:
-                for i, k in enumerate(range(first_block, last_block)):
+
+                def start(i, k):
                     g0 = k * self.block_variants
                     g1 = min(G, g0 + self.block_variants)
                     buf = ring[i % depth][:g1 - g0]
@@ -162,8 +163,8 @@ class PlinkBedSource(GenotypeSource):
                     base = 3 + g0 * self.row_bytes
                     step = -(-nbytes // self.read_threads)
 
-                    def read(i, flat=flat, base=base, nbytes=nbytes, step=step):
-                        lo, hi = i * step, min(nbytes, (i + 1) * step)
+                    def read(j):
+                        lo, hi = j * step, min(nbytes, (j + 1) * step)
                         done = lo
                         while done < hi:  # preadv releases the GIL: the slices are read in parallel
                             got = os.preadv(fd, [memoryview(flat[done:hi])], base + done)
@@ -171,7 +172,15 @@ class PlinkBedSource(GenotypeSource):
                                 raise IOError('unexpected end of .bed file')
                             done += got
 
-                    list(pool.map(read, range(self.read_threads)))
+                    return g0, g1, buf, [pool.submit(read, j) for j in range(self.read_threads)]
+
+                ks = list(range(first_block, last_block))
+                nxt = start(0, ks[0]) if ks else None
+                for i, k in enumerate(ks):
+                    g0, g1, buf, futs = nxt
+                    nxt = start(i + 1, ks[i + 1]) if i + 1 < len(ks) else None
+                    for f in futs:
+                        f.result()
                     yield self.meta.iloc[g0:g1], GenotypeBlock(buf, 'plink2', self.missing, pinned=pinned)
         finally:
             os.close(fd)
