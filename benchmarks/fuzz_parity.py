@@ -21,16 +21,19 @@ def main():
     from oracle import linreg_oracle as orc
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     rg = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-    edges_n = [129, 130, 255, 256, 257, 383, 384, 385, 511, 513, 640, 1000, 1025, 2049]
+    edges_n = [129, 130, 255, 256, 257, 383, 384, 385, 511, 512, 513, 640, 1000, 1025, 2049, 4097, 6150]
     edges_g = [1, 7, 8, 17, 18, 19, 35, 36, 37, 127, 128, 129, 255, 256, 257, 300]
     modes = [dict(), dict(GLR_SPLIT8='2', GLR_S8_PAIR='2'), dict(GLR_SPLIT8='2', GLR_S8_PAIR='0'), dict(GLR_SPLIT8='0'),
-             dict(GLR_MASK8='2', GLR_SPLIT8='2'), dict(GLR_MASK_SPARSE='2'), dict(GLR_MASK_SPARSE='0', GLR_MASK8='0')]
-    knobs = ('GLR_SPLIT8', 'GLR_S8_PAIR', 'GLR_MASK8', 'GLR_MASK_SPARSE')
+             dict(GLR_MASK8='2', GLR_SPLIT8='2'), dict(GLR_MASK_SPARSE='2'), dict(GLR_MASK_SPARSE='0', GLR_MASK8='0'),
+             # round 2: sample-range split of the int8 kernel, optimistic form (replayed when the block has missing calls)
+             dict(GLR_SPLIT8='2', GLR_SPLIT='3'), dict(GLR_SPLIT8='2', GLR_S8_PAIR='0', GLR_SPLIT='2'),
+             dict(GLR_SPLIT8='2', GLR_OPTIMISTIC='2'), dict(GLR_SPLIT8='2', GLR_S8_PAIR='0', GLR_SPLIT='5', GLR_OPTIMISTIC='2')]
+    knobs = ('GLR_SPLIT8', 'GLR_S8_PAIR', 'GLR_MASK8', 'GLR_MASK_SPARSE', 'GLR_SPLIT', 'GLR_OPTIMISTIC')
     done = 0
     for case in range(n_cases):
         N = int(rg.choice(edges_n))
         G = int(rg.choice(edges_g))
-        K = int(rg.choice([0, 1, 2, 5, 16, 17, 18, 20]))
+        K = int(rg.choice([0, 1, 2, 5, 16, 17, 18, 20, 33, 70]))
         P = int(rg.choice([1, 2, 3, 17, 18, 19, 36, 40]))
         if N - K - 2 < 5:
             continue

@@ -71,7 +71,7 @@ class LogRegDesc(C.Structure):
     _fields_ = [('abi_version', C.c_int32), ('device', C.c_int32), ('n_samples', C.c_int64), ('n_geno_samples', C.c_int64),
                 ('n_covariates', C.c_int32), ('n_phenotypes', C.c_int32), ('n_contigs', C.c_int32), ('reserved', C.c_int32),
                 ('C', C.c_void_p), ('gamma', C.c_void_p), ('Y_res', C.c_void_p), ('inv_CtGammaC', C.c_void_p),
-                ('keep_idx', C.c_void_p)]
+                ('keep_idx', C.c_void_p), ('Q', C.c_void_p)]
 
 
 class Timing(C.Structure):

@@ -16,6 +16,13 @@
 //   epilogue: logreg_epilogue_kernel
 // The decode of packed genotypes (PLINK 2-bit / int8 states, optional mean substitution) is the same fused operand
 // load as in the linear path.
+//
+// correction = 'approx-firth' first residualises the genotypes LINEARLY against the covariate basis, X <- X - Q Q^T X
+// (log_reg.py:312-313), and runs the score test on that.  With a = Q^T x (K more columns of the same contraction) the
+// quantities of x_lin = x - Q a follow from those of x:
+//   b_lin = b - (C^T Gamma Q) a,   v_lin = v - (Q^T Y_res) . a,   D_lin = D - 2 a . (R^-T b) + a^T (Q^T Gamma Q) a
+// (Q^T Gamma x = R^-T C^T Gamma x because C = Q R), so no residual matrix is formed on the device either.  The Firth
+// refits of the flagged tests stay on the host, as in the reference.
 #include <algorithm>
 #include <cmath>
 #include <string>
@@ -70,6 +77,11 @@ struct glr_logreg_state {
   double* inv = nullptr;                 // [C][P][K][K]
   double* ctgc = nullptr;                // [C][P][K][K]   C^T Gamma C
   double* tvec = nullptr;                // [C][P][K]      C^T Y_res
+  int lin = 0;                           // 1: linear residualisation first (approx-firth): Q columns follow in W
+  double* m1 = nullptr;                  // [C][P][K][K]   C^T Gamma Q
+  double* m2 = nullptr;                  // [C][P][K][K]   Q^T Gamma Q
+  double* t2 = nullptr;                  // [C][P][K]      Q^T Y_res
+  double* rinvt = nullptr;               // [K][K]         R^-T, R = Q^T C
   int64_t* drop_idx = nullptr;
   int64_t n_drop = 0;
   int sm_count = 148;
@@ -77,56 +89,95 @@ struct glr_logreg_state {
   Buf geno, out, s_part, s_red, mom_part, mom, v1, d_part, d_red;
 };
 
+struct LogregEpi {
+  const double *S, *D;
+  int64_t ldS;
+  int K, P, G, lin;
+  const double *inv, *ctgc, *tvec;     // of this contig
+  const double *m1, *m2, *t2, *rinvt;  // lin only
+  double *chisq, *pvalue;
+};
+
 // thread = (phenotype, variant)
-__global__ void logreg_epilogue_kernel(const double* S, const double* D, int64_t ldS, int K, int P, int G, const double* inv,
-                                       const double* ctgc, const double* tvec, double* chisq, double* pvalue) {
+__global__ void logreg_epilogue_kernel(const LogregEpi e) {
+  constexpr int kLocalK = 64;
+  const int K = e.K, G = e.G;
+  const int64_t ldS = e.ldS;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)P * G) return;
+  if (idx >= (int64_t)e.P * G) return;
   const int p = (int)(idx / G);
   const int g = (int)(idx - (int64_t)p * G);
-  const double* b = S + (int64_t)p * (K + 1) * ldS + g;  // b[k] = b[k * ldS]
-  const double v = b[(int64_t)K * ldS];                   // Y_res^T x
-  const double* ip = inv + (int64_t)p * K * K;
-  const double* ap = ctgc + (int64_t)p * K * K;
-  const double* tp = tvec + (int64_t)p * K;
-  // q = inv b;  tq = t . q;  bq = b . q;  qaq = q^T A q
-  constexpr int kLocalK = 32;
+  const double* bs = e.S + (int64_t)p * (K + 1) * ldS + g;  // b[k] = bs[k * ldS]
+  double v = bs[(int64_t)K * ldS];                           // Y_res^T x
+  double Dv = e.D[(int64_t)p * ldS + g];                     // x^T Gamma x
+  const double* ip = e.inv + (int64_t)p * K * K;
+  const double* ap = e.ctgc + (int64_t)p * K * K;
+  const double* tp = e.tvec + (int64_t)p * K;
   double tq = 0.0, bq = 0.0, qaq = 0.0;
   if (K <= kLocalK) {
-    double q[kLocalK];
+    double b[kLocalK], q[kLocalK];
+    for (int c = 0; c < K; ++c) b[c] = bs[(int64_t)c * ldS];
+    if (e.lin) {
+      // linear residualisation against Q folded into the contractions (see the header of this file)
+      const double* as = e.S + (int64_t)e.P * (K + 1) * ldS + g;  // a[k] = Q^T x
+      const double* m1 = e.m1 + (int64_t)p * K * K;
+      const double* m2 = e.m2 + (int64_t)p * K * K;
+      const double* t2 = e.t2 + (int64_t)p * K;
+      double a[kLocalK];
+      for (int c = 0; c < K; ++c) a[c] = as[(int64_t)c * ldS];
+      double cross = 0.0, quad = 0.0, ta = 0.0;
+      for (int c = 0; c < K; ++c) {
+        double rb = 0.0, m2a = 0.0;
+        for (int d = 0; d < K; ++d) {
+          rb = fma(e.rinvt[c * K + d], b[d], rb);  // (R^-T b)[c] = (Q^T Gamma x)[c]
+          m2a = fma(m2[c * K + d], a[d], m2a);
+        }
+        cross = fma(a[c], rb, cross);
+        quad = fma(a[c], m2a, quad);
+        ta = fma(t2[c], a[c], ta);
+      }
+      Dv = Dv - 2.0 * cross + quad;
+      v -= ta;
+      for (int c = 0; c < K; ++c) {
+        double m1a = 0.0;
+        for (int d = 0; d < K; ++d) m1a = fma(m1[c * K + d], a[d], m1a);
+        q[c] = b[c] - m1a;
+      }
+      for (int c = 0; c < K; ++c) b[c] = q[c];
+    }
     for (int c = 0; c < K; ++c) {
       double qc = 0.0;
-      for (int d = 0; d < K; ++d) qc = fma(ip[c * K + d], b[(int64_t)d * ldS], qc);
+      for (int d = 0; d < K; ++d) qc = fma(ip[c * K + d], b[d], qc);
       q[c] = qc;
       tq = fma(tp[c], qc, tq);
-      bq = fma(b[(int64_t)c * ldS], qc, bq);
+      bq = fma(b[c], qc, bq);
     }
     for (int c = 0; c < K; ++c) {
       double aq = 0.0;
       for (int d = 0; d < K; ++d) aq = fma(ap[c * K + d], q[d], aq);
       qaq = fma(q[c], aq, qaq);
     }
-  } else {  // many covariates: q is recomputed instead of stored (O(K^3) per test, rarely used)
+  } else {  // many covariates (score test only): q is recomputed instead of stored, O(K^3) per test
     for (int c = 0; c < K; ++c) {
       double qc = 0.0;
-      for (int d = 0; d < K; ++d) qc = fma(ip[c * K + d], b[(int64_t)d * ldS], qc);
+      for (int d = 0; d < K; ++d) qc = fma(ip[c * K + d], bs[(int64_t)d * ldS], qc);
       tq = fma(tp[c], qc, tq);
-      bq = fma(b[(int64_t)c * ldS], qc, bq);
+      bq = fma(bs[(int64_t)c * ldS], qc, bq);
       double aq = 0.0;
       for (int d = 0; d < K; ++d) {
         double qd = 0.0;
-        for (int e = 0; e < K; ++e) qd = fma(ip[d * K + e], b[(int64_t)e * ldS], qd);
+        for (int f = 0; f < K; ++f) qd = fma(ip[d * K + f], bs[(int64_t)f * ldS], qd);
         aq = fma(ap[c * K + d], qd, aq);
       }
       qaq = fma(qc, aq, qaq);
     }
   }
   const double num = (v - tq) * (v - tq);
-  const double den = D[(int64_t)p * ldS + g] - 2.0 * bq + qaq;
+  const double den = Dv - 2.0 * bq + qaq;
   const double x2 = num / den;
-  chisq[idx] = x2;
+  e.chisq[idx] = x2;
   // scipy.stats.chi2.sf(x, 1) = erfc(sqrt(x / 2)); sf of a negative statistic is 1
-  pvalue[idx] = x2 != x2 ? x2 : (x2 < 0.0 ? 1.0 : erfc(sqrt(0.5 * x2)));
+  e.pvalue[idx] = x2 != x2 ? x2 : (x2 < 0.0 ? 1.0 : erfc(sqrt(0.5 * x2)));
 }
 
 extern "C" {
@@ -135,7 +186,8 @@ int glr_logreg_state_destroy(glr_logreg_state* st) {
   if (!st) return 0;
   cudaSetDevice(st->device);
   if (st->stream) cudaStreamSynchronize(st->stream);
-  for (void* p : {(void*)st->wpk, (void*)st->gpk, (void*)st->qb0, (void*)st->inv, (void*)st->ctgc, (void*)st->tvec, (void*)st->drop_idx})
+  for (void* p : {(void*)st->wpk, (void*)st->gpk, (void*)st->qb0, (void*)st->inv, (void*)st->ctgc, (void*)st->tvec, (void*)st->drop_idx,
+                  (void*)st->m1, (void*)st->m2, (void*)st->t2, (void*)st->rinvt})
     if (p) cudaFree(p);
   for (Buf* b : {&st->geno, &st->out, &st->s_part, &st->s_red, &st->mom_part, &st->mom, &st->v1, &st->d_part, &st->d_red})
     if (b->p) cudaFree(b->p);
@@ -193,7 +245,9 @@ int glr_logreg_state_create(const glr_logreg_desc* d, glr_logreg_state** out) {
   } tmp;
   tmp.v.push_back(d_g2r);
 
-  st->Mcols = P * (K + 1);
+  st->lin = d->Q ? 1 : 0;
+  if (st->lin && K > 64) return api_fail(GLR_ERR_INVALID, "the linear residualisation of approx-firth takes at most 64 covariates");
+  st->Mcols = P * (K + 1) + (st->lin ? K : 0);
   const int n_mt = (int)ceil_div(st->Mcols, 8);
   st->MT = std::min(n_mt, kMaxMT);
   st->n_groups = (int)ceil_div(n_mt, kMaxMT);
@@ -213,6 +267,45 @@ int glr_logreg_state_create(const glr_logreg_desc* d, glr_logreg_state** out) {
 
   // per contig: W = [gamma_p o C | Y_res_p]_p (row-major [N x P (K + 1)], built on the host), C^T Gamma C, t = C^T Y_res
   std::vector<double> W((size_t)N * st->Mcols), A((size_t)C * P * K * K, 0.0), T((size_t)C * P * K, 0.0);
+  std::vector<double> M1, M2, T2, Rit;
+  if (st->lin) {
+    M1.assign(A.size(), 0.0);
+    M2.assign(A.size(), 0.0);
+    T2.assign(T.size(), 0.0);
+    // R = Q^T C; R^-T by Gauss-Jordan with partial pivoting on the K x K matrix (host, once)
+    std::vector<double> R((size_t)K * K, 0.0), Inv((size_t)K * K, 0.0);
+    for (int64_t s = 0; s < N; ++s)
+      for (int k = 0; k < K; ++k)
+        for (int l = 0; l < K; ++l) R[k * K + l] = fma(d->Q[s * K + k], d->C[s * K + l], R[k * K + l]);
+    for (int k = 0; k < K; ++k) Inv[k * K + k] = 1.0;
+    for (int col = 0; col < K; ++col) {
+      int piv = col;
+      for (int r = col + 1; r < K; ++r)
+        if (std::fabs(R[r * K + col]) > std::fabs(R[piv * K + col])) piv = r;
+      if (R[piv * K + col] == 0.0) return api_fail(GLR_ERR_INVALID, "Q^T C is singular: Q must be the orthonormal basis of C");
+      for (int l = 0; l < K; ++l) {
+        std::swap(R[col * K + l], R[piv * K + l]);
+        std::swap(Inv[col * K + l], Inv[piv * K + l]);
+      }
+      const double dinv = 1.0 / R[col * K + col];
+      for (int l = 0; l < K; ++l) {
+        R[col * K + l] *= dinv;
+        Inv[col * K + l] *= dinv;
+      }
+      for (int r = 0; r < K; ++r) {
+        if (r == col) continue;
+        const double f = R[r * K + col];
+        if (f == 0.0) continue;
+        for (int l = 0; l < K; ++l) {
+          R[r * K + l] -= f * R[col * K + l];
+          Inv[r * K + l] -= f * Inv[col * K + l];
+        }
+      }
+    }
+    Rit.assign((size_t)K * K, 0.0);
+    for (int k = 0; k < K; ++k)
+      for (int l = 0; l < K; ++l) Rit[k * K + l] = Inv[l * K + k];  // transpose of R^-1
+  }
   double *dW = nullptr, *dG = nullptr;
   CUL(cudaMalloc(&dW, W.size() * 8));
   tmp.v.push_back(dW);
@@ -237,6 +330,25 @@ int glr_logreg_state_create(const glr_logreg_desc* d, glr_logreg_state** out) {
           for (int l = 0; l < K; ++l) Ap[k * K + l] = fma(gk, cs[l], Ap[k * K + l]);
           Tc[p * K + k] = fma(cs[k], ysp, Tc[p * K + k]);
         }
+        if (st->lin) {
+          const double* qs = d->Q + s * K;
+          double* M1p = M1.data() + ((size_t)c * P + p) * K * K;
+          double* M2p = M2.data() + ((size_t)c * P + p) * K * K;
+          double* T2p = T2.data() + ((size_t)c * P + p) * K;
+          for (int k = 0; k < K; ++k) {
+            const double gc = gsp * cs[k], gq = gsp * qs[k];
+            for (int l = 0; l < K; ++l) {
+              M1p[k * K + l] = fma(gc, qs[l], M1p[k * K + l]);
+              M2p[k * K + l] = fma(gq, qs[l], M2p[k * K + l]);
+            }
+            T2p[k] = fma(qs[k], ysp, T2p[k]);
+          }
+        }
+      }
+      if (st->lin) {
+        const double* qs = d->Q + s * K;
+        double* wq = ws + (size_t)P * (K + 1);
+        for (int k = 0; k < K; ++k) wq[k] = qs[k];
       }
     }
     CUL(cudaMemcpy(dW, W.data(), W.size() * 8, cudaMemcpyHostToDevice));
@@ -251,6 +363,16 @@ int glr_logreg_state_create(const glr_logreg_desc* d, glr_logreg_state** out) {
   CUL(cudaMemcpy(st->ctgc, A.data(), A.size() * 8, cudaMemcpyHostToDevice));
   CUL(cudaMalloc(&st->tvec, T.size() * 8));
   CUL(cudaMemcpy(st->tvec, T.data(), T.size() * 8, cudaMemcpyHostToDevice));
+  if (st->lin) {
+    CUL(cudaMalloc(&st->m1, M1.size() * 8));
+    CUL(cudaMemcpy(st->m1, M1.data(), M1.size() * 8, cudaMemcpyHostToDevice));
+    CUL(cudaMalloc(&st->m2, M2.size() * 8));
+    CUL(cudaMemcpy(st->m2, M2.data(), M2.size() * 8, cudaMemcpyHostToDevice));
+    CUL(cudaMalloc(&st->t2, T2.size() * 8));
+    CUL(cudaMemcpy(st->t2, T2.data(), T2.size() * 8, cudaMemcpyHostToDevice));
+    CUL(cudaMalloc(&st->rinvt, Rit.size() * 8));
+    CUL(cudaMemcpy(st->rinvt, Rit.data(), Rit.size() * 8, cudaMemcpyHostToDevice));
+  }
   CUL(cudaGetLastError());
   guard.s = nullptr;
   *out = st;
@@ -356,10 +478,25 @@ int glr_logreg_run_block(glr_logreg_state* st, const glr_block_desc* b, double* 
   double* d_chi = st->out.as<double>();
   double* d_p = d_chi + (size_t)P * G;
   const int64_t total = (int64_t)P * G;
-  logreg_epilogue_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, s>>>(st->s_red.as<double>(), st->d_red.as<double>(), ldS, K, P, G,
-                                                                         st->inv + (int64_t)b->contig * P * K * K,
-                                                                         st->ctgc + (int64_t)b->contig * P * K * K,
-                                                                         st->tvec + (int64_t)b->contig * P * K, d_chi, d_p);
+  LogregEpi ep;
+  ep.S = st->s_red.as<double>();
+  ep.D = st->d_red.as<double>();
+  ep.ldS = ldS;
+  ep.K = K;
+  ep.P = P;
+  ep.G = G;
+  ep.lin = st->lin;
+  const int64_t coff = (int64_t)b->contig * P * K * K, toff = (int64_t)b->contig * P * K;
+  ep.inv = st->inv + coff;
+  ep.ctgc = st->ctgc + coff;
+  ep.tvec = st->tvec + toff;
+  ep.m1 = st->lin ? st->m1 + coff : nullptr;
+  ep.m2 = st->lin ? st->m2 + coff : nullptr;
+  ep.t2 = st->lin ? st->t2 + toff : nullptr;
+  ep.rinvt = st->rinvt;
+  ep.chisq = d_chi;
+  ep.pvalue = d_p;
+  logreg_epilogue_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, s>>>(ep);
   CUL(cudaGetLastError());
   CUL(cudaMemcpyAsync(chisq, d_chi, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
   CUL(cudaMemcpyAsync(pvalue, d_p, (size_t)total * 8, cudaMemcpyDeviceToHost, s));

@@ -1,5 +1,5 @@
-"""B200-native drop-in for ``glow.gwas.logistic_regression`` (reference: python/glow/gwas/log_reg.py), score test
-(``correction='none'``).
+"""B200-native drop-in for ``glow.gwas.logistic_regression`` (reference: python/glow/gwas/log_reg.py): the score test
+on the device, the approximate Firth refit of the significant tests on the host (as in the reference).
 
 Same signature, validation and output columns as the reference.  The driver-side preparation -- one null logistic
 model per phenotype (and per contig with LOCO offsets), log_reg.py:160-200 -- stays on the host: the reference fits it
@@ -15,6 +15,7 @@ from typing import Any, Dict, List, Optional, Sequence, Union
 import numpy as np
 import pandas as pd
 
+from . import approx_firth as af
 from . import functions as gwas_fx
 from .functions import _VALUES_COLUMN_NAME, _get_indices_to_drop
 from .. import _capi
@@ -28,10 +29,11 @@ correction_approx_firth = 'approx-firth'
 
 @dataclass
 class LogRegState:
-    """log_reg.py:153-158 (without the Firth offset)."""
+    """log_reg.py:153-158."""
     inv_CtGammaC: np.ndarray  # n_phenotypes x n_covariates x n_covariates
     gamma: np.ndarray  # n_samples x n_phenotypes
     Y_res: np.ndarray  # n_samples x n_phenotypes
+    firth_offset: Optional[np.ndarray] = None  # n_samples x n_phenotypes (approx-firth only)
 
 
 def _logistic_null_model_predictions(y, X, mask, offset, max_iter=100, tol=1e-8):
@@ -80,7 +82,8 @@ def _prepare_one_phenotype(C, y, offset):
     return y_res, gamma, np.linalg.inv(CtGammaC)
 
 
-def _create_log_reg_state(phenotype_df, offset_df, C, contigs) -> Union[LogRegState, Dict[str, LogRegState]]:
+def _create_log_reg_state(phenotype_df, offset_df, C, contigs, correction=correction_none,
+                          add_intercept=True) -> Union[LogRegState, Dict[str, LogRegState]]:
     """log_reg.py:223-275, without the Spark distribution of the null fits."""
     offset_type = gwas_fx._validate_offset(phenotype_df, offset_df)
     if offset_type == gwas_fx._OffsetType.LOCO_OFFSET and contigs is not None:
@@ -89,14 +92,16 @@ def _create_log_reg_state(phenotype_df, offset_df, C, contigs) -> Union[LogRegSt
     names = list(phenotype_df.columns)
 
     def one_state(off_df):
-        ys, gs, invs = [], [], []
+        ys, gs, invs, fos = [], [], [], []
         for j, name in enumerate(names):
             off = None if off_df is None else off_df[name].reindex(phenotype_df.index).to_numpy(np.float64)
             y_res, gamma, inv = _prepare_one_phenotype(C, Y[:, j], off)
             ys.append(y_res)
             gs.append(gamma)
             invs.append(inv)
-        return LogRegState(np.stack(invs), np.column_stack(gs), np.column_stack(ys))
+            if correction == correction_approx_firth:  # log_reg.py:197-199
+                fos.append(af.perform_null_firth_fit(Y[:, j], C, ~np.isnan(Y[:, j]), off, add_intercept))
+        return LogRegState(np.stack(invs), np.column_stack(gs), np.column_stack(ys), np.column_stack(fos) if fos else None)
 
     if offset_type == gwas_fx._OffsetType.NO_OFFSET:
         return one_state(None)
@@ -109,7 +114,9 @@ def _create_log_reg_state(phenotype_df, offset_df, C, contigs) -> Union[LogRegSt
 class LogRegDeviceState:
     """Replica of (C, gamma, Y_res, inv_CtGammaC per contig) on one GPU."""
 
-    def __init__(self, Cmat, states: Sequence[LogRegState], keep_idx=None, n_geno_samples=None, device=0):
+    def __init__(self, Cmat, states: Sequence[LogRegState], keep_idx=None, n_geno_samples=None, device=0, Q=None):
+        """``Q`` (orthonormal basis of ``Cmat``): the genotypes are first residualised linearly against it, as the
+        reference does for correction='approx-firth' (log_reg.py:312-313)."""
         self._lib = _capi.load()
         self._handle = C_.c_void_p()
         Cmat = np.ascontiguousarray(Cmat, dtype=np.float64)
@@ -120,13 +127,18 @@ class LogRegDeviceState:
         K = Cmat.shape[1]
         if keep_idx is not None:
             keep_idx = np.ascontiguousarray(keep_idx, dtype=np.int64)
+        if Q is not None:
+            Q = np.ascontiguousarray(Q, dtype=np.float64)
+            if Q.shape != Cmat.shape:
+                raise ValueError('Q must have the shape of the covariate matrix')
         self.N, self.K, self.P, self.n_contigs = N, K, P, n_contigs
         self.Ng = int(n_geno_samples) if n_geno_samples is not None else N
         self.device = device
         d = _capi.LogRegDesc(abi_version=_capi.GLR_ABI_VERSION, device=device, n_samples=N, n_geno_samples=self.Ng, n_covariates=K,
                              n_phenotypes=P, n_contigs=n_contigs, C=Cmat.ctypes.data, gamma=gamma.ctypes.data,
                              Y_res=y_res.ctypes.data, inv_CtGammaC=inv.ctypes.data,
-                             keep_idx=None if keep_idx is None else keep_idx.ctypes.data)
+                             keep_idx=None if keep_idx is None else keep_idx.ctypes.data,
+                             Q=None if Q is None else Q.ctypes.data)
         _capi.check(self._lib.glr_logreg_state_create(C_.byref(d), C_.byref(self._handle)))
 
     def run(self, block, contig: int = 0):
@@ -179,9 +191,11 @@ def logistic_regression(genotype_df,
 
     Arguments, defaults and output columns are the reference's; ``device`` is the only addition.  ``genotype_df`` is a
     pandas DataFrame, an iterable of pandas DataFrames, or a :class:`glow_b200.sources.GenotypeSource`.
-    ``correction='none'`` runs entirely on the device.  The approximate Firth correction (log_reg.py:330-348,
-    approx_firth.py) is a per-significant-variant CPU refinement in the reference and is not part of this build:
-    asking for it raises NotImplementedError instead of silently returning uncorrected statistics.
+    The score test of every (variant, phenotype) runs on the device.  With ``correction='approx-firth'`` (the
+    reference's default) the tests whose p-value is below ``pvalue_threshold`` are then refitted with the approximate
+    Firth method on the host, one variant at a time, exactly as the reference does (log_reg.py:330-348,
+    approx_firth.py); it needs the genotype values on the host, so it takes pandas / array / ``.bed`` input but not
+    blocks that only live in device memory (``ResidentSource``, ``BgenSource``).
     """
     if correction not in (correction_none, correction_approx_firth):
         raise ValueError(f"Only supported correction methods are '{correction_none}' and '{correction_approx_firth}'")
@@ -189,10 +203,6 @@ def logistic_regression(genotype_df,
     np_dt = gwas_fx._regression_dtype(dt)
     if isinstance(values_column, str) and values_column == gwas_fx._GENOTYPES_COLUMN_NAME:
         raise ValueError(f'The values column should not be called "{gwas_fx._GENOTYPES_COLUMN_NAME}"')
-    if correction == correction_approx_firth:
-        raise NotImplementedError("correction='approx-firth' is not available in glow_b200 (the score test, "
-                                  "correction='none', runs on the GPU); pass correction='none'")
-
     gt_indices_to_drop = None
     _covs = covariate_df
     if intersect_samples:  # log_reg.py:117-124
@@ -212,7 +222,12 @@ def logistic_regression(genotype_df,
         Cmat = gwas_fx._add_intercept(Cmat, phenotype_df.shape[0])
     if Cmat.size == 0:
         raise ValueError('logistic_regression needs at least one covariate column (or add_intercept=True)')
-    state = _create_log_reg_state(phenotype_df, offset_df, Cmat, contigs)
+    firth = correction == correction_approx_firth
+    Q = np.linalg.qr(Cmat)[0] if firth else None  # log_reg.py:133-136
+    Y = phenotype_df.to_numpy(np.float64, copy=True)
+    Y_mask = ~np.isnan(Y)
+    np.nan_to_num(Y, copy=False)
+    state = _create_log_reg_state(phenotype_df, offset_df, Cmat, contigs, correction, add_intercept)
     phenotype_names = phenotype_df.columns.to_series().astype('str')
 
     states = list(state.values()) if isinstance(state, dict) else [state]
@@ -223,7 +238,7 @@ def logistic_regression(genotype_df,
         k = np.ones(n_geno, dtype=bool)
         k[np.asarray(gt_indices_to_drop, dtype=np.int64)] = False
         keep = np.flatnonzero(k).astype(np.int64)
-    engine = LogRegDeviceState(Cmat, states, keep_idx=keep, n_geno_samples=n_geno, device=device)
+    engine = LogRegDeviceState(Cmat, states, keep_idx=keep, n_geno_samples=n_geno, device=device, Q=Q)
 
     from ..sources import GenotypeSource
 
@@ -256,14 +271,67 @@ def logistic_regression(genotype_df,
                     groups.append((meta[sel], sub, contig_index[contig]))
             for m, blk, ci in groups:
                 res = engine.run(blk, ci)
+                if firth:
+                    _apply_firth(res, blk, states[ci], Y, Y_mask, Q, keep, n_geno, pvalue_threshold)
                 parts.append(_assemble(m, res, phenotype_names, np_dt))
     finally:
         engine.close()
+    result_cols = (['effect', 'stderror', 'correctionSucceeded'] if firth else []) + ['chisq', 'pvalue', 'phenotype']  # log_reg.py:95-108
     if not parts:
-        return pd.DataFrame(columns=['chisq', 'pvalue', 'phenotype'])
+        return pd.DataFrame(columns=result_cols)
     out = pd.concat(parts) if len(parts) > 1 else parts[0]
-    passthrough = [c for c in out.columns if c not in ('chisq', 'pvalue', 'phenotype')]
-    return out[passthrough + ['chisq', 'pvalue', 'phenotype']]
+    passthrough = [c for c in out.columns if c not in result_cols]
+    return out[passthrough + result_cols]
+
+
+def _apply_firth(res, block, state, Y, Y_mask, Q, keep, n_geno, pvalue_threshold):
+    """log_reg.py:330-348: tests below the threshold are refitted with the approximate Firth method (host)."""
+    P, G = res['chisq'].shape
+    res['effect'] = np.full((P, G), np.nan)
+    res['stderror'] = np.full((P, G), np.nan)
+    res['correctionSucceeded'] = np.full((P, G), None, dtype=object)
+    flagged = np.argwhere(res['pvalue'] < pvalue_threshold)
+    if not len(flagged):
+        return
+    X = None
+    cache = {}
+    for p, g in flagged:
+        if g not in cache:
+            if X is None:
+                X = _decode_for_firth(block, n_geno, keep)
+            x = X[g]
+            cache[g] = x - Q @ (Q.T @ x)  # the linear residualisation of log_reg.py:312-313
+        fit = af.correct_approx_firth(cache[g], Y[:, p], state.firth_offset[:, p], Y_mask[:, p])
+        if fit is None:
+            res['correctionSucceeded'][p, g] = False
+        else:
+            res['correctionSucceeded'][p, g] = True
+            res['effect'][p, g], res['stderror'][p, g] = fit.effect, fit.stderror
+            res['chisq'][p, g], res['pvalue'][p, g] = fit.chisq, fit.pvalue
+
+
+def _decode_for_firth(block, n_geno, keep) -> np.ndarray:
+    """float64 [G, N] genotype values of a host block as the regression sees them, in phenotype-row order: 2-bit decode
+    (PlinkRowToInternalRowConverter.scala:40-47 + genotype_states), mean substitution over ALL genotype samples
+    (MeanSubstitute.scala:57-84; the values column is evaluated before np.delete), then the dropped samples removed
+    (log_reg.py:303-304)."""
+    if isinstance(block, ResidentBlock):
+        raise NotImplementedError("correction='approx-firth' needs the genotype values on the host: it does not take blocks "
+                                  "that live only in device memory (ResidentSource / BgenSource)")
+    data = block.data
+    if block.format == 'plink2':
+        codes = np.empty((data.shape[0], data.shape[1] * 4), dtype=np.uint8)
+        for j in range(4):
+            codes[:, j::4] = (data >> (2 * j)) & 3
+        X = np.array([2.0, -1.0, 1.0, 0.0])[codes[:, :n_geno]]
+    else:
+        X = np.array(data, dtype=np.float64)
+    if block.format in ('plink2', 'i8') and block.missing == 'mean':
+        for row in X:
+            miss = row == -1.0
+            if miss.any() and not miss.all():
+                row[miss] = row[~miss].sum() / (row.size - miss.sum())
+    return X if keep is None else X[:, keep]
 
 
 def _validate_binary(covariate_df, phenotype_df, intersect_samples):
@@ -285,6 +353,10 @@ def _assemble(meta: pd.DataFrame, res, phenotype_names, out_dt) -> pd.DataFrame:
     G = meta.shape[0]
     P = res['chisq'].shape[0]
     cols = {c: np.tile(meta[c].to_numpy(), P) for c in meta.columns}
+    if 'effect' in res:  # approx-firth columns (log_reg.py:95-101)
+        cols['effect'] = np.ravel(res['effect']).astype(out_dt, copy=False)
+        cols['stderror'] = np.ravel(res['stderror']).astype(out_dt, copy=False)
+        cols['correctionSucceeded'] = np.ravel(res['correctionSucceeded'])
     cols['chisq'] = np.ravel(res['chisq']).astype(out_dt, copy=False)
     cols['pvalue'] = np.ravel(res['pvalue']).astype(out_dt, copy=False)
     cols['phenotype'] = np.repeat(np.asarray(list(phenotype_names), dtype=object), G)

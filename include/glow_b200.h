@@ -195,6 +195,9 @@ typedef struct glr_logreg_desc {
   const double* Y_res;       /* [contigs][N x P]  LogRegState.Y_res = y - yhat, 0 where missing */
   const double* inv_CtGammaC;/* [contigs][P][K x K] LogRegState.inv_CtGammaC */
   const int64_t* keep_idx;   /* [N] genotype-array index of each phenotype row (np.delete, log_reg.py:303-304) or NULL */
+  const double* Q;           /* [N x K] orthonormal basis of C (np.linalg.qr(C)[0], log_reg.py:134) or NULL.  Non-NULL =
+                                correction 'approx-firth': the genotypes are first residualised linearly, X - Q Q^T X
+                                (log_reg.py:312-313), and the score test runs on that (K <= 64) */
 } glr_logreg_desc;
 int glr_logreg_state_create(const glr_logreg_desc* desc, glr_logreg_state** out);
 int glr_logreg_state_destroy(glr_logreg_state* st);

@@ -385,8 +385,38 @@ def golden_logreg():
         arrays[f'{name}/ref_chisq'] = out['chisq'].to_numpy(np.float64).reshape(P, G)
         arrays[f'{name}/ref_pvalue'] = out['pvalue'].to_numpy(np.float64).reshape(P, G)
         assert list(out['phenotype'][:G]) == ['t0'] * G
+    # correction='approx-firth': score test on linearly residualised genotypes + Firth refits below the threshold
+    firth_cases = {
+        'firth': dict(N=120, G=24, P=2, K=3, missing=0.0, offset=False, threshold=0.2),
+        'firth_missing_offset': dict(N=150, G=30, P=3, K=2, missing=0.08, offset=True, threshold=0.3),
+    }
+    for name, c in firth_cases.items():
+        N, G, P, K = c['N'], c['G'], c['P'], c['K']
+        X = rg.binomial(2, rg.uniform(0.1, 0.5, (G, 1)), (G, N)).astype(np.float64)
+        cov = pd.DataFrame(rg.standard_normal((N, K)))
+        eta = 0.8 * (X[:P].T - X[:P].T.mean(axis=0)) - 0.5
+        Y = (rg.random((N, P)) < 1 / (1 + np.exp(-eta))).astype(np.float64)
+        if c['missing']:
+            Y[rg.random((N, P)) < c['missing']] = np.nan
+        phe = pd.DataFrame(Y, columns=[f't{i}' for i in range(P)])
+        off = pd.DataFrame(0.3 * rg.standard_normal((N, P)), columns=phe.columns) if c['offset'] else None
+        out, score_p = refshim.reference_firth_test(X, phe, cov, pvalue_threshold=c['threshold'], offset_df=off)
+        arrays[f'{name}/X'] = X
+        arrays[f'{name}/phenotypes'] = Y
+        arrays[f'{name}/covariates'] = cov.to_numpy(np.float64)
+        arrays[f'{name}/intercept'] = np.array(1)
+        arrays[f'{name}/threshold'] = np.array(c['threshold'])
+        if off is not None:
+            arrays[f'{name}/offsets'] = off.to_numpy(np.float64)
+        for k in ('effect', 'stderror', 'chisq', 'pvalue'):
+            arrays[f'{name}/ref_{k}'] = out[k].to_numpy(np.float64).reshape(P, G)
+        arrays[f'{name}/ref_score_pvalue'] = score_p.reshape(P, G)
+        arrays[f'{name}/ref_succeeded'] = np.array([-1 if v is None else int(v) for v in out['correctionSucceeded']]).reshape(P, G)
+        n_corr = int((arrays[f'{name}/ref_succeeded'] >= 0).sum())
+        assert 0 < n_corr < P * G, n_corr
+        print(f'firth case {name}: {n_corr} of {P * G} tests corrected')
     np.savez_compressed(os.path.join(OUT, 'logreg_cases.npz'), **arrays)
-    print('logreg golden cases:', ', '.join(cases))
+    print('logreg golden cases:', ', '.join(list(cases) + list(firth_cases)))
 
 
 if __name__ == '__main__':

@@ -388,3 +388,54 @@ def load_wgr():
             else:
                 sys.modules[name] = old
     return _loaded_wgr
+
+
+def reference_firth_test(genotype_matrix, phenotype_df, covariate_df, pvalue_threshold=0.05, add_intercept=True, offset_df=None):
+    """correction='approx-firth' through the reference: state rows from ``_prepare_one_phenotype`` (null Firth fit included),
+    ONE block through ``_logistic_regression_inner`` -- which residualises the genotypes against Q and runs the score
+    test -- and then the correction loop of log_reg.py:330-348 restated: under pandas 3 its chained assignments
+    (``out_df.effect.iloc[i] = ...``) no longer write into ``out_df`` (copy-on-write), so the reference's own
+    ``approx_firth.correct_approx_firth`` is applied here to the same rows it would have been applied to."""
+    import warnings
+    import pandas as pd
+    fx, _ = load()
+    lr = load_logreg()
+    af = sys.modules.get('glow.gwas.approx_firth') or lr.af
+    C = covariate_df.to_numpy(copy=True)
+    if add_intercept:
+        C = fx._add_intercept(C, phenotype_df.shape[0])
+    Y = phenotype_df.to_numpy(copy=True)
+    Y_mask = ~np.isnan(Y)
+    Y[~Y_mask] = 0
+    Q = np.linalg.qr(C)[0]
+    rows = []
+    for p in phenotype_df:
+        d = {'label': p, 'values': phenotype_df[p].to_numpy(copy=True)}
+        if offset_df is not None:
+            d['offset'] = offset_df[p].to_numpy(copy=True)
+        rows.append(lr._prepare_one_phenotype(C, pd.Series(d), lr.correction_approx_firth, add_intercept))
+    names = phenotype_df.columns.to_series().astype('str')
+    state = lr._pdf_to_log_reg_state(pd.DataFrame(rows), names, C.shape[1])
+    Xg = np.asarray(genotype_matrix, dtype=np.float64)
+    values_df = pd.DataFrame({fx._VALUES_COLUMN_NAME: list(Xg.copy())})
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out = lr._logistic_regression_inner(values_df, state, C, Y, Y_mask, Q, lr.correction_approx_firth, pvalue_threshold,
+                                            names, None)
+    out = out.reset_index(drop=True)
+    G = Xg.shape[0]
+    X = Xg.T.copy()
+    X = fx._residualize_in_place(X, Q)
+    eff, se, ok = np.full(len(out), np.nan), np.full(len(out), np.nan), np.full(len(out), None, dtype=object)
+    chisq, pv = out['chisq'].to_numpy(dtype=np.float64).copy(), out['pvalue'].to_numpy(dtype=np.float64).copy()
+    score_p = pv.copy()
+    for i in np.where(score_p < pvalue_threshold)[0]:
+        snp, ph = i % G, int(i / G)
+        fit = af.correct_approx_firth(X[:, snp], Y[:, ph], state.firth_offset[:, ph], Y_mask[:, ph])
+        if fit is None:
+            ok[i] = False
+        else:
+            ok[i] = True
+            eff[i], se[i], chisq[i], pv[i] = fit.effect, fit.stderror, fit.chisq, fit.pvalue
+    return pd.DataFrame({'effect': eff, 'stderror': se, 'correctionSucceeded': ok, 'chisq': chisq, 'pvalue': pv,
+                         'phenotype': out['phenotype'].to_numpy()}), score_p

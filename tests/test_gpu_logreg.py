@@ -117,3 +117,65 @@ def test_c_abi_logreg_errors(rg):
     assert lib.glr_logreg_state_create(C.byref(d), C.byref(h)) == _capi.ERR_INVALID
     assert b'dimensions' in lib.glr_last_error()
     assert lib.glr_logreg_state_destroy(None) == 0
+
+
+@pytest.mark.parametrize('name', ['firth', 'firth_missing_offset'])
+def test_approx_firth_reference_fixtures(name):
+    """correction='approx-firth' (the reference's default): score test on linearly residualised genotypes on the device,
+    Firth refits of the tests below the threshold on the host; fixtures from the reference's log_reg.py + approx_firth.py."""
+    import glow_b200
+    c = load_cases()[name]
+    phe, cov, off, icpt = case_frames(c)
+    G, P = c['X'].shape[0], phe.shape[1]
+    pdf = pd.DataFrame({'values': list(c['X']), 'idx': np.arange(G)})
+    out = glow_b200.gwas.logistic_regression(pdf, phe, cov, off if off is not None else pd.DataFrame({}),
+                                             pvalue_threshold=float(c['threshold']), add_intercept=icpt)
+    assert out.columns.tolist() == ['idx', 'effect', 'stderror', 'correctionSucceeded', 'chisq', 'pvalue', 'phenotype']
+    got_ok = np.array([-1 if v is None else int(v) for v in out['correctionSucceeded']]).reshape(P, G)
+    assert np.array_equal(got_ok, c['ref_succeeded'])
+    for k, rtol in (('chisq', 1e-8), ('pvalue', 1e-6), ('effect', 1e-8), ('stderror', 1e-8)):
+        g, r = out[k].to_numpy(np.float64).reshape(P, G), c[f'ref_{k}']
+        assert np.array_equal(np.isnan(g), np.isnan(r)), k
+        ok = ~np.isnan(r)
+        np.testing.assert_allclose(g[ok], r[ok], rtol=rtol, atol=1e-13, err_msg=k)
+
+
+def test_approx_firth_on_packed_blocks_and_linear_residualisation(rg):
+    """The score test of the approx-firth mode (genotypes residualised linearly first, folded into the device epilogue)
+    against the oracle fed with explicitly residualised genotypes, on 2-bit and int8 blocks; the Firth refit decodes
+    the flagged rows on the host.  Device-only blocks are refused."""
+    import glow_b200
+    from glow_b200.gwas.log_reg import LogRegDeviceState
+    from glow_b200.engine import GenotypeBlock
+    N, G, P, K = 700, 90, 2, 5
+    states = rg.binomial(2, rg.uniform(0.1, 0.5, (G, 1)), (G, N)).astype(np.int64)
+    states[rg.random((G, N)) < 0.02] = -1
+    cov = pd.DataFrame(rg.standard_normal((N, K)) * 0.5)
+    Y = (rg.random((N, P)) < 0.35).astype(np.float64)
+    Y[rg.random((N, P)) < 0.05] = np.nan
+    phe = pd.DataFrame(Y, columns=['a', 'b'])
+    C, mask, st = lo.prepare_state(phe, cov)
+    Q = np.linalg.qr(C)[0]
+    X = orc.mean_substitute(states.astype(np.float64))
+    Xl = (X.T - Q @ (Q.T @ X.T)).T
+    ref = lo.block_score_test(Xl, C, mask, st)
+    eng = LogRegDeviceState(C, [st], Q=Q)
+    _close(eng.run(GenotypeBlock(pack_plink(states), 'plink2', 'mean')), ref, 'lin-residualised plink2')
+    _close(eng.run(GenotypeBlock(states.astype(np.int8), 'i8', 'mean')), ref, 'lin-residualised i8')
+    _close(eng.run(GenotypeBlock(X, 'f64')), ref, 'lin-residualised f64')
+    eng.close()
+    bed = bytes([0x6c, 0x1b, 0x01]) + pack_plink(states).tobytes()
+    meta = pd.DataFrame({'idx': np.arange(G)})
+    a = glow_b200.gwas.logistic_regression(glow_b200.PlinkBedSource(bed, N, meta, block_variants=40), phe, cov, pvalue_threshold=0.2)
+    pdf = meta.copy()
+    pdf['values'] = list(X)
+    b = glow_b200.gwas.logistic_regression(pdf, phe, cov, pvalue_threshold=0.2)
+    key = lambda d: d.sort_values(['phenotype', 'idx'], kind='stable').reset_index(drop=True)
+    a, b = key(a), key(b)
+    assert a['correctionSucceeded'].tolist() == b['correctionSucceeded'].tolist() and a['correctionSucceeded'].notna().sum() > 0
+    for k in ('effect', 'stderror', 'chisq', 'pvalue'):
+        np.testing.assert_allclose(a[k].to_numpy(np.float64), b[k].to_numpy(np.float64), rtol=1e-7, atol=1e-13, equal_nan=True)
+    res = glow_b200.ResidentSource(glow_b200.PlinkBedSource(bed, N, meta), devices=[0])
+    with pytest.raises(NotImplementedError, match='host'):
+        glow_b200.gwas.logistic_regression(res, phe, cov, pvalue_threshold=0.9)
+    res.close()

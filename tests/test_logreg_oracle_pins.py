@@ -117,5 +117,36 @@ def test_product_null_fit_matches_oracle(rg):
         plr.logistic_regression(pd.DataFrame({'values': [np.zeros(N)]}), phe + 0.5, cov, correction='none')
     with pytest.raises(ValueError, match='correction methods'):
         plr.logistic_regression(pd.DataFrame({'values': [np.zeros(N)]}), phe, cov, correction='bogus')
-    with pytest.raises(NotImplementedError):
-        plr.logistic_regression(pd.DataFrame({'values': [np.zeros(N)]}), phe, cov)
+
+
+@pytest.mark.parametrize('name', ['firth', 'firth_missing_offset'])
+def test_host_firth_port_reproduces_reference_fixtures(name):
+    """The product's host-side approximate Firth refit (glow_b200/gwas/approx_firth.py) against fixtures produced by the
+    reference's own approx_firth.py: null fit offsets, per-variant refits, failure flags.  The score statistics that
+    select the tests come from the oracle here (the GPU suite takes them from the device)."""
+    from glow_b200.gwas import approx_firth as paf
+    c = load_cases()[name]
+    phe, cov, off, icpt = case_frames(c)
+    thr = float(c['threshold'])
+    C, mask, st = lo.prepare_state(phe, cov, off, add_intercept=icpt)
+    Q = np.linalg.qr(C)[0]
+    X = c['X']
+    Xl = (X.T - Q @ (Q.T @ X.T)).T  # log_reg.py:312-313
+    res = lo.block_score_test(Xl, C, mask, st)
+    np.testing.assert_allclose(res['pvalue'], c['ref_score_pvalue'], rtol=1e-9)
+    Y = np.nan_to_num(c['phenotypes'])
+    P, G = res['chisq'].shape
+    for p in range(P):
+        o = None if off is None else off.iloc[:, p].to_numpy()
+        fo = paf.perform_null_firth_fit(Y[:, p], C, mask[:, p], o, icpt)
+        for g in range(G):
+            if res['pvalue'][p, g] >= thr:
+                assert c['ref_succeeded'][p, g] == -1
+                np.testing.assert_allclose(res['chisq'][p, g], c['ref_chisq'][p, g], rtol=1e-9)
+                continue
+            fit = paf.correct_approx_firth(Xl[g], Y[:, p], fo, mask[:, p])
+            assert (fit is not None) == bool(c['ref_succeeded'][p, g] == 1)
+            if fit is not None:
+                np.testing.assert_allclose([fit.effect, fit.stderror, fit.chisq, fit.pvalue],
+                                           [c['ref_effect'][p, g], c['ref_stderror'][p, g], c['ref_chisq'][p, g], c['ref_pvalue'][p, g]],
+                                           rtol=1e-8)
