@@ -321,12 +321,21 @@ def run_config(torch, dev, name, label, N, K_cov, P, G, fmt, hbm_peak, i8_peak, 
     Q, Y, mask, ydy, scale, dof = _prep_state(rg, N, K_cov, P, missing, n_contigs)
     st = DeviceState(Q=Q, Y=Y, Y_mask=mask, YdotY=ydy, Y_scale=scale, dof=dof, device=dev.index)
     del Y, mask
-    if fmt == 'plink2':
+    if fmt in ('plink2', 'i8'):
         global MISSING_RATE
         keep, MISSING_RATE = MISSING_RATE, call_missing
         X = gen_packed_device(torch, G, N, 5, dev)
         MISSING_RATE = keep
         stride = X.shape[1]
+        if fmt == 'i8':  # genotype_states as int8: unpack the 2-bit block on the device (00 -> 2, 01 -> -1, 10 -> 1, 11 -> 0)
+            lut = torch.tensor([2, -1, 1, 0], dtype=torch.int8, device=dev)
+            S8 = torch.empty((G, N), dtype=torch.int8, device=dev)
+            for g0 in range(0, G, 2048):
+                blk = X[g0:g0 + 2048].to(torch.int64)
+                codes = torch.stack([(blk >> (2 * j)) & 3 for j in range(4)], dim=2).reshape(blk.shape[0], -1)[:, :N]
+                S8[g0:g0 + 2048] = lut[codes]
+                del blk, codes
+            X, stride = S8, N
     else:
         X = torch.empty((G, N), dtype=torch.float64, device=dev)
         for g0 in range(0, G, 4096):
@@ -357,6 +366,7 @@ def run_config(torch, dev, name, label, N, K_cov, P, G, fmt, hbm_peak, i8_peak, 
     line = dict(config=label, N=N, K=K, P=P, variants_per_block=G, format=fmt, unique_masks=U, missing_call_rate=call_missing if fmt == 'plink2' else 0.0,
                 tests_per_s=P * G / (acc['total_ms'] / 1e3), block_ms=acc['total_ms'], blocks_timed=reps,
                 stage_ms={k: round(acc[k], 4) for k in ('prepass_ms', 'gram_ms', 'masked_ms', 'epilogue_ms')}, path_flags=int(path),
+                genotype_gbs=float(G) * stride / (acc['gram_ms'] / 1e3) / 1e9,
                 finite=float(torch.isfinite(outs['pvalue']).double().mean().item()))
     gram_s = acc['gram_ms'] / 1e3
     if path & _capi.PATH_SPLIT8:
@@ -394,6 +404,8 @@ def run_other_configs(torch, dev, hbm_peak, i8_peak):
          dict(N=500_000, K_cov=16, P=1, G=37_888, fmt='plink2', call_missing=0.0)),
         ('cfg2_missing_phenotype', 'configs[2] shape with 2 % of the phenotype values unobserved (masked second pass)',
          dict(N=500_000, K_cov=16, P=1, G=37_888, fmt='plink2', missing=0.02)),
+        ('cfg2_int8_states', 'configs[2] shape with genotype_states as int8 arrays (1 byte per genotype) on the int8 tensor path',
+         dict(N=500_000, K_cov=16, P=1, G=37_888, fmt='i8')),
         ('cfg2_spark_batch', 'configs[2] shape in blocks of 10 000 variants (Spark default Arrow batch, lin_reg.py:277-282): sample range split across CTAs',
          dict(N=500_000, K_cov=16, P=1, G=10_000, fmt='plink2')),
     ]

@@ -70,6 +70,7 @@ struct Lane {
   bool has_masked = false, has_prepass = false;
   bool optimistic = false;  // the block in flight runs the form without the missing-call operand
   bool counted = false;     // flags[1] of the block in flight is meaningful
+  bool checked = false;     // flags[0] must be read back at wait time
   glr_block_desc blk{};     // the block in flight (for the re-run of an optimistic block that had missing calls)
   glr_block_out blk_out{};
   int launches = 0;
@@ -611,8 +612,9 @@ static size_t row_bytes_of(int format, int64_t n) {
   }
 }
 
-// `replay`: second run of a block whose optimistic form met a missing call; its genotypes are already on the device
-static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, const glr_block_out* o, bool replay) {
+// `replay`: second run of a block whose first run was void (its genotypes are already on the device): 1 = the optimistic form
+// met a missing call -> full form; 2 = the int8 tensor-core form of an int8 block met a value outside {-1, 0, 1, 2} -> FP64 path
+static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, const glr_block_out* o, int replay) {
   if (!st || !b || !o) return fail(GLR_ERR_INVALID, "null argument");
   if (lane_id < 0 || lane_id >= (int)st->lanes.size()) return fail(GLR_ERR_INVALID, "lane out of range");
   Lane& L = st->lanes[lane_id];
@@ -637,6 +639,7 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   L.has_prepass = false;
   L.optimistic = false;
   L.counted = false;
+  L.checked = false;
   L.path = replay ? GLR_PATH_REPLAYED : 0;
   if (!replay) {
     L.blk = *b;
@@ -723,9 +726,13 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   // 30 TFLOP/s on the padded column count plus its pre-pass.
   bool use_split8 = false;
   Split8Plan plan;
-  if (st->split8 && b->format == GLR_FMT_PLINK2) {
+  // int8 genotype states take the same kernel (128 bytes per stage instead of 32, values checked on the fly) when the rows
+  // are 4-byte aligned
+  const bool i8_ok = b->format == GLR_FMT_I8 && replay != 2 &&
+                     ((reinterpret_cast<uintptr_t>(d_geno) | (uintptr_t)b->row_stride_bytes) & 3) == 0;
+  if (st->split8 && (b->format == GLR_FMT_PLINK2 || i8_ok)) {
     plan = split8_plan(G, st->s8_ncb, st->s8_stages, st->sm_count, st->s8_pair_mode, st->force_split);
-    const double t_s8 = plan.makespan_stages * 540.0 / 1.7e9 + (plan.n_split > 1 ? 8e-6 : 0.0);
+    const double t_s8 = plan.makespan_stages * (i8_ok ? 700.0 : 540.0) / 1.7e9 + (plan.n_split > 1 ? 8e-6 : 0.0);
     const double t_dmma = (double)G * (2.0 * (double)st->Ng * (double)Mpad / 30e12 + (double)st->Ng / 4.0 / 5e12) /
                               std::min(1.0, (double)(ctas * n_split) / st->sm_count) + 10e-6;
     use_split8 = st->split8 >= 2 || t_s8 < t_dmma;
@@ -733,7 +740,7 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   const bool fused_counts = use_split8 && st->n_drop == 0;
   // optimistic form: no missing-call operand while the stream of blocks has shown no missing call (validated in the
   // kernel; a violation re-runs the block at wait time)
-  const bool optimistic = use_split8 && fused_counts && !replay && st->optimistic_mode != GLR_OFF && !st->expect_missing;
+  const bool optimistic = use_split8 && fused_counts && replay == 0 && st->optimistic_mode != GLR_OFF && !st->expect_missing;
   if (scrub) {
     launch_zero_dropped(d_geno, b->row_stride_bytes, G, b->format, st->drop_idx, st->n_drop, s);
     ++L.launches;
@@ -794,6 +801,7 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
     launch_split8(sp, st->sm_count, s);
     L.optimistic = optimistic;
     L.counted = fused_counts;
+    L.checked = fused_counts || b->format == GLR_FMT_I8;
     L.path |= GLR_PATH_SPLIT8 | (plan.pair ? GLR_PATH_SPLIT8_PAIR : 0) | (plan.n_split > 1 ? GLR_PATH_SPLIT8_NSPLIT : 0) |
               (optimistic ? GLR_PATH_OPTIMISTIC : 0);
     if (plan.n_split > 1) L.launches += 1;
@@ -958,14 +966,14 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
     for (int i = 0; i < n_out; ++i)
       CU(cudaMemcpyAsync(outs[i], d_outs[i], out_elems * 8, cudaMemcpyDeviceToHost, s));
   }
-  if (L.counted) CU(cudaMemcpyAsync(L.h_flags, L.flags.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (L.checked) CU(cudaMemcpyAsync(L.h_flags, L.flags.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(L.ev[5], s));
   L.busy = true;
   return 0;
 }
 
 int glr_block_submit(glr_state* st, int lane_id, const glr_block_desc* b, const glr_block_out* o) {
-  return submit_impl(st, lane_id, b, o, false);
+  return submit_impl(st, lane_id, b, o, 0);
 }
 
 int glr_block_wait(glr_state* st, int lane_id) {
@@ -975,17 +983,26 @@ int glr_block_wait(glr_state* st, int lane_id) {
   if (!L.busy) return fail(GLR_ERR_STATE, "no block in flight on this lane");
   CU(cudaSetDevice(st->device));
   CU(cudaStreamSynchronize(L.stream));
-  if (L.counted) {
-    if (L.optimistic && L.h_flags[0] != 0) {
-      // the block had missing calls after all: its results are void; run it again in the full form
-      st->expect_missing = true;
-      if (int rc = submit_impl(st, lane_id, &L.blk, &L.blk_out, true)) {
+  if (L.checked) {
+    // void results: an int8 block with values outside {-1, 0, 1, 2} goes to the FP64 path (any int8 value is legal there);
+    // an optimistic block that had missing calls after all is run again in the full form
+    const int redo = (L.h_flags[0] & 2) ? 2 : ((L.optimistic && (L.h_flags[0] & 1)) ? 1 : 0);
+    if (redo) {
+      if (redo == 1) st->expect_missing = true;
+      if (int rc = submit_impl(st, lane_id, &L.blk, &L.blk_out, redo)) {
         L.busy = false;
         return rc;
       }
       CU(cudaStreamSynchronize(L.stream));
+      if ((L.h_flags[0] & 2) && redo == 1) {  // (both at once: the full form found bad values too)
+        if (int rc = submit_impl(st, lane_id, &L.blk, &L.blk_out, 2)) {
+          L.busy = false;
+          return rc;
+        }
+        CU(cudaStreamSynchronize(L.stream));
+      }
     }
-    if (!L.optimistic) st->expect_missing = L.h_flags[1] != 0;
+    if (L.counted && !L.optimistic) st->expect_missing = L.h_flags[1] != 0;
   }
   L.busy = false;
   glr_timing t{};

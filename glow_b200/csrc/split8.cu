@@ -187,6 +187,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
       "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -253,7 +258,10 @@ __device__ long long g_s8_prof[160][3][8];  // [cta][issuer 0 / issuer 1 / decod
 // completion is multicast to both.
 // kNoE: "optimistic" form for blocks expected to have no missing call: no indicator operand, no De MMAs (half the tensor
 // work).  The decode still checks every code; a missing call raises *p.flags and the host re-runs the block in the full form.
-template <int kAlign, bool kPair, bool kNoE>
+// kFmt: GLR_FMT_PLINK2 (2-bit rows, 32 bytes per stage) or GLR_FMT_I8 (genotype_states as int8, 128 bytes per stage; kAlign = 16
+// or 4).  The int8 form assumes values in {-1, 0, 1, 2}; it checks every byte while decoding and raises *p.flags |= 2 when
+// it meets anything else, upon which the host re-runs the block on the FP64 path (any int8 value is legal there).
+template <int kAlign, bool kPair, bool kNoE, int kFmt = GLR_FMT_PLINK2>
 __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NC = p.NC;
@@ -437,15 +445,49 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
     uint32_t g0 = 0;
     int icount = 0;
     uint32_t miss_seen = 0;  // kNoE: OR of the code-01 bits met
+    uint32_t bad_seen = 0;   // int8 form: bits of bytes outside {-1, 0, 1, 2}
     for (int item = first_item; item < n_items; item += item_stride, ++icount) {
       int tile, cb, kbeg, kcnt;
       s8_item_split(item, n_tiles, p.n_cb, n_split, per, n_st_all, tile, cb, kbeg, kcnt);
       if (kPair) tile = tile * 2 + (int)rank;  // the pair's two 128-variant halves
       const int v = min(tile * kS8TileV + vloc, p.x.n_variants - 1);
       const uint8_t* row = p.x.base + (int64_t)v * p.x.stride;
-      uint32_t nxt[kS8Words + 1];
-      uint32_t sh_nxt;
+      constexpr int kIn = kFmt == GLR_FMT_I8 ? 32 : kS8Words + 1;  // input words held one stage ahead
+      uint32_t nxt[kIn];
+      uint32_t sh_nxt = 0;
       auto load = [&](int64_t k) {  // k = absolute stage
+        if constexpr (kFmt == GLR_FMT_I8) {
+          const int64_t s0 = k * kS8K;
+          if (s0 + kS8K <= n_geno) {
+            if (kAlign == 16) {
+              const uint4* q4 = reinterpret_cast<const uint4*>(row + s0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint4 t = __ldg(q4 + i);
+                nxt[4 * i] = t.x;
+                nxt[4 * i + 1] = t.y;
+                nxt[4 * i + 2] = t.z;
+                nxt[4 * i + 3] = t.w;
+              }
+            } else {
+              const uint32_t* qw = reinterpret_cast<const uint32_t*>(row + s0);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) nxt[i] = __ldg(qw + i);
+            }
+          } else {  // last stage of the row: samples beyond n_geno read as 0
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              uint32_t w = 0;
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                const int64_t off = s0 + i * 4 + b;
+                if (off < n_geno) w |= (uint32_t)__ldg(row + off) << (8 * b);
+              }
+              nxt[i] = w;
+            }
+          }
+          return;
+        }
         const int64_t b0 = k * 32;
         if (b0 + 4 * kS8Words + 3 <= full_bytes) {  // every word touched lies inside the whole bytes of the row
           const uint8_t* q8 = row + b0;
@@ -490,7 +532,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       int n00 = 0;
       const int k_first = (int)((grp ^ g0) & 1u);
       // a 128-byte line of the row feeds 4 stages: the group on the even stages pulls lines into L2 well ahead
-      if (k_first == 0) {
+      if (kFmt != GLR_FMT_I8 && k_first == 0) {
 #pragma unroll
         for (int l = 0; l < 4; ++l)
           if ((int64_t)kbeg * 32 + l * 128 < row_bytes) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (int64_t)kbeg * 32 + l * 128));
@@ -499,6 +541,47 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       for (int k = k_first; k < kcnt; k += 2) {
         const uint32_t g = g0 + (uint32_t)k;
         const int64_t ka = kbeg + k;
+        const uint32_t sa = g & (kAR - 1);
+        const uint32_t a_x = lane_addr + kS8ColA + sa * kASlot, a_e = a_x + 32;
+        if constexpr (kFmt == GLR_FMT_I8) {
+          // ---- int8 genotype states: 128 bytes of the row per stage.  The registers cannot hold a decoded stage next to
+          // the prefetched one, so the TMEM slot is awaited first and the stage is decoded and stored in four 32-sample parts.
+          uint32_t w[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = nxt[i];
+          if (k + 2 < kcnt) load(ka + 2);
+          if (g >= (uint32_t)kAR) {
+            uint64_t* bar = &sm->done[(g - kAR) & (kWR - 1)];
+            s8_wait_keep1(bar, ((g - kAR) >> kWRLog) & 1u, w);
+          }
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t xs8[8], es8[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // 16 samples = 4 input words -> 4 output words in the order of the 2-bit decode
+              const uint32_t* in = w + 8 * c + 4 * h;
+              uint32_t t[4];
+              asm("prmt.b32 %0, %1, %2, 0x6420;\n" : "=r"(t[0]) : "r"(in[0]), "r"(in[1]));  // samples 0, 2, 4, 6
+              asm("prmt.b32 %0, %1, %2, 0x6420;\n" : "=r"(t[1]) : "r"(in[2]), "r"(in[3]));  // 8, 10, 12, 14
+              asm("prmt.b32 %0, %1, %2, 0x7531;\n" : "=r"(t[2]) : "r"(in[0]), "r"(in[1]));  // 1, 3, 5, 7
+              asm("prmt.b32 %0, %1, %2, 0x7531;\n" : "=r"(t[3]) : "r"(in[2]), "r"(in[3]));  // 9, 11, 13, 15
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t e = (t[j] >> 7) & 0x01010101u;           // -1 = 0xFF: missing
+                const uint32_t u = t[j] ^ (e * 0xFFu);                   // missing -> 0, everything else unchanged
+                // anything but -1, 0, 1, 2: a value above 2 (bits 2..6, or bits 0 and 1 together), a negative one other than -1
+                bad_seen |= (u & 0xFCFCFCFCu) | (u & (u >> 1) & 0x01010101u) | (u & (e * 0xFFu));
+                n00 += __popc(u & 0x02020202u);                          // number of alternate-homozygous calls
+                xs8[4 * h + j] = u & 0x03030303u;
+                es8[4 * h + j] = e;
+                if (kNoE) miss_seen |= e;
+              }
+            }
+            tmem_st8(a_x + 8 * c, xs8);
+            if constexpr (!kNoE) tmem_st8(a_e + 8 * c, es8);
+          }
+        } else {
         S8_T(d0);
         uint32_t w[kS8Words];
 #pragma unroll
@@ -534,7 +617,6 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
             es[4 * i + 3] = s8_prmt(0x00000100u, od_hi);
           }
         }
-        const uint32_t sa = g & (kAR - 1);
         S8_T(d1);
         // the MMAs that read this TMEM slot last (stage g - ring depth) must have completed
         if (g >= (uint32_t)kAR) {
@@ -545,19 +627,11 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         }
         S8_T(d2);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t a_x = lane_addr + kS8ColA + sa * kASlot, a_e = a_x + 32;
         tmem_st16(a_x, xs);
         tmem_st16(a_x + 16, xs + 16);
         if constexpr (!kNoE) {
           tmem_st16(a_e, es);
           tmem_st16(a_e + 16, es + 16);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (kPair) s8_arrive_cta(&sm->full_a[sa], 0);
-          else mbar_arrive(&sm->full_a[sa]);
         }
 #ifdef GLR_S8_PROFILE
         if (warp == kS8FirstDecodeWarp && lane == 0) {
@@ -568,6 +642,14 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           S8_ACC(2, 5, 1, 0);
         }
 #endif
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair) s8_arrive_cta(&sm->full_a[sa], 0);
+          else mbar_arrive(&sm->full_a[sa]);
+        }
       }
       const int64_t vg = (int64_t)tile * kS8TileV + vloc;
       const bool v_ok = vg < p.x.n_variants;
@@ -652,7 +734,11 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       g0 += (uint32_t)kcnt;
     }
     if (kNoE) {
-      if (__any_sync(0xffffffffu, (miss_seen & 0x55555555u) != 0) && lane == 0) atomicOr(p.flags, 1);
+      const uint32_t m = kFmt == GLR_FMT_I8 ? miss_seen : (miss_seen & 0x55555555u);
+      if (__any_sync(0xffffffffu, m != 0) && lane == 0) atomicOr(p.flags, 1);
+    }
+    if (kFmt == GLR_FMT_I8) {
+      if (__any_sync(0xffffffffu, bad_seen != 0) && lane == 0) atomicOr(p.flags, 2);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -760,7 +846,8 @@ size_t split8_ws_bytes(int n_cb, int NC, int64_t ldS) { return (size_t)n_cb * 2 
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   if (p.x.n_variants <= 0) return;
   const uintptr_t misal = reinterpret_cast<uintptr_t>(p.x.base) | (uintptr_t)p.x.stride;
-  const int align = (misal & 7) == 0 ? 8 : ((misal & 3) == 0 ? 4 : 0);
+  const bool i8 = p.x.format == GLR_FMT_I8;
+  const int align = i8 ? ((misal & 15) == 0 ? 16 : 4) : ((misal & 7) == 0 ? 8 : ((misal & 3) == 0 ? 4 : 0));
   const int n_items1 = (p.x.n_variants + kS8TileV - 1) / kS8TileV * p.n_cb * p.n_split;
   const int n_items2 = (p.x.n_variants + 2 * kS8TileV - 1) / (2 * kS8TileV) * p.n_cb * p.n_split;
   bool pair = p.pair != 0;
@@ -773,10 +860,17 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   static long long zero[160][3][8];
   cudaMemcpyToSymbol(g_s8_prof, zero, sizeof(zero));
 #endif
+  using Kern = void (*)(const Split8Params);
+  auto pick = [&](bool pr) -> Kern {
+#define GLR_S8_K(A, F) (pr ? (no_e ? (Kern)split8_kernel<A, true, true, F> : (Kern)split8_kernel<A, true, false, F>) \
+                           : (no_e ? (Kern)split8_kernel<A, false, true, F> : (Kern)split8_kernel<A, false, false, F>))
+    if (i8) return align == 16 ? GLR_S8_K(16, GLR_FMT_I8) : GLR_S8_K(4, GLR_FMT_I8);
+    return align == 8 ? GLR_S8_K(8, GLR_FMT_PLINK2) : (align == 4 ? GLR_S8_K(4, GLR_FMT_PLINK2) : GLR_S8_K(0, GLR_FMT_PLINK2));
+#undef GLR_S8_K
+  };
   if (pair) {
     const size_t smem = (size_t)(no_e ? kS8WRingMax : kS8WRing) * (p.NC / 2) * kS8K + sizeof(Split8Smem) + 64;
-    auto kern = no_e ? (align == 8 ? split8_kernel<8, true, true> : (align ? split8_kernel<4, true, true> : split8_kernel<0, true, true>))
-                     : (align == 8 ? split8_kernel<8, true, false> : (align ? split8_kernel<4, true, false> : split8_kernel<0, true, false>));
+    Kern kern = pick(true);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * std::min(n_items2, sm_count / 2));
@@ -797,8 +891,7 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   }
   if (!pair) {
     const size_t smem = (size_t)kS8WRing * p.NC * kS8K + sizeof(Split8Smem) + 64;
-    auto kern = no_e ? (align == 8 ? split8_kernel<8, false, true> : (align ? split8_kernel<4, false, true> : split8_kernel<0, false, true>))
-                     : (align == 8 ? split8_kernel<8, false, false> : (align ? split8_kernel<4, false, false> : split8_kernel<0, false, false>));
+    Kern kern = pick(false);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<std::min(n_items1, sm_count), kS8Threads, smem, st>>>(p);
   }

@@ -372,3 +372,53 @@ def test_bgen_source_runs_on_the_device(rg, tmp_path, bits, compress):
     want = lo.block_score_test(orc.mean_substitute(states.astype(np.float64)), C, mask, lst)
     got = lo_out.sort_values(['phenotype', 'start'], kind='stable')
     np.testing.assert_allclose(got['chisq'].to_numpy(), want['chisq'].ravel(), rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize('N,G,P,K', [(1000, 300, 1, 16), (4100, 700, 3, 5), (2048, 129, 20, 16)])
+@pytest.mark.parametrize('pair', ['force', 'off'])
+def test_int8_states_on_the_int8_tensor_path(rg, N, G, P, K, pair):
+    """genotype_states as int8 (GLR_FMT_I8) through split8_kernel: same digit-split contraction, 128 bytes of the row per
+    stage.  The kernel checks every value; a block with anything outside {-1, 0, 1, 2} is re-run on the FP64 path, where
+    any int8 value is legal."""
+    from glow_b200 import _capi
+    from glow_b200.engine import DeviceState, GenotypeBlock
+    states = rg.integers(0, 3, (G, N)).astype(np.int8)
+    states[rg.random((G, N)) < 0.03] = -1
+    states[:, :3] = [0, 1, 2]
+    cov = pd.DataFrame(rg.standard_normal((N, K)))
+    Y = rg.standard_normal((N, P))
+    Y[rg.random((N, P)) < 0.02] = np.nan
+    phe = pd.DataFrame(Y)
+    st = orc.prepare_state(phe, cov)
+    eng = DeviceState(Q=st.Q, Y=st.y_state.Y[None], Y_mask=st.Y_mask, YdotY=st.y_state.YdotY[None], Y_scale=st.Y_scale, dof=st.dof,
+                      options={'split8': 'force', 'split8_pair': pair})
+    for policy in ('mean', 'minus_one'):
+        X = states.astype(np.float64)
+        ref = orc.block_stats(orc.mean_substitute(X) if policy == 'mean' else X, st)
+        got = eng.run(GenotypeBlock(states, 'i8', policy))
+        path = eng.timing(0)['path']
+        assert path & _capi.PATH_SPLIT8 and not path & (_capi.PATH_DMMA | _capi.PATH_REPLAYED), path
+        assert_stats_close(got, ref, label=f'i8 on split8 {policy}')
+        # the same block as 2-bit rows gives the same bits (same kernel arithmetic, other decode)
+        got2 = eng.run(GenotypeBlock(pack_plink(states.astype(np.int64)), 'plink2', policy))
+        for k in STATS:
+            assert np.array_equal(got[k], got2[k], equal_nan=True), k
+    # rows that are not 4-byte aligned (odd sample count): the block takes the FP64 path
+    st3 = orc.prepare_state(phe.iloc[:N - 1], cov.iloc[:N - 1])
+    eng3 = DeviceState(Q=st3.Q, Y=st3.y_state.Y[None], Y_mask=st3.Y_mask, YdotY=st3.y_state.YdotY[None], Y_scale=st3.Y_scale,
+                       dof=st3.dof, options={'split8': 'force', 'split8_pair': pair})
+    odd = np.ascontiguousarray(states[:, :N - 1])
+    got = eng3.run(GenotypeBlock(odd, 'i8', 'mean'))
+    assert eng3.timing(0)['path'] & _capi.PATH_DMMA
+    assert_stats_close(got, orc.block_stats(orc.mean_substitute(odd.astype(np.float64)), st3), label='i8 unaligned rows')
+    eng3.close()
+    # values outside {-1, 0, 1, 2} (triploid call sums, say): detected in the kernel, block re-run on the FP64 path
+    wild = states.copy()
+    wild[5, 7] = 3
+    wild[G - 1, N - 1] = 4
+    wild[9, 100] = -2
+    got = eng.run(GenotypeBlock(wild, 'i8', 'minus_one'))
+    path = eng.timing(0)['path']
+    assert path & _capi.PATH_REPLAYED and path & _capi.PATH_DMMA, path
+    assert_stats_close(got, orc.block_stats(wild.astype(np.float64), st), label='i8 out of range -> FP64 path')
+    eng.close()
