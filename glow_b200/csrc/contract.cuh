@@ -357,6 +357,13 @@ struct XLoader<GLR_FMT_I8, NT> {
 // ------------------------------------------------------------------------------------------------
 // shared-memory ring
 // ------------------------------------------------------------------------------------------------
+// Release of a shared-memory stage that the consumers read with ordinary loads (generic proxy) and the producer refills
+// with cp.async.bulk (async proxy): the reads must be ordered before the refill ACROSS the proxies, which the mbarrier
+// hand-off alone does not do -- fence.proxy.async before the arrive.  Without it a refill occasionally overtook the last
+// reads of a stage: wrong values in single rows of S for one warp's 16 variants, a few times per 10^4 warps, seen only
+// with short-lived CTAs of the float64 kernels (found in round 2 by the permutation test of configs[1]).
+__device__ __forceinline__ void stage_release_fence() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 struct Ring {
   uint64_t* full;
   uint64_t* empty;
@@ -515,10 +522,13 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) gram_kernel(const GramPar
           for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, xb[nt]);
       }
     }
+    stage_release_fence();
     __syncwarp();
     if (lane == 0) mbar_arrive(&ring.empty[s]);
   }
 
+  // (no thread leaves with cp.async copies in flight: the loaders run a few units ahead of use)
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
   // C fragment: lane (r, j) holds rows r of each m-tile, variants 2j, 2j+1 of each n-tile
   double* Sz = p.S + (int64_t)blockIdx.z * p.s_slab;
 #pragma unroll
@@ -672,6 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) masked_kernel(const MaskedParams 
         }
       }
     }
+    stage_release_fence();
     __syncwarp();
     if (lane == 0) mbar_arrive(&ring.empty[s]);
   }

@@ -315,3 +315,26 @@ def test_adversarial_dynamic_range(form):
         res = eng.run(GenotypeBlock(packed, 'plink2', 'mean'), contig=ci)
         assert_stats_close(res, orc.block_stats(X, st, c), label=f'adversarial range, {form}, contig {c}')
     eng.close()
+
+
+def test_float64_blocks_are_reproducible_with_short_lived_ctas(rg):
+    """Regression for a cross-proxy hazard found in round 2: stages of the shared operand are read with ordinary loads and
+    refilled by cp.async.bulk; without a proxy fence before the release a refill occasionally overtook the last reads --
+    wrong rows for one warp's 16 variants, a few per 10^4 warps, only with short-lived CTAs of the float64 kernels (few
+    samples or a split sample range, many variants) and FMA tail columns.  The same block must give the same bits on every
+    run, and permuted variants permuted results."""
+    from glow_b200.engine import GenotypeBlock
+    N, G, P, K = 3328, 60_000, 7, 10
+    cov = pd.DataFrame(rg.standard_normal((N, K)))
+    X = rg.integers(0, 3, (G, N)).astype(np.float64) + 0.1 * rg.random((G, N), dtype=np.float32)
+    phe = pd.DataFrame(rg.standard_normal((N, P)))
+    for opts in ({}, {'sample_split': 3}):
+        eng, st = _engine_for(phe, cov, options=opts)
+        first = eng.run(GenotypeBlock(X, 'f64'))
+        for _ in range(5):
+            again = eng.run(GenotypeBlock(X, 'f64'))
+            for k in STATS:
+                assert np.array_equal(again[k], first[k], equal_nan=True), (k, opts)
+        idx = np.sort(rg.choice(G, 64, replace=False))
+        assert_stats_close({k: first[k][:, idx] for k in STATS}, orc.block_stats(X[idx], st), label='short CTAs')
+        eng.close()
