@@ -313,6 +313,16 @@ def _prep_state(rg, N, K_cov, P, missing=0.0, n_contigs=1):
     return Q, np.stack(Ys), mask, np.stack(ydys), scale, N - C.shape[1] - 1
 
 
+def digit_rows(n_q, n_y, path, unique_masks):
+    """Digit rows the int8 contraction of a block needed: 7 per phenotype-side column; per covariate column 7, or -- when
+    the block ran on the reduced-digit image (glr_options.q_digits = automatic) -- 6 if a masked pass follows, else 5."""
+    from glow_b200 import _capi
+    qd = 7
+    if path & _capi.PATH_Q_DIGITS_LO:
+        qd = int(os.environ.get('GLR_Q_DIGITS', '0')) or (6 if unique_masks > 0 else 5)
+    return qd * n_q + 7 * n_y
+
+
 def run_config(torch, dev, name, label, N, K_cov, P, G, fmt, hbm_peak, i8_peak, missing=0.0, n_contigs=1, call_missing=MISSING_RATE,
                min_seconds=0.3):
     from glow_b200 import _capi
@@ -371,11 +381,12 @@ def run_config(torch, dev, name, label, N, K_cov, P, G, fmt, hbm_peak, i8_peak, 
     gram_s = acc['gram_ms'] / 1e3
     if path & _capi.PATH_SPLIT8:
         operands = 1 if path & _capi.PATH_OPTIMISTIC else 2
-        ops = 2.0 * N * (7 * cols) * operands * G
+        ops = 2.0 * N * digit_rows(K - 1, cols - (K - 1), path, U) * operands * G
         line['roofline'] = dict(kernel='split8_kernel' + (' (optimistic form: no missing-call operand)' if operands == 1 else ''),
                                 bound='tensor', achieved=ops / gram_s / 1e12, peak=i8_peak, unit='TFLOP/s',
                                 frac=ops / gram_s / 1e12 / i8_peak if i8_peak == i8_peak else None,
-                                op_type='int8 tensor-core operations, algorithmic digit rows', share_of_block=acc['gram_ms'] / acc['total_ms'],
+                                op_type='int8 tensor-core operations, algorithmic digit rows',
+                                digit_rows=digit_rows(K - 1, cols - (K - 1), path, U), share_of_block=acc['gram_ms'] / acc['total_ms'],
                                 fp64_equivalent_tflops=2.0 * N * cols * G / gram_s / 1e12)
         if U and acc['masked_ms'] > 0:
             line['masked_pass'] = dict(ms=acc['masked_ms'], form='int8' if path & _capi.PATH_MASK_INT8 else
@@ -709,17 +720,20 @@ def main():
         flops_f64_equiv = 2.0 * n * cols * G                      # FP64 flops of the contraction as formulated
         flops_ref = float(n) * (4 * K + 4 * P + 2) * G            # reference formulation, SURVEY.md section 8(d)
         gram_s = stage['gram_ms'] / 1e3
-        # int8 digit-split kernel: 7 digit rows per column, two int8 operands (genotype, missing indicator)
-        ops_int8 = 2.0 * n * (7 * cols) * 2 * G
+        # int8 digit-split kernel: 7 digit rows per phenotype column, 5-7 per covariate column (what the block actually
+        # ran with), two int8 operands (genotype, missing indicator)
+        rows = digit_rows(K - 1, P, path, state.unique_masks)
+        ops_int8 = 2.0 * n * rows * 2 * G
         n_cb = -(-cols // 18)                                     # column blocks of up to 18 columns
-        nc_rows = -(-(7 * -(-cols // n_cb) + 1) // 16) * 16       # digit rows per block incl. the row of ones = MMA N
+        nc_rows = -(-((rows if n_cb == 1 else 7 * -(-cols // n_cb)) + 1) // 16) * 16  # rows per block incl. the ones = MMA N
         ops_int8_issued = 2.0 * (-(-n // 128) * 128) * nc_rows * n_cb * 2 * (-(-G // 128) * 128)
         achieved = ops_int8 / gram_s / 1e12
         default_shape = n == N_SAMPLES and G == 148 * 256
         roof = {
             'kernel': 'split8_kernel (tcgen05.mma.cta_group::2 kind::i8 on CTA pairs, A = decoded genotypes of 2 x 128 '
                       'variants in TMEM, B = digit rows split over the pair\'s shared memory, M256 N128 K32, accumulators in '
-                      'TMEM; exact 7-digit radix-256 split of the FP64 operand, '
+                      'TMEM; radix-256 digit split of the FP64 operand (7 digits per phenotype column, 5-7 per covariate '
+                      'column with a certified error bound per test), '
                       '2-bit decode + genotype counts fused, FP64 recombination in the epilogue)',
             'bound': 'tensor',
             'achieved': achieved,
@@ -743,10 +757,12 @@ def main():
                     '~1.9 GHz); MEASURED_PEAKS.json has no int8 entry -- 2 x its bf16 burst figure is given beside it. Under a real '
                     'load the board sits at its power cap and the SM clock drops (see clocks)',
             'ops_per_launch_algorithmic': ops_int8,
+            'digit_rows': rows,
+            'mma_n': nc_rows,
             'issued_tops_incl_padding': ops_int8_issued / gram_s / 1e12,
             'fp64_equivalent_tflops': flops_f64_equiv / gram_s / 1e12,
             'reference_equivalent_tflops': flops_ref / gram_s / 1e12,
-            'algorithmic_bytes_per_launch': float(G) * row_bytes + 7.0 * n * cols,
+            'algorithmic_bytes_per_launch': float(G) * row_bytes + float(n) * rows,
             'avg_launch_ms': stage['gram_ms'],
             'launches_timed': args.steps * B,
             'share_of_step': stage['gram_ms'] / max(stage['total_ms'], 1e-9),

@@ -27,8 +27,10 @@ def main():
              dict(GLR_MASK8='2', GLR_SPLIT8='2'), dict(GLR_MASK_SPARSE='2'), dict(GLR_MASK_SPARSE='0', GLR_MASK8='0'),
              # round 2: sample-range split of the int8 kernel, optimistic form (replayed when the block has missing calls)
              dict(GLR_SPLIT8='2', GLR_SPLIT='3'), dict(GLR_SPLIT8='2', GLR_S8_PAIR='0', GLR_SPLIT='2'),
-             dict(GLR_SPLIT8='2', GLR_OPTIMISTIC='2'), dict(GLR_SPLIT8='2', GLR_S8_PAIR='0', GLR_SPLIT='5', GLR_OPTIMISTIC='2')]
-    knobs = ('GLR_SPLIT8', 'GLR_S8_PAIR', 'GLR_MASK8', 'GLR_MASK_SPARSE', 'GLR_SPLIT', 'GLR_OPTIMISTIC')
+             dict(GLR_SPLIT8='2', GLR_OPTIMISTIC='2'), dict(GLR_SPLIT8='2', GLR_S8_PAIR='0', GLR_SPLIT='5', GLR_OPTIMISTIC='2'),
+             dict(GLR_SPLIT8='2', GLR_Q_DIGITS='7'), dict(GLR_SPLIT8='2', GLR_Q_DIGITS='3', GLR_SPLIT='2'),
+             dict(GLR_SPLIT8='2', GLR_Q_DIGITS='6', GLR_OPTIMISTIC='2')]
+    knobs = ('GLR_SPLIT8', 'GLR_S8_PAIR', 'GLR_MASK8', 'GLR_MASK_SPARSE', 'GLR_SPLIT', 'GLR_OPTIMISTIC', 'GLR_Q_DIGITS')
     done = 0
     for case in range(n_cases):
         N = int(rg.choice(edges_n))

@@ -17,6 +17,7 @@ ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = -1, -2, -3, -4
 AUTO, OFF, FORCE = 0, 1, 2  # glr_tristate
 PATH_SPLIT8, PATH_SPLIT8_PAIR, PATH_SPLIT8_NSPLIT, PATH_PREPASS, PATH_DMMA = 1, 2, 4, 8, 16
 PATH_MASK_SPARSE, PATH_MASK_INT8, PATH_MASK_DMMA, PATH_OPTIMISTIC, PATH_REPLAYED, PATH_MASK_GENERIC = 32, 64, 128, 256, 512, 1024
+PATH_Q_DIGITS_LO = 2048
 
 _dp = C.POINTER(C.c_double)
 
@@ -25,7 +26,7 @@ class Options(C.Structure):
     """glr_options: kernel-selection knobs, all zero = defaults."""
     _fields_ = [('split8', C.c_int32), ('split8_pair', C.c_int32), ('mask_sparse', C.c_int32), ('mask_int8', C.c_int32),
                 ('keep_intercept', C.c_int32), ('no_tail', C.c_int32), ('sample_split', C.c_int32),
-                ('optimistic_calls', C.c_int32)]
+                ('optimistic_calls', C.c_int32), ('q_digits', C.c_int32)]
 
 
 _TRI = {None: AUTO, 'auto': AUTO, 'off': OFF, 'never': OFF, 'force': FORCE, 'always': FORCE}
@@ -37,7 +38,7 @@ def make_options(opts=None) -> 'Options':
     for k, v in (opts or {}).items():
         if k not in dict(Options._fields_):
             raise ValueError(f'unknown option {k!r}')
-        if k in ('keep_intercept', 'no_tail', 'sample_split'):
+        if k in ('keep_intercept', 'no_tail', 'sample_split', 'q_digits'):
             setattr(o, k, int(v))
         else:
             if v not in _TRI:

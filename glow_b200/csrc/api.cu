@@ -68,7 +68,7 @@ struct Lane {
   int32_t* h_flags = nullptr;  // pinned mirror of `flags` ([0] optimistic form met a missing call, [1] missing calls of the block)
   bool busy = false;
   bool has_masked = false, has_prepass = false;
-  bool optimistic = false;  // the block in flight runs the form without the missing-call operand
+  bool optimistic = false, lo_digits = false;  // the block in flight runs the form without the missing-call operand
   bool counted = false;     // flags[1] of the block in flight is meaningful
   bool checked = false;     // flags[0] must be read back at wait time
   glr_block_desc blk{};     // the block in flight (for the re-run of an optimistic block that had missing calls)
@@ -87,6 +87,10 @@ int tri_knob(int32_t field, const char* env) {
   return (field == GLR_OFF || field == GLR_FORCE) ? field : GLR_AUTO;
 }
 bool flag_knob(int32_t field, const char* env) { return field != 0 || getenv(env) != nullptr; }
+int knob_int(int32_t field, const char* env) {
+  if (const char* e = getenv(env)) return atoi(e);
+  return field;
+}
 
 int pick_mt(int n_mtiles) {
   return n_mtiles < 1 ? 1 : (n_mtiles > 8 ? 8 : n_mtiles);
@@ -120,6 +124,13 @@ struct glr_state {
   int64_t s8_stages = 0, s8_contig_bytes = 0;
   int8_t* w8 = nullptr;       // [C][column block][stage][NC][128]
   double* s8_scale = nullptr; // [C][s8_cols]
+  // reduced-digit image: the Q columns with lo_digits digits (results certified per test, a block that fails is re-run
+  // on the full image); built when one column block holds all columns
+  int s8_n_lo = 0, s8_lo_digits = 7, s8_NC_lo = 0;
+  int64_t s8_contig_bytes_lo = 0;
+  int8_t* w8_lo = nullptr;
+  double* s8_scale_lo = nullptr;
+  int exact_hold = 0;  // blocks for which the full image is used after a failed certificate
   // masked pass
   int U = 0, MT2 = 1, n_groups2 = 0, KT2 = 0;
   double* qb = nullptr;
@@ -440,11 +451,25 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   const int split8_mode = tri_knob(d->opt.split8, "GLR_SPLIT8");
   if (split8_mode != GLR_OFF && st->Mcols > 0 && Ng < (int64_t)8000000 && Ng > 3 * 128) {  // >= 4 stages: one per issuer warp
     st->s8_cols = st->Mcols;
-    split8_geometry(st->s8_cols, &st->s8_ncb, &st->s8_cpb, &st->s8_NC);
+    split8_geometry(st->s8_cols, 0, 7, &st->s8_ncb, &st->s8_cpb, &st->s8_NC);
     st->s8_stages = ceil_div(Ng, 128);
     st->s8_contig_bytes = (int64_t)st->s8_ncb * st->s8_stages * st->s8_NC * 128;
     // the digit image costs about 7.1 bytes per W entry (the FP64 image costs 8): built while it fits 16 GiB
     if ((int64_t)C * st->s8_contig_bytes <= ((int64_t)16 << 30)) st->split8 = split8_mode == GLR_FORCE ? 2 : 1;
+    // reduced digits for the Q columns: 5 when every phenotype is fully observed, 6 when a masked pass follows (its
+    // certificate is looser); worth building only when it removes a 16-row step of the MMA N dimension
+    int qd = knob_int(d->opt.q_digits, "GLR_Q_DIGITS");
+    if (qd == 0) qd = st->U > 0 ? 6 : 5;
+    if (st->split8 && st->s8_ncb == 1 && Kg > 0 && qd >= 3 && qd < 7) {
+      int ncb, cpb, nc;
+      split8_geometry(st->s8_cols, Kg, qd, &ncb, &cpb, &nc);
+      if (nc < st->s8_NC && (int64_t)C * (st->s8_contig_bytes + st->s8_stages * nc * 128) <= ((int64_t)16 << 30)) {
+        st->s8_n_lo = Kg;
+        st->s8_lo_digits = qd;
+        st->s8_NC_lo = nc;
+        st->s8_contig_bytes_lo = st->s8_stages * nc * 128;
+      }
+    }
   }
   if (st->split8) {
     CU(st->alloc(&st->w8, (size_t)C * st->s8_contig_bytes));
@@ -452,6 +477,11 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     CU(st->alloc(&st->s8_scale, (size_t)C * st->s8_cols * sizeof(double)));
     CU(cudaMalloc(&d_colmax, (size_t)st->s8_cols * sizeof(double)));
     tmp.v.push_back(d_colmax);
+    if (st->s8_n_lo) {
+      CU(st->alloc(&st->w8_lo, (size_t)C * st->s8_contig_bytes_lo));
+      CU(cudaMemsetAsync(st->w8_lo, 0, (size_t)C * st->s8_contig_bytes_lo, s0));
+      CU(st->alloc(&st->s8_scale_lo, (size_t)C * st->s8_cols * sizeof(double)));
+    }
   }
   for (int c = 0; c < C; ++c) {
     double* dst = st->wpk + (int64_t)c * st->w_contig_doubles;
@@ -464,14 +494,17 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
     }
     launch_pack_a(dY, N, P, 0, P, d_g2r, Ng, dst, Kg, st->MT, st->tail, st->n_chunks, s0);
     if (st->split8) {
-      int8_t* d8 = st->w8 + (int64_t)c * st->s8_contig_bytes;
-      if (Kg > 0)
-        launch_pack_split8(dQ, N, K, st->has_icpt, Kg, d_colmax, d_g2r, Ng, d8, 0, st->s8_cpb, st->s8_NC, st->s8_stages, s0);
-      launch_pack_split8(dY, N, P, 0, P, d_colmax + Kg, d_g2r, Ng, d8, Kg, st->s8_cpb, st->s8_NC, st->s8_stages, s0);
-      if (st->verbose) {  // mask and raw-phenotype columns of the verbose outputs (lin_reg.py:234-237)
-        launch_pack_split8(dM, N, P, 0, P, d_colmax + Kg + P, d_g2r, Ng, d8, Kg + P, st->s8_cpb, st->s8_NC, st->s8_stages, s0);
-        launch_pack_split8(dYraw, N, P, 0, P, d_colmax + Kg + 2 * P, d_g2r, Ng, d8, Kg + 2 * P, st->s8_cpb, st->s8_NC,
-                           st->s8_stages, s0);
+      for (int img = 0; img < (st->s8_n_lo ? 2 : 1); ++img) {  // the full image, then the reduced-digit one
+        int8_t* d8 = img ? st->w8_lo + (int64_t)c * st->s8_contig_bytes_lo : st->w8 + (int64_t)c * st->s8_contig_bytes;
+        const int nc = img ? st->s8_NC_lo : st->s8_NC, n_lo = img ? st->s8_n_lo : 0, lo = st->s8_lo_digits;
+        if (Kg > 0)
+          launch_pack_split8(dQ, N, K, st->has_icpt, Kg, d_colmax, d_g2r, Ng, d8, 0, st->s8_cpb, nc, st->s8_stages, n_lo, lo, s0);
+        launch_pack_split8(dY, N, P, 0, P, d_colmax + Kg, d_g2r, Ng, d8, Kg, st->s8_cpb, nc, st->s8_stages, n_lo, lo, s0);
+        if (st->verbose) {  // mask and raw-phenotype columns of the verbose outputs (lin_reg.py:234-237)
+          launch_pack_split8(dM, N, P, 0, P, d_colmax + Kg + P, d_g2r, Ng, d8, Kg + P, st->s8_cpb, nc, st->s8_stages, n_lo, lo, s0);
+          launch_pack_split8(dYraw, N, P, 0, P, d_colmax + Kg + 2 * P, d_g2r, Ng, d8, Kg + 2 * P, st->s8_cpb, nc,
+                             st->s8_stages, n_lo, lo, s0);
+        }
       }
       CU(cudaMemcpyAsync(st->s8_scale + (int64_t)c * st->s8_cols, d_colmax, (size_t)st->s8_cols * sizeof(double),
                          cudaMemcpyDeviceToDevice, s0));
@@ -589,9 +622,15 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   }
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
-  if (st->split8) {  // scale_c = max|w_c| * 2^-54
-    std::vector<double> sc((size_t)C * st->s8_cols);
+  if (st->split8) {  // scale_c = max|w_c| * 2^-54 (2^-(8 d - 2) for a column with d digits)
+    std::vector<double> sc((size_t)C * st->s8_cols), lo;
     CU(cudaMemcpy(sc.data(), st->s8_scale, sc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (st->s8_n_lo) {
+      lo = sc;
+      for (size_t i = 0; i < lo.size(); ++i)
+        lo[i] = std::ldexp(lo[i], (int)(i % st->s8_cols) < st->s8_n_lo ? -(8 * st->s8_lo_digits - 2) : -54);
+      CU(cudaMemcpy(st->s8_scale_lo, lo.data(), lo.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     for (auto& v : sc) v = std::ldexp(v, -54);
     CU(cudaMemcpy(st->s8_scale, sc.data(), sc.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
@@ -612,8 +651,11 @@ static size_t row_bytes_of(int format, int64_t n) {
   }
 }
 
-// `replay`: second run of a block whose first run was void (its genotypes are already on the device): 1 = the optimistic form
-// met a missing call -> full form; 2 = the int8 tensor-core form of an int8 block met a value outside {-1, 0, 1, 2} -> FP64 path
+// `replay`: re-run of a block whose previous run was void (its genotypes are already on the device), a set of:
+//   kReplayFull  the optimistic form met a missing call -> form with the missing-call operand
+//   kReplayFp64  the int8 tensor-core form of an int8 block met a value outside {-1, 0, 1, 2} -> FP64 path
+//   kReplayExact a test failed the digit certificate of the reduced-digit image -> full 7-digit image
+enum { kReplayFull = 1, kReplayFp64 = 2, kReplayExact = 4 };
 static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, const glr_block_out* o, int replay) {
   if (!st || !b || !o) return fail(GLR_ERR_INVALID, "null argument");
   if (lane_id < 0 || lane_id >= (int)st->lanes.size()) return fail(GLR_ERR_INVALID, "lane out of range");
@@ -638,6 +680,7 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   L.has_masked = false;
   L.has_prepass = false;
   L.optimistic = false;
+  L.lo_digits = false;
   L.counted = false;
   L.checked = false;
   L.path = replay ? GLR_PATH_REPLAYED : 0;
@@ -699,7 +742,7 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
     if (int rc = L.s_part.ensure((size_t)n_split * Mpad * ldS * 8)) return rc;
   if (int rc = L.mom.ensure((size_t)2 * ldS * 8)) return rc;
   if (int rc = L.v1.ensure((size_t)ldS * 8)) return rc;
-  if (int rc = L.xx.ensure((size_t)ldS * 8)) return rc;
+  if (int rc = L.xx.ensure((size_t)3 * ldS * 8)) return rc;
   if (float_fmt && n_split > 1)
     if (int rc = L.mom_part.ensure((size_t)n_split * 2 * ldS * 8)) return rc;
   const int n_out = st->verbose ? 7 : 4;
@@ -728,7 +771,7 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   Split8Plan plan;
   // int8 genotype states take the same kernel (128 bytes per stage instead of 32, values checked on the fly) when the rows
   // are 4-byte aligned
-  const bool i8_ok = b->format == GLR_FMT_I8 && replay != 2 &&
+  const bool i8_ok = b->format == GLR_FMT_I8 && !(replay & kReplayFp64) &&
                      ((reinterpret_cast<uintptr_t>(d_geno) | (uintptr_t)b->row_stride_bytes) & 3) == 0;
   if (st->split8 && (b->format == GLR_FMT_PLINK2 || i8_ok)) {
     plan = split8_plan(G, st->s8_ncb, st->s8_stages, st->sm_count, st->s8_pair_mode, st->force_split);
@@ -740,7 +783,10 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   const bool fused_counts = use_split8 && st->n_drop == 0;
   // optimistic form: no missing-call operand while the stream of blocks has shown no missing call (validated in the
   // kernel; a violation re-runs the block at wait time)
-  const bool optimistic = use_split8 && fused_counts && replay == 0 && st->optimistic_mode != GLR_OFF && !st->expect_missing;
+  const bool optimistic = use_split8 && fused_counts && !(replay & (kReplayFull | kReplayFp64)) &&
+                          st->optimistic_mode != GLR_OFF && !st->expect_missing;
+  // reduced-digit image unless a certificate failed recently
+  const bool lo_digits = use_split8 && st->s8_n_lo > 0 && !(replay & kReplayExact) && st->exact_hold == 0;
   if (scrub) {
     launch_zero_dropped(d_geno, b->row_stride_bytes, G, b->format, st->drop_idx, st->n_drop, s);
     ++L.launches;
@@ -778,12 +824,15 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   if (use_split8) {
     Split8Params sp{};
     sp.x = x;
-    sp.w8 = st->w8 + (int64_t)b->contig * st->s8_contig_bytes;
-    sp.scale = st->s8_scale + (int64_t)b->contig * st->s8_cols;
+    sp.w8 = lo_digits ? st->w8_lo + (int64_t)b->contig * st->s8_contig_bytes_lo
+                      : st->w8 + (int64_t)b->contig * st->s8_contig_bytes;
+    sp.scale = (lo_digits ? st->s8_scale_lo : st->s8_scale) + (int64_t)b->contig * st->s8_cols;
     sp.n_cols = st->s8_cols;
     sp.n_cb = st->s8_ncb;
     sp.cpb = st->s8_cpb;
-    sp.NC = st->s8_NC;
+    sp.NC = lo_digits ? st->s8_NC_lo : st->s8_NC;
+    sp.n_lo = lo_digits ? st->s8_n_lo : 0;
+    sp.lo_digits = st->s8_lo_digits;
     sp.fused_counts = fused_counts ? 1 : 0;
     sp.missing_policy = b->missing_policy;
     sp.n_stages = st->s8_stages;
@@ -801,9 +850,10 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
     launch_split8(sp, st->sm_count, s);
     L.optimistic = optimistic;
     L.counted = fused_counts;
-    L.checked = fused_counts || b->format == GLR_FMT_I8;
+    L.lo_digits = lo_digits;
+    L.checked = fused_counts || b->format == GLR_FMT_I8 || lo_digits;
     L.path |= GLR_PATH_SPLIT8 | (plan.pair ? GLR_PATH_SPLIT8_PAIR : 0) | (plan.n_split > 1 ? GLR_PATH_SPLIT8_NSPLIT : 0) |
-              (optimistic ? GLR_PATH_OPTIMISTIC : 0);
+              (optimistic ? GLR_PATH_OPTIMISTIC : 0) | (lo_digits ? GLR_PATH_Q_DIGITS_LO : 0);
     if (plan.n_split > 1) L.launches += 1;
   } else {
     launch_gram(gp, s);
@@ -958,6 +1008,13 @@ static int submit_impl(glr_state* st, int lane_id, const glr_block_desc* b, cons
   ep.n = st->verbose ? d_outs[4] : nullptr;
   ep.sum_x = st->verbose ? d_outs[5] : nullptr;
   ep.ytx = st->verbose ? d_outs[6] : nullptr;
+  if (L.lo_digits) {
+    ep.lo_scale = st->s8_scale_lo + (int64_t)b->contig * st->s8_cols;
+    ep.sum_x_row = L.mom.as<double>() + ldS;
+    ep.n_lo = st->s8_n_lo;
+    ep.lo_row0 = st->has_icpt;
+    ep.flags = L.flags.as<int32_t>();
+  }
   launch_epilogue(ep, L.xx.as<double>(), s);
   L.launches += 2;
   CU(cudaEventRecord(L.ev[4], s));
@@ -985,25 +1042,27 @@ int glr_block_wait(glr_state* st, int lane_id) {
   CU(cudaStreamSynchronize(L.stream));
   if (L.checked) {
     // void results: an int8 block with values outside {-1, 0, 1, 2} goes to the FP64 path (any int8 value is legal there);
-    // an optimistic block that had missing calls after all is run again in the full form
-    const int redo = (L.h_flags[0] & 2) ? 2 : ((L.optimistic && (L.h_flags[0] & 1)) ? 1 : 0);
-    if (redo) {
-      if (redo == 1) st->expect_missing = true;
-      if (int rc = submit_impl(st, lane_id, &L.blk, &L.blk_out, redo)) {
+    // an optimistic block that had missing calls after all is run again in the full form; a block with a test whose digit
+    // certificate failed is run again on the 7-digit image.  Each re-run can only add conditions: at most 3 rounds.
+    int mode = 0;
+    for (int round = 0; round < 3 && L.checked; ++round) {
+      int need = mode;
+      if (L.h_flags[0] & 2) need |= kReplayFp64;
+      if (L.optimistic && (L.h_flags[0] & 1)) need |= kReplayFull;
+      if (L.lo_digits && (L.h_flags[0] & 4)) need |= kReplayExact;
+      if (need == mode) break;
+      mode = need;
+      if (mode & kReplayFull) st->expect_missing = true;
+      if (mode & kReplayExact) st->exact_hold = 32;
+      if (int rc = submit_impl(st, lane_id, &L.blk, &L.blk_out, mode)) {
         L.busy = false;
         return rc;
       }
       CU(cudaStreamSynchronize(L.stream));
-      if ((L.h_flags[0] & 2) && redo == 1) {  // (both at once: the full form found bad values too)
-        if (int rc = submit_impl(st, lane_id, &L.blk, &L.blk_out, 2)) {
-          L.busy = false;
-          return rc;
-        }
-        CU(cudaStreamSynchronize(L.stream));
-      }
     }
     if (L.counted && !L.optimistic) st->expect_missing = L.h_flags[1] != 0;
   }
+  if (!(L.path & GLR_PATH_REPLAYED) && st->exact_hold > 0) --st->exact_hold;
   L.busy = false;
   glr_timing t{};
   cudaEventElapsedTime(&t.total_ms, L.ev[0], L.ev[4]);

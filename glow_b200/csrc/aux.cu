@@ -147,8 +147,19 @@ void launch_reduce_splits(const double* part, double* out, int64_t rows, int64_t
 constexpr int kEpiThreads = 256;
 
 // xx_full[v] = sum x^2 - |Q^T x|^2  (= |x - Q Q^T x|^2, the fully observed XdotX)
+//
+// Digit certificate.  A column q_c stored with d digits is the exact column q_c + e_c with |e_c[s]| <= 0.51 u_c,
+// u_c = max|q_c| 2^-(8d-2) (round to nearest plus the rounding of the division), and the integer contraction is exact, so
+// the computed a_c = q_c.x + e_c.x with |e_c.x| <= 0.51 u_c sum|x| =: t_c, and
+//   |xx_computed - xx_exact| = |sum_c (a_c^2 - (a_c - e_c.x)^2)| <= sum_c (2 |a_c| + t_c) t_c.
+// sum|x| <= max(sum x, sum x^2): the entries are >= 0 (mean substitution) or in {-1, 0, 1, 2} (|x| <= x^2).
+// A phenotype with missing samples takes XdotX = xx - D (complement form) or XdotX = D, D = sum over a sample subset of
+// r_s^2 with r = x - Q a: the error of a moves r_s by sum_c q_c[s] (e_c.x), so (Cauchy-Schwarz, |q_c| = 1)
+//   |D_computed - D_exact| <= (2 sqrt(D) + T) T,  T = sum_c t_c.
+// Both bounds are written next to xx; the epilogue compares them with every test's XdotX.
 __global__ void __launch_bounds__(kEpiThreads) xx_full_kernel(const double* S, const double* sxx, int K, int G,
-                                                               int64_t ldS, double* xx) {
+                                                               int64_t ldS, double* xx, const double* lo_scale,
+                                                               const double* sum_x_row, int n_lo, int lo_row0) {
   const int v = blockIdx.x * kEpiThreads + threadIdx.x;
   if (v >= G) return;
   double a2 = 0.0;
@@ -157,6 +168,17 @@ __global__ void __launch_bounds__(kEpiThreads) xx_full_kernel(const double* S, c
     a2 = fma(a, a, a2);
   }
   xx[v] = sxx[v] - a2;
+  if (lo_scale) {
+    const double sabs = fmax(sum_x_row[v], sxx[v]);
+    double cert = 0.0, tsum = 0.0;
+    for (int c = 0; c < n_lo; ++c) {
+      const double t = 0.51 * lo_scale[c] * sabs;
+      cert += (2.0 * fabs(S[(int64_t)(lo_row0 + c) * ldS + v]) + t) * t;
+      tsum += t;
+    }
+    xx[ldS + v] = cert;
+    xx[2 * ldS + v] = tsum;
+  }
 }
 
 // one thread per (phenotype, variant) test: the p-value loops are latency bound, so parallelism
@@ -168,6 +190,15 @@ __global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpiloguePar
   const int mid = p.mask_id[ph];
   const double XdotX = mid < 0 ? xx_full[v] : (p.d_is_complement ? xx_full[v] - p.D[(int64_t)mid * p.ldS + v] : p.D[(int64_t)mid * p.ldS + v]);
   const double XdotY = p.S[(int64_t)(p.K + ph) * p.ldS + v];
+  // (a variant that is numerically inside the span of the covariates has no meaningful statistics in any arithmetic)
+  if (p.lo_scale) {
+    double cert = (mid < 0 || p.d_is_complement) ? xx_full[p.ldS + v] : 0.0;
+    if (mid >= 0) {
+      const double T = xx_full[2 * p.ldS + v];
+      cert += (2.0 * sqrt(fabs(p.D[(int64_t)mid * p.ldS + v])) + T) * T;
+    }
+    if (cert > kDigitCertTol * XdotX && XdotX > 1e-9 * p.sxx[v]) atomicOr(p.flags, 4);
+  }
   const double recip = 1.0 / XdotX;                                             // lin_reg.py:241
   const double beta = XdotY * recip;                                            // :242
   const double se = sqrt((p.YdotY[ph] * recip - beta * beta) / p.dof);          // :243
@@ -187,7 +218,8 @@ __global__ void __launch_bounds__(kEpiThreads) epilogue_kernel(const EpiloguePar
 void launch_epilogue(const EpilogueParams& p, double* xx_scratch, cudaStream_t st) {
   if (p.G <= 0 || p.P <= 0) return;
   const unsigned gx = (unsigned)ceil_div(p.G, kEpiThreads);
-  xx_full_kernel<<<gx, kEpiThreads, 0, st>>>(p.S, p.sxx, p.K, p.G, p.ldS, xx_scratch);
+  xx_full_kernel<<<gx, kEpiThreads, 0, st>>>(p.S, p.sxx, p.K, p.G, p.ldS, xx_scratch, p.lo_scale, p.sum_x_row, p.n_lo,
+                                             p.lo_row0);
   for (int p0 = 0; p0 < p.P; p0 += 65535) {  // gridDim.y limit
     EpilogueParams q = p;
     const int np = p.P - p0 < 65535 ? p.P - p0 : 65535;

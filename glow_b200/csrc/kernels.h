@@ -46,10 +46,12 @@ void launch_gram(const GramParams& p, cudaStream_t st);
 struct Split8Params {
   BlockView x;           // PLINK2 block; x.v1 = missing substitute per variant (used when !fused_counts)
   const int8_t* w8;      // packed digits of this contig: [column block][stage][NC rows][128 B], 128-byte swizzled
-  const double* scale;   // [n_cols] column scale = max|w_c| * 2^-54
-  int32_t n_cols;        // columns of W in the GEMM (7 digit rows each)
+  const double* scale;   // [n_cols] column scale = max|w_c| * 2^-(8 digits - 2)
+  int32_t n_cols;        // columns of W in the GEMM (7 digit rows each, see n_lo)
   int32_t n_cb;          // column blocks (1 for <= 18 columns, 2 for <= 36)
-  int32_t cpb;           // columns per block; digit row 7 * cpb of every block is the row of ones
+  int32_t cpb;           // columns per block; the digit row after the last column of every block is the row of ones
+  int32_t n_lo;          // the first n_lo columns carry lo_digits digits instead of 7 (single-block images only; the
+  int32_t lo_digits;     // caller certifies the results, see digit_certificate in aux.cu)
   int32_t NC;            // digit rows per block = MMA N (multiple of 16, <= 128)
   int32_t fused_counts;  // 1: the kernel derives v1 / sum x^2 / sum x from the codes it decodes (no pre-pass)
   int32_t missing_policy;
@@ -74,11 +76,16 @@ struct Split8Plan {
 Split8Plan split8_plan(int n_variants, int n_cb, int64_t n_stages, int sm_count, int pair_mode, int force_split);
 size_t split8_ws_bytes(int n_cb, int NC, int64_t ldS);
 void launch_split8(Split8Params p, int sm_count, cudaStream_t st);
-void split8_geometry(int n_cols, int* n_cb, int* cpb, int* NC);
+// n_lo / lo_digits: the reduced-digit image (n_lo = 0 for the plain one); it exists only when one block holds all columns
+void split8_geometry(int n_cols, int n_lo, int lo_digits, int* n_cb, int* cpb, int* NC);
+// digit row of local column lc inside its block, and of the row of ones (= split8_row0(cpb, ...))
+__host__ __device__ inline int split8_row0(int lc, int n_lo, int lo_digits) {
+  return 7 * lc - (7 - lo_digits) * (lc < n_lo ? lc : n_lo);
+}
 double measure_s8_issue_rate(int sm_count, double ms_target, cudaStream_t st);  // TOP/s, < 0 on failure
 void launch_pack_split8(const double* src, int64_t N, int64_t ld, int c0, int ncols, double* colmax_scratch,
                         const int64_t* geno_to_row, int64_t Ng, int8_t* dst, int dst_col0, int cpb, int NC,
-                        int64_t n_stages, cudaStream_t st);
+                        int64_t n_stages, int n_lo, int lo_digits, cudaStream_t st);
 
 // ---- pass 2 (only when some phenotype has missing samples): D = Mu^T (X - Q A)^2 ----------------
 struct MaskedParams {
@@ -159,8 +166,15 @@ struct EpilogueParams {
   PvalConst pc;
   double *effect, *stderror, *tvalue, *pvalue;  // [P][G]
   double *n, *sum_x, *ytx;                      // verbose, [P][G]
+  // digit certificate (reduced-digit image of split8.cu): rows lo_row0 .. lo_row0 + n_lo - 1 of S were computed from
+  // columns quantised to lo_scale[c]; a test whose certified error of XdotX exceeds kDigitCertTol * XdotX raises flags |= 4
+  const double* lo_scale = nullptr;  // [n_lo] quantum of each reduced column, nullptr = nothing to certify
+  const double* sum_x_row = nullptr; // [ldS] sum of x per variant
+  int32_t n_lo = 0, lo_row0 = 0;
+  int32_t* flags = nullptr;
 };
-// xx_scratch: [G] doubles of workspace (fully observed XdotX per variant)
+constexpr double kDigitCertTol = 1e-11;  // 100 x inside the 1e-9 parity tolerance of the statistics
+// xx_scratch: [3][ldS] doubles of workspace (fully observed XdotX per variant; the two certified error bounds)
 void launch_epilogue(const EpilogueParams& p, double* xx_scratch, cudaStream_t st);
 
 void launch_pvalues(const double* t, int64_t n, PvalConst pc, double* p, cudaStream_t st);

@@ -668,8 +668,9 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         double mu = -1.0;
         {
           uint32_t zx[8], ze[8];
-          tmem_ld8(lane_addr + p.cpb * kS8Digits, zx);  // column 7 cpb = the row of ones
-          if (!kNoE) tmem_ld8(lane_addr + kS8ColDe + p.cpb * kS8Digits, ze);
+          const int r1 = split8_row0(p.cpb, p.n_lo, p.lo_digits);  // the row of ones follows the last column
+          tmem_ld8(lane_addr + r1, zx);
+          if (!kNoE) tmem_ld8(lane_addr + kS8ColDe + r1, ze);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
           if (p.fused_counts) {
             const double sx = (double)(int32_t)zx[0];                  // 2 n00 + n10
@@ -696,13 +697,15 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         }
         for (int c = (int)grp; c < ncols; c += 2) {
           uint32_t zx[8], ze[8];
-          tmem_ld8(lane_addr + c * kS8Digits, zx);
-          if (!kNoE) tmem_ld8(lane_addr + kS8ColDe + c * kS8Digits, ze);
+          const int r0 = split8_row0(c, p.n_lo, p.lo_digits), nd = c < p.n_lo ? p.lo_digits : kS8Digits;
+          tmem_ld8(lane_addr + r0, zx);
+          if (!kNoE) tmem_ld8(lane_addr + kS8ColDe + r0, ze);
           asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
           double acc = 0.0;
 #pragma unroll
           for (int i = kS8Digits - 1; i >= 0; --i)
-            acc = fma(acc, 256.0, kNoE ? (double)(int32_t)zx[i] : fma(mu, (double)(int32_t)ze[i], (double)(int32_t)zx[i]));
+            if (i < nd)
+              acc = fma(acc, 256.0, kNoE ? (double)(int32_t)zx[i] : fma(mu, (double)(int32_t)ze[i], (double)(int32_t)zx[i]));
           p.S[(int64_t)(col0 + c) * p.ldS + vg] = acc * p.scale[col0 + c];
         }
       } else {
@@ -749,10 +752,11 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
   }
 }
 
-void split8_geometry(int n_cols, int* n_cb, int* cpb, int* NC) {
+void split8_geometry(int n_cols, int n_lo, int lo_digits, int* n_cb, int* cpb, int* NC) {
   *n_cb = (n_cols + 17) / 18;
   *cpb = (n_cols + *n_cb - 1) / *n_cb;
-  *NC = (int)round_up((int64_t)*cpb * kS8Digits + 1, 16);
+  if (*n_cb > 1) n_lo = 0;
+  *NC = (int)round_up((int64_t)split8_row0(*cpb, n_lo, lo_digits) + 1, 16);
 }
 
 // Recombination of the split form: thread = (variant, column block) reads the summed int32 digit rows and does exactly
@@ -767,7 +771,7 @@ __global__ void split8_finalize_kernel(const Split8Params p, int no_e) {
   const double n_geno = (double)p.x.n_geno;
   double mu = -1.0;
   if (p.fused_counts) {
-    const int64_t r1 = (int64_t)p.cpb * kS8Digits;
+    const int64_t r1 = split8_row0(p.cpb, p.n_lo, p.lo_digits);
     const double sx = (double)zx[r1 * p.ldS];
     const int32_t cm = no_e ? 0 : ze[r1 * p.ldS];
     const double c01 = (double)cm;
@@ -786,8 +790,10 @@ __global__ void split8_finalize_kernel(const Split8Params p, int no_e) {
   for (int c = 0; c < ncols; ++c) {
     double acc = 0.0;
 #pragma unroll
+    const int r0 = split8_row0(c, p.n_lo, p.lo_digits), nd = c < p.n_lo ? p.lo_digits : kS8Digits;
     for (int i = kS8Digits - 1; i >= 0; --i) {
-      const int64_t r = (int64_t)c * kS8Digits + i;
+      if (i >= nd) continue;
+      const int64_t r = r0 + i;
       const double dx = (double)zx[r * p.ldS];
       acc = fma(acc, 256.0, no_e ? dx : fma(mu, (double)ze[r * p.ldS], dx));
     }
@@ -1003,7 +1009,8 @@ double measure_s8_issue_rate(int sm_count, double ms_target, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------
 // packing: W (row-major [N x ld], columns c0..c0+ncols) -> per column block and 128-sample stage a
-// swizzled image [NC digit rows][128 bytes]; row of (local column c, digit i) = 7 c + i, row 7 cpb = ones.
+// swizzled image [NC digit rows][128 bytes]; row of (local column c, digit i) = split8_row0(c) + i (7 c + i when every
+// column has 7 digits), row split8_row0(cpb) = ones.  A column with d digits is quantised to 8 d - 1 bits.
 // Inside each 16-sample group the bytes follow the sample order the decode produces (see split8_kernel).
 // ------------------------------------------------------------------------------------------------
 __global__ void colmax_kernel(const double* src, int64_t N, int64_t ld, int c0, int ncols, double* out) {
@@ -1022,7 +1029,7 @@ __global__ void colmax_kernel(const double* src, int64_t N, int64_t ld, int c0, 
 
 __global__ void pack_split8_kernel(const double* src, int64_t N, int64_t ld, int c0, int ncols, const double* colmax,
                                    const int64_t* geno_to_row, int64_t Ng, int8_t* dst, int dst_col0, int cpb, int NC,
-                                   int64_t n_stages) {
+                                   int64_t n_stages, int n_lo, int lo_digits) {
   const int64_t total = (int64_t)ncols * n_stages * kS8K;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -1034,34 +1041,35 @@ __global__ void pack_split8_kernel(const double* src, int64_t N, int64_t ld, int
     if (row >= 0 && row < N) v = src[row * ld + c0 + c];
   }
   const double mx = colmax[c];
-  long long q = mx > 0.0 ? __double2ll_rn(v / mx * 18014398509481984.0 /* 2^54 */) : 0ll;
+  const int gc = dst_col0 + c, cb = gc / cpb, lc = gc - cb * cpb;
+  const int nd = lc < n_lo ? lo_digits : kS8Digits;
+  long long q = mx > 0.0 ? __double2ll_rn(v / mx * (double)(1ll << (8 * nd - 2))) : 0ll;
   const int64_t stage = sg / kS8K;
   const int k = (int)(sg % kS8K);
   const int r16 = k & 15;  // sample inside its 16-sample group -> byte position (register j, byte b) of the decode
   const int pos = (((r16 >> 3) | ((r16 & 1) << 1)) << 2) | ((r16 >> 1) & 3);
-  const int gc = dst_col0 + c, cb = gc / cpb, lc = gc - cb * cpb;
   int8_t* base = dst + ((int64_t)cb * n_stages + stage) * NC * kS8K;
-#pragma unroll
-  for (int i = 0; i < kS8Digits; ++i) {
+  const int r0 = split8_row0(lc, n_lo, lo_digits);
+  for (int i = 0; i < nd; ++i) {
     const long long d = ((q + 128) & 255) - 128;  // balanced digit in [-128, 127]
     q = (q - d) >> 8;
-    const int r = lc * kS8Digits + i;
+    const int r = r0 + i;
     base[(int64_t)r * kS8K + (((k >> 4) ^ (r & 7)) << 4) + pos] = (int8_t)d;
   }
   if (lc == 0) {  // the first column of a block also writes the block's row of ones
-    const int r = cpb * kS8Digits;
+    const int r = split8_row0(cpb, n_lo, lo_digits);
     base[(int64_t)r * kS8K + (((k >> 4) ^ (r & 7)) << 4) + pos] = 1;
   }
 }
 
 void launch_pack_split8(const double* src, int64_t N, int64_t ld, int c0, int ncols, double* colmax_scratch,
                         const int64_t* geno_to_row, int64_t Ng, int8_t* dst, int dst_col0, int cpb, int NC, int64_t n_stages,
-                        cudaStream_t st) {
+                        int n_lo, int lo_digits, cudaStream_t st) {
   if (ncols <= 0) return;
   colmax_kernel<<<ncols, 256, 0, st>>>(src, N, ld, c0, ncols, colmax_scratch);
   const int64_t total = (int64_t)ncols * n_stages * kS8K;
   pack_split8_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(src, N, ld, c0, ncols, colmax_scratch, geno_to_row,
-                                                                      Ng, dst, dst_col0, cpb, NC, n_stages);
+                                                                      Ng, dst, dst_col0, cpb, NC, n_stages, n_lo, lo_digits);
 }
 
 }  // namespace glr

@@ -75,6 +75,11 @@ typedef struct glr_options {
   int32_t optimistic_calls;/* glr_tristate: run PLINK2 blocks without the missing-call operand while the previous block of
                               the state had no missing call, re-running a block that turns out to have one (results are
                               identical either way): automatic | never | (FORCE = start optimistic at the first block) */
+  int32_t q_digits;        /* radix-256 digits of the covariate columns in the int8 contraction: 0 = automatic (5, or 6
+                              when a phenotype has missing samples), 7 = always the full precision.  With fewer than 7
+                              digits every test carries a certified bound of the error of XdotX; a block with a test
+                              whose bound exceeds 1e-11 XdotX is re-run with 7 digits, so results stay within 1e-11 of
+                              the 7-digit ones (which are exact to FP64 rounding) */
 } glr_options;
 
 typedef struct glr_state glr_state; /* opaque */
@@ -159,7 +164,8 @@ typedef enum glr_path_flags {
   GLR_PATH_MASK_DMMA = 128,   /* masked pass: FP64 DMMA */
   GLR_PATH_OPTIMISTIC = 256,  /* block ran without the missing-call operand */
   GLR_PATH_REPLAYED = 512,    /* ... and was re-run because it had missing calls */
-  GLR_PATH_MASK_GENERIC = 1024 /* masked pass: generic FP64 form (more than 64 covariates) */
+  GLR_PATH_MASK_GENERIC = 1024, /* masked pass: generic FP64 form (more than 64 covariates) */
+  GLR_PATH_Q_DIGITS_LO = 2048   /* first pass with reduced-digit covariate columns (results certified) */
 } glr_path_flags;
 
 int glr_abi_version(void);

@@ -40,7 +40,7 @@ def test_ctypes_structs_match_header_layout():
     int main(void) {
       printf("%zu %zu %zu %zu\n", sizeof(glr_state_desc), sizeof(glr_block_desc), sizeof(glr_block_out), sizeof(glr_timing));
       printf("%zu %zu %zu %zu\n", offsetof(glr_state_desc, Q), offsetof(glr_state_desc, dof), offsetof(glr_state_desc, memspace), offsetof(glr_block_desc, row_stride_bytes));
-      printf("%zu %zu %zu %zu\n", sizeof(glr_options), offsetof(glr_state_desc, opt), offsetof(glr_options, optimistic_calls), offsetof(glr_timing, path));
+      printf("%zu %zu %zu %zu\n", sizeof(glr_options), offsetof(glr_state_desc, opt), offsetof(glr_options, q_digits), offsetof(glr_timing, path));
       return 0;
     }'''
     import tempfile
@@ -55,7 +55,7 @@ def test_ctypes_structs_match_header_layout():
                          ctypes.sizeof(_capi.Timing)]
     assert sizes[4:8] == [_capi.StateDesc.Q.offset, _capi.StateDesc.dof.offset, _capi.StateDesc.memspace.offset,
                           _capi.BlockDesc.row_stride_bytes.offset]
-    assert sizes[8:] == [ctypes.sizeof(_capi.Options), _capi.StateDesc.opt.offset, _capi.Options.optimistic_calls.offset,
+    assert sizes[8:] == [ctypes.sizeof(_capi.Options), _capi.StateDesc.opt.offset, _capi.Options.q_digits.offset,
                          _capi.Timing.path.offset]
     o = _capi.make_options({'split8': 'force', 'split8_pair': 'off', 'sample_split': 3})
     assert (o.split8, o.split8_pair, o.mask_sparse, o.sample_split) == (_capi.FORCE, _capi.OFF, _capi.AUTO, 3)

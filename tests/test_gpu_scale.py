@@ -338,3 +338,53 @@ def test_float64_blocks_are_reproducible_with_short_lived_ctas(rg):
         idx = np.sort(rg.choice(G, 64, replace=False))
         assert_stats_close({k: first[k][:, idx] for k in STATS}, orc.block_stats(X[idx], st), label='short CTAs')
         eng.close()
+
+
+def _max_rel(a, b):
+    ok = np.isfinite(a) & np.isfinite(b) & (b != 0)
+    return float(np.max(np.abs(a[ok] - b[ok]) / np.abs(b[ok]))) if ok.any() else 0.0
+
+
+@pytest.mark.parametrize('missing_phenotype', [False, True])
+def test_reduced_digit_covariates_are_certified(missing_phenotype):
+    """The covariate columns enter the int8 contraction with 5 digits (6 when a masked pass follows) instead of 7.  Every
+    test carries a certified bound of the error this causes in XdotX (aux.cu: xx_full_kernel); the default run must take
+    the reduced image, stay within 1e-11 of the 7-digit results, and a run whose certificate fails (3 digits, test only)
+    must be re-run on the 7-digit image and give its bits."""
+    from glow_b200 import _capi
+    from glow_b200.engine import GenotypeBlock
+    from gpu_utils import gen_packed_gpu, unpack_states
+    rg = np.random.default_rng(8)
+    N, G, K, P = 200_000, 1024, 16, 2
+    cov = rg.standard_normal((N, K))
+    cov[:, 3] = rg.random(N) < 0.002            # rare binary covariate: a column whose maximum is far above its rms
+    packed = gen_packed_gpu(G, N, seed=21, missing=0.01)
+    Y = rg.standard_normal((N, P)) + 0.02 * unpack_states(packed[:P], N).T
+    if missing_phenotype:
+        Y[rg.random((N, P)) < 0.15] = np.nan
+    st = orc.prepare_state(pd.DataFrame(Y), pd.DataFrame(cov))
+    blk = GenotypeBlock(packed, 'plink2', 'mean')
+    e7 = _engine_from(st, {'split8': 'force', 'q_digits': 7})
+    want = e7.run(blk)
+    assert not e7.timing(0)['path'] & _capi.PATH_Q_DIGITS_LO
+    e7.close()
+    eng = _engine_from(st, {'split8': 'force'})
+    got = eng.run(blk)
+    path = eng.timing(0)['path']
+    assert path & _capi.PATH_Q_DIGITS_LO and not path & _capi.PATH_REPLAYED, path
+    eng.close()
+    for k, tol in (('effect', 1e-11), ('stderror', 1e-11), ('tvalue', 1e-11), ('pvalue', 1e-9)):
+        assert _max_rel(got[k], want[k]) <= tol, (k, _max_rel(got[k], want[k]))
+    idx = np.array([0, 1, 511, 1023])
+    assert_stats_close({k: got[k][:, idx] for k in STATS}, _subset_ref(packed, st, N, idx), label='reduced digits')
+    # failed certificate -> same block again on the 7-digit image; the state then stays on it for a while
+    e3 = _engine_from(st, {'split8': 'force', 'q_digits': 3})
+    r3 = e3.run(blk)
+    path = e3.timing(0)['path']
+    assert path & _capi.PATH_REPLAYED and not path & _capi.PATH_Q_DIGITS_LO, path
+    r3b = e3.run(blk)
+    assert not e3.timing(0)['path'] & (_capi.PATH_REPLAYED | _capi.PATH_Q_DIGITS_LO)
+    e3.close()
+    for k in STATS:
+        assert np.array_equal(r3[k], want[k], equal_nan=True), k
+        assert np.array_equal(r3b[k], want[k], equal_nan=True), k

@@ -57,3 +57,33 @@ def test_integer_contraction_with_recombination_matches_exact_dot_product():
     assert float(err_split) <= 4 * N * 2.0**-53 * mx            # a-priori bound: N operand errors of ~1 ulp(max|w|) * |x| <= 2
     assert float(err_split) <= 1e-15 * scale                    # in practice: at the FP64 rounding level of the result
     assert float(err_split) <= 8 * float(err_fp64_gemm) + 1e-17 * scale
+
+
+def test_reduced_digit_certificate_bounds_the_true_error():
+    """The certificate of aux.cu (xx_full_kernel): with the covariate columns quantised to d digits, the error of
+    XdotX = sum x^2 - sum_c a_c^2 is at most sum_c (2 |a_c| + t_c) t_c with t_c = 0.51 u_c sum|x|, u_c = max|q_c| 2^-(8d-2).
+    Checked in exact rational arithmetic for d = 5 and 6, including a column with an outlier."""
+    rg = np.random.default_rng(4)
+    N, K = 4000, 5
+    C = rg.standard_normal((N, K))
+    C[17, 2] = 1e4
+    Q, _ = np.linalg.qr(C - C.mean(0))
+    x = rg.integers(0, 3, N).astype(np.float64)
+    x[rg.random(N) < 0.02] = 0.37                       # mean-substituted entries (>= 0)
+    xf = [Fraction(float(v)) for v in x]
+    sabs = float(sum(xf))
+    for d in (5, 6):
+        err_xx, cert = Fraction(0), 0.0
+        for c in range(K):
+            q = Q[:, c]
+            mx = float(np.max(np.abs(q)))
+            u = mx * 2.0**-(8 * d - 2)
+            qi = np.rint(q / mx * 2.0**(8 * d - 2))     # what pack_split8_kernel stores
+            a_hat = sum(Fraction(int(v)) * xv for v, xv in zip(qi, xf)) * Fraction(u)   # exact integer contraction, rescaled
+            a = sum(Fraction(float(v)) * xv for v, xv in zip(q, xf))
+            t = 0.51 * u * sabs
+            assert abs(a_hat - a) <= Fraction(t)
+            err_xx += a_hat * a_hat - a * a
+            cert += (2.0 * abs(float(a_hat)) + t) * t
+        assert abs(err_xx) <= Fraction(cert)
+        assert cert > 0.0
