@@ -63,8 +63,15 @@ namespace glr {
 constexpr int kS8K = 128;      // samples per stage = bytes per digit row per stage
 constexpr int kS8TileV = 128;  // variants per tile = TMEM lanes
 constexpr int kS8Digits = 7;
-constexpr int kS8DecodeWarps = 8;
-constexpr int kS8FirstDecodeWarp = 4;
+#ifndef GLR_S8_GROUPS
+#define GLR_S8_GROUPS 3
+#endif
+#ifndef GLR_S8_FIRST_DECODE
+#define GLR_S8_FIRST_DECODE 4
+#endif
+constexpr int kS8Groups = GLR_S8_GROUPS;  // decode groups of 4 warps (one per TMEM lane quarter); group = stage index mod kS8Groups
+constexpr int kS8DecodeWarps = 4 * kS8Groups;
+constexpr int kS8FirstDecodeWarp = GLR_S8_FIRST_DECODE;
 #ifndef GLR_S8_ISSUERS
 #define GLR_S8_ISSUERS 4
 #endif
@@ -208,7 +215,7 @@ struct Split8Smem {
   uint64_t peer_w[kS8WRingMax];  // pair mode, leader: the peer CTA's half of a digit stage has landed
   uint32_t tmem_base;
   uint32_t pad;
-  int32_t n00[2][kS8TileV];  // per stage-parity group: homozygous-alternate (code 00) count per variant
+  int32_t n00[kS8Groups][kS8TileV];  // per decode group: homozygous-alternate (code 00) count per variant
 };
 
 // Work-item order.  A round of concurrently running items should touch few distinct digit blocks (128 N bytes
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       mbar_init(&sm->done[s], 1);
     }
     for (int s = 0; s < kS8WRingMax; ++s) mbar_init(&sm->peer_w[s], 1);
-    for (int s = 0; s < kS8ARingMax; ++s) mbar_init(&sm->full_a[s], (kPair ? 2 : 1) * kS8DecodeWarps / 2);
+    for (int s = 0; s < kS8ARingMax; ++s) mbar_init(&sm->full_a[s], (kPair ? 2 : 1) * 4);  // the 4 warps of one group
     mbar_init(&sm->tmem_full, kS8Issuers);  // every MMA issuer thread commits its last stage of the item
     mbar_init(&sm->tmem_empty, (kPair ? 2 : 1) * kS8DecodeWarps);
     mbar_init(&sm->tile_started, 1);
@@ -436,7 +443,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
   } else if (warp >= kS8FirstDecodeWarp) {
     // ---- decode + count (8 warps), epilogue ----
     const int q = warp & 3;                                 // TMEM lane quarter this warp may access
-    const uint32_t grp = (warp - kS8FirstDecodeWarp) >> 2;  // takes the stages with global parity grp
+    const uint32_t grp = (warp - kS8FirstDecodeWarp) >> 2;  // takes the stages with global index = grp mod kS8Groups
     const int vloc = q * 32 + lane;                         // variant of the tile = TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int64_t n_geno = p.x.n_geno;
@@ -530,7 +537,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         }
       };
       int n00 = 0;
-      const int k_first = (int)((grp ^ g0) & 1u);
+      const int k_first = (int)((grp + (uint32_t)kS8Groups - g0 % (uint32_t)kS8Groups) % (uint32_t)kS8Groups);
       // a 128-byte line of the row feeds 4 stages: the group on the even stages pulls lines into L2 well ahead
       if (kFmt != GLR_FMT_I8 && k_first == 0) {
 #pragma unroll
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           if ((int64_t)kbeg * 32 + l * 128 < row_bytes) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (int64_t)kbeg * 32 + l * 128));
       }
       load(kbeg + k_first);
-      for (int k = k_first; k < kcnt; k += 2) {
+      for (int k = k_first; k < kcnt; k += kS8Groups) {
         const uint32_t g = g0 + (uint32_t)k;
         const int64_t ka = kbeg + k;
         const uint32_t sa = g & (kAR - 1);
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           uint32_t w[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) w[i] = nxt[i];
-          if (k + 2 < kcnt) load(ka + 2);
+          if (k + kS8Groups < kcnt) load(ka + kS8Groups);
           if (g >= (uint32_t)kAR) {
             uint64_t* bar = &sm->done[(g - kAR) & (kWR - 1)];
             s8_wait_keep1(bar, ((g - kAR) >> kWRLog) & 1u, w);
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         uint32_t w[kS8Words];
 #pragma unroll
         for (int i = 0; i < kS8Words; ++i) w[i] = kAlign ? nxt[i] : __funnelshift_r(nxt[i], nxt[i + 1], sh_nxt);
-        if (k + 2 < kcnt) load(ka + 2);
+        if (k + kS8Groups < kcnt) load(ka + kS8Groups);
         if ((ka & 3) == 0 && (ka + 16) * 32 < row_bytes)
           asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (ka + 16) * 32));
         // decode into registers first, THEN wait for the TMEM slot: the slot frees up when the MMAs of stage g - 4
@@ -655,7 +662,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
       const bool v_ok = vg < p.x.n_variants;
       if (n_split == 1) {
         sm->n00[grp][vloc] = n00;
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // all decode warps: both groups' counts are in shared memory
+        asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kS8DecodeWarps) : "memory");  // all decode warps: every group's counts are in shared memory
       } else if (cb == 0 && v_ok && n00 != 0) {
         atomicAdd(p.n00_ws + vg, n00);
       }
@@ -675,7 +682,10 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
           if (p.fused_counts) {
             const double sx = (double)(int32_t)zx[0];                  // 2 n00 + n10
             const double c01 = kNoE ? 0.0 : (double)(int32_t)ze[0];    // missing calls
-            const double c00 = (double)(sm->n00[0][vloc] + sm->n00[1][vloc]);
+            int c00i = 0;
+#pragma unroll
+            for (int gq = 0; gq < kS8Groups; ++gq) c00i += sm->n00[gq][vloc];
+            const double c00 = (double)c00i;
             if (p.missing_policy == GLR_MISSING_MEAN && c01 < (double)n_geno)
               mu = sx / ((double)n_geno - c01);  // MeanSubstitute.scala:57-84
             if (cb == 0 && grp == 0) {
@@ -695,7 +705,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
             mu = p.x.v1[min(vg, (int64_t)p.x.n_variants - 1)];
           }
         }
-        for (int c = (int)grp; c < ncols; c += 2) {
+        for (int c = (int)grp; c < ncols; c += kS8Groups) {
           uint32_t zx[8], ze[8];
           const int r0 = split8_row0(c, p.n_lo, p.lo_digits), nd = c < p.n_lo ? p.lo_digits : kS8Digits;
           tmem_ld8(lane_addr + r0, zx);
@@ -712,7 +722,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         // partial digit sums of this sample range: exact integer atomics into the zeroed workspace
         // zws[cb][accumulator][digit row][ldS]; the two groups split the 8-row chunks
         int32_t* zx_ws = p.z_ws + (int64_t)cb * 2 * NC * p.ldS + vg;
-        for (int ch = (int)grp; ch < (NC >> 3); ch += 2) {  // rows of absent columns hold zeros: no atomics issued
+        for (int ch = (int)grp; ch < (NC >> 3); ch += kS8Groups) {  // rows of absent columns hold zeros: no atomics issued
           uint32_t zx[8], ze[8];
           tmem_ld8(lane_addr + ch * 8, zx);
           if (!kNoE) tmem_ld8(lane_addr + kS8ColDe + ch * 8, ze);
@@ -733,7 +743,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
         if (kPair) s8_arrive_cta(&sm->tmem_empty, 0);
         else mbar_arrive(&sm->tmem_empty);
       }
-      if (n_split == 1) asm volatile("bar.sync 1, 256;\n" ::: "memory");  // n00[] may be rewritten
+      if (n_split == 1) asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kS8DecodeWarps) : "memory");  // n00[] may be rewritten
       g0 += (uint32_t)kcnt;
     }
     if (kNoE) {
