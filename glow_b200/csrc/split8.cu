@@ -63,21 +63,34 @@ namespace glr {
 constexpr int kS8K = 128;      // samples per stage = bytes per digit row per stage
 constexpr int kS8TileV = 128;  // variants per tile = TMEM lanes
 constexpr int kS8Digits = 7;
+// Warp roles of a CTA: kIssuers MMA issuer warps (stage g is issued by warp g % kIssuers), then kGroups decode groups of
+// 4 warps (one warp per TMEM lane quarter; group g % kGroups decodes stage g), then the producer warp (digit operand,
+// TMEM allocation).  Registers per thread follow from the warps per SM sub-partition (16 K registers each): 17-20 warps
+// -> 96, 21-24 -> 80.  The form with the missing-call operand keeps 64 decoded words live across the TMEM slot wait and
+// needs the 96; the optimistic form needs half of that and takes more groups instead.  Measured (37 888 x 500 k, short
+// runs): 2 groups / 4 issuers 2.57 | 2.35 ms (full | optimistic form), 3 / 4: 2.37 | 2.11, 4 / 2: 2.26 | 1.74; 5 or 6
+// groups in the optimistic form: within 4 % of 4.  Moving registers from the issuers to the decode warps with setmaxnreg
+// (4 groups / 4 issuers, 21 warps, 88 registers for the decode) was 4 % slower than 4 / 2 at 96.
 #ifndef GLR_S8_GROUPS
-#define GLR_S8_GROUPS 3
+#define GLR_S8_GROUPS 4
 #endif
-#ifndef GLR_S8_FIRST_DECODE
-#define GLR_S8_FIRST_DECODE 4
-#endif
-constexpr int kS8Groups = GLR_S8_GROUPS;  // decode groups of 4 warps (one per TMEM lane quarter); group = stage index mod kS8Groups
-constexpr int kS8DecodeWarps = 4 * kS8Groups;
-constexpr int kS8FirstDecodeWarp = GLR_S8_FIRST_DECODE;
 #ifndef GLR_S8_ISSUERS
-#define GLR_S8_ISSUERS 4
+#define GLR_S8_ISSUERS 2
 #endif
-constexpr int kS8Issuers = GLR_S8_ISSUERS;  // warps 0-3 (or 0-1): stage g is issued by warp g % kS8Issuers
-constexpr int kS8ProducerWarp = kS8FirstDecodeWarp + kS8DecodeWarps;  // warp 12: digit-operand producer, TMEM allocation
-constexpr int kS8Threads = (kS8ProducerWarp + 1) * 32;
+#ifndef GLR_S8_GROUPS_NOE
+#define GLR_S8_GROUPS_NOE GLR_S8_GROUPS
+#endif
+#ifndef GLR_S8_ISSUERS_NOE
+#define GLR_S8_ISSUERS_NOE GLR_S8_ISSUERS
+#endif
+template <bool kNoE>
+struct S8Shape {
+  static constexpr int kGroups = kNoE ? GLR_S8_GROUPS_NOE : GLR_S8_GROUPS;
+  static constexpr int kIssuers = kNoE ? GLR_S8_ISSUERS_NOE : GLR_S8_ISSUERS;  // power of two
+  static constexpr int kThreads = (kIssuers + 4 * kGroups + 1) * 32;
+};
+constexpr int kS8MaxGroups = 8;
+constexpr int kS8MaxIssuers = 4;  // (split8_plan: every sample range has at least this many stages)
 constexpr int kS8Words = 8;  // 32-bit words (16 samples each) per decode thread per stage
 constexpr int kS8WRing = 8;  // digit-operand stages in shared memory (also the depth of the completion barriers)
 constexpr int kS8WRingMax = 16;  // CTA pairs in the optimistic form: a stage takes half as long, so twice as many digit stages
@@ -215,7 +228,7 @@ struct Split8Smem {
   uint64_t peer_w[kS8WRingMax];  // pair mode, leader: the peer CTA's half of a digit stage has landed
   uint32_t tmem_base;
   uint32_t pad;
-  int32_t n00[kS8Groups][kS8TileV];  // per decode group: homozygous-alternate (code 00) count per variant
+  int32_t n00[kS8MaxGroups][kS8TileV];  // per decode group: homozygous-alternate (code 00) count per variant
 };
 
 // Work-item order.  A round of concurrently running items should touch few distinct digit blocks (128 N bytes
@@ -269,7 +282,11 @@ __device__ long long g_s8_prof[160][3][8];  // [cta][issuer 0 / issuer 1 / decod
 // or 4).  The int8 form assumes values in {-1, 0, 1, 2}; it checks every byte while decoding and raises *p.flags |= 2 when
 // it meets anything else, upon which the host re-runs the block on the FP64 path (any int8 value is legal there).
 template <int kAlign, bool kPair, bool kNoE, int kFmt = GLR_FMT_PLINK2>
-__global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Params p) {
+__global__ void __launch_bounds__(S8Shape<kNoE>::kThreads, 1) split8_kernel(const Split8Params p) {
+  constexpr int kS8Groups = S8Shape<kNoE>::kGroups, kS8Issuers = S8Shape<kNoE>::kIssuers;
+  constexpr int kS8DecodeWarps = 4 * kS8Groups, kS8FirstDecodeWarp = kS8Issuers;
+  constexpr int kS8ProducerWarp = kS8FirstDecodeWarp + kS8DecodeWarps;
+  static_assert(kS8Groups <= kS8MaxGroups && kS8Issuers <= kS8MaxIssuers && (kS8Issuers & (kS8Issuers - 1)) == 0, "warp roles");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int NC = p.NC;
   const uint32_t rank = kPair ? s8_cta_rank() : 0u;
@@ -441,7 +458,7 @@ __global__ void __launch_bounds__(kS8Threads, 1) split8_kernel(const Split8Param
 #endif
     }
   } else if (warp >= kS8FirstDecodeWarp) {
-    // ---- decode + count (8 warps), epilogue ----
+    // ---- decode + count, epilogue ----
     const int q = warp & 3;                                 // TMEM lane quarter this warp may access
     const uint32_t grp = (warp - kS8FirstDecodeWarp) >> 2;  // takes the stages with global index = grp mod kS8Groups
     const int vloc = q * 32 + lane;                         // variant of the tile = TMEM lane
@@ -824,9 +841,9 @@ Split8Plan split8_plan(int n_variants, int n_cb, int64_t n_stages, int sm_count,
     for (int ns = 1; ns <= max_split; ++ns) {
       if (force_split > 0 && ns != std::min(force_split, max_split)) continue;
       // ns ranges of `per` stages (even), the last one shorter but with a stage for every issuer warp:
-      // n_stages - (ns - 1) per >= kS8Issuers
+      // n_stages - (ns - 1) per >= kS8MaxIssuers
       const int per = ns == 1 ? (int)n_stages : (int)round_up(ceil_div(n_stages, ns), 2);
-      if (ns > 1 && (int64_t)(ns - 1) * per + kS8Issuers > n_stages) {
+      if (ns > 1 && (int64_t)(ns - 1) * per + kS8MaxIssuers > n_stages) {
         if (force_split > 0) {  // forced but not feasible: fall back to the unsplit form
           ns_out = 1;
           per_out = (int)n_stages;
@@ -877,6 +894,7 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   cudaMemcpyToSymbol(g_s8_prof, zero, sizeof(zero));
 #endif
   using Kern = void (*)(const Split8Params);
+  const unsigned n_threads = no_e ? S8Shape<true>::kThreads : S8Shape<false>::kThreads;
   auto pick = [&](bool pr) -> Kern {
 #define GLR_S8_K(A, F) (pr ? (no_e ? (Kern)split8_kernel<A, true, true, F> : (Kern)split8_kernel<A, true, false, F>) \
                            : (no_e ? (Kern)split8_kernel<A, false, true, F> : (Kern)split8_kernel<A, false, false, F>))
@@ -890,7 +908,7 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * std::min(n_items2, sm_count / 2));
-    cfg.blockDim = dim3(kS8Threads);
+    cfg.blockDim = dim3(n_threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -909,7 +927,7 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
     const size_t smem = (size_t)kS8WRing * p.NC * kS8K + sizeof(Split8Smem) + 64;
     Kern kern = pick(false);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<std::min(n_items1, sm_count), kS8Threads, smem, st>>>(p);
+    kern<<<std::min(n_items1, sm_count), n_threads, smem, st>>>(p);
   }
   if (p.n_split > 1) {
     const dim3 grid((unsigned)ceil_div(p.x.n_variants, 128), (unsigned)p.n_cb);
