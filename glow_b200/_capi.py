@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GLOW_B200_LIB') or os.path.join(_HERE, 'lib', 'libglow_b200.so')  # (override: A/B runs of differently built libraries)
 
-GLR_ABI_VERSION = 2
+GLR_ABI_VERSION = 3
 FMT_F64, FMT_F32, FMT_I8, FMT_PLINK2 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 MISSING_AS_MINUS_ONE, MISSING_MEAN = 0, 1

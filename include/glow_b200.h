@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GLR_ABI_VERSION 2
+#define GLR_ABI_VERSION 3
 
 typedef enum glr_status {
   GLR_OK = 0,
