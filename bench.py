@@ -428,6 +428,97 @@ def run_other_configs(torch, dev, hbm_peak, i8_peak):
     return out
 
 
+def run_next_rows(torch, dev):
+    """SURVEY.md section 8f rows built beyond the linear block loop, each with a measured rate: N3 logistic score test
+    (device block loop), N2 BGEN probabilities -> 2-bit rows, N4 GloWGR LOCO apply step."""
+    import ctypes as C
+    from glow_b200 import _capi
+    from glow_b200.engine import ResidentBlock
+    from glow_b200.gwas import log_reg as lr
+    out = []
+    lib = _capi.load()
+    # ---- N3: logistic score test at the configs[2] shape, genotypes resident in HBM ----
+    try:
+        rg = np.random.default_rng(17)
+        N, K, G = N_SAMPLES, N_COV + 1, 37_888
+        Cm = np.column_stack([np.ones(N), rg.standard_normal((N, K - 1))])
+        y = (rg.random(N) < 1.0 / (1.0 + np.exp(-(0.3 * Cm[:, 1] - 0.5)))).astype(np.float64)
+        y_res, gamma, inv = lr._prepare_one_phenotype(Cm, y, None)
+        state = lr.LogRegDeviceState(Cm, [lr.LogRegState(inv[None], gamma[:, None], y_res[:, None], None)], device=dev.index)
+        X = gen_packed_device(torch, G, N, 9, dev)
+        blk = ResidentBlock(X.data_ptr(), X.shape[1], G, 'plink2', 'mean', dev.index)
+        for _ in range(2):
+            res = state.run(blk)
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or time.perf_counter() - t0 < 0.5:
+            res = state.run(blk)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        state.close()
+        out.append(dict(config='N3 logistic_regression(correction="none") block loop, configs[2] shape (500k samples, 16 covariates + '
+                               'intercept, 1 binary phenotype, 2-bit, 1 % missing calls), block resident in HBM',
+                        tests_per_s=G / dt, block_ms=dt * 1e3, variants_per_block=G, blocks_timed=reps,
+                        finite=float(np.isfinite(res['pvalue']).mean()),
+                        kernels='split8_kernel twice (int8 tensor cores: [gamma o C | Y_res]^T x with fused counts, then gamma^T x^2 '
+                                'with the squared-call table) + logreg_epilogue_kernel; wall clock of glr_logreg_run_block incl. '
+                                'the copy of chisq / pvalue to the host',
+                        fp64_equivalent_tflops=2.0 * N * (K + 2) * G / dt / 1e12,
+                        genotype_gbs_two_reads=2.0 * G * X.shape[1] / dt / 1e9))
+        del X
+    except Exception as exc:  # noqa: BLE001
+        out.append(dict(config='N3 logistic score test', error=f'{type(exc).__name__}: {exc}'))
+    # ---- N2: BGEN layout-2 probabilities (8 bit) -> PLINK 2-bit rows on the device, host in / device out ----
+    try:
+        rg = np.random.default_rng(18)
+        G, N = 2_048, 100_000
+        probs = rg.integers(0, 256, (G, 2 * N), dtype=np.uint8)
+        ploidy = np.full((G, N), 2, dtype=np.uint8)
+        dst = torch.empty((G, (N + 3) // 4), dtype=torch.uint8, device=dev)
+        call = lambda: _capi.check(lib.glr_bgen_to_plink2(dev.index, probs.ctypes.data, ploidy.ctypes.data, G, N, 8, 0.9,
+                                                          C.c_void_p(dst.data_ptr()), dst.shape[1]))  # noqa: E731
+        call()
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or time.perf_counter() - t0 < 0.3:
+            call()
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        out.append(dict(config='N2 glr_bgen_to_plink2: 8-bit BGEN probability pairs of 2 048 variants x 100 000 samples (pageable host '
+                               'memory) -> hard calls -> 2-bit rows in HBM',
+                        input_gbs=(probs.nbytes + ploidy.nbytes) / dt / 1e9, genotypes_per_s=G * N / dt, block_ms=dt * 1e3,
+                        note='bound by the host-to-device copy of 3 bytes per genotype from pageable memory'))
+        del probs, ploidy, dst
+    except Exception as exc:  # noqa: BLE001
+        out.append(dict(config='N2 BGEN conversion', error=f'{type(exc).__name__}: {exc}'))
+    # ---- N4: GloWGR LOCO apply step ----
+    try:
+        rg = np.random.default_rng(19)
+        N, H, NB, NC = 50_000, 1_000, 10, 22
+        Xr = rg.standard_normal((N, H))
+        mu, sig = Xr.mean(0), Xr.std(0)
+        B = rg.standard_normal((NB, H)) / H
+        hc = rg.integers(0, NC, H).astype(np.int32)
+        sb = (np.arange(N) * NB // N).astype(np.int32)
+        res = np.empty((NC, N))
+        call = lambda: _capi.check(lib.glr_loco_predict(dev.index, N, H, NB, NC, Xr.ctypes.data, mu.ctypes.data, sig.ctypes.data,
+                                                        B.ctypes.data, hc.ctypes.data, sb.ctypes.data, None, 0, None,
+                                                        res.ctypes.data))  # noqa: E731
+        call()
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or time.perf_counter() - t0 < 0.3:
+            call()
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        ref = ((Xr[:64] - mu) / sig * B[sb[:64]])
+        want = np.stack([ref[:, hc != c].sum(1) for c in range(NC)])
+        out.append(dict(config='N4 glr_loco_predict: 50 000 samples x 1 000 reduced headers, 10 sample blocks, 22 chromosomes, host in / '
+                               'host out',
+                        input_gbs=Xr.nbytes / dt / 1e9, offsets_per_s=NC * N / dt, call_ms=dt * 1e3,
+                        max_abs_err_vs_numpy=float(np.abs(res[:, :64] - want).max())))
+    except Exception as exc:  # noqa: BLE001
+        out.append(dict(config='N4 LOCO apply', error=f'{type(exc).__name__}: {exc}'))
+    return out
+
+
 def run_e2e_api(torch, dev, n_variants=65_536, block_variants=8_192):
     """Public API on a .bed FILE in tmpfs: everything a user waits for (file -> pinned staging -> H2D -> kernels -> D2H ->
     pandas frame), state creation included."""
@@ -663,6 +754,7 @@ def main():
     dmma = None
     cpu = None
     configs = None
+    next_rows = None
     e2e_api = None
     if rank == 0:
         peaks = {}
@@ -836,6 +928,7 @@ def main():
         torch.cuda.empty_cache()
         if not args.skip_configs:
             configs = run_other_configs(torch, dev, hbm_peak, issue_rate)
+            next_rows = run_next_rows(torch, dev)
         if not args.skip_e2e_api:
             try:
                 e2e_api = run_e2e_api(torch, dev)
@@ -871,6 +964,7 @@ def main():
             'roofline': roof,
             'dmma_f64_path': dmma,
             'configs': configs,
+            'next_rows': next_rows,
             'cpu_baseline': cpu,
             'stage_ms_per_batch': stage,
             'finite_fraction': frac_finite

@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(S8Shape<kNoE>::kThreads, 1) split8_kernel(cons
     const int64_t full_bytes = n_geno >> 2;
     uint32_t g0 = 0;
     int icount = 0;
+    const uint32_t x_lut = p.x_lut ? p.x_lut : 0x00010002u;
     uint32_t miss_seen = 0;  // kNoE: OR of the code-01 bits met
     uint32_t bad_seen = 0;   // int8 form: bits of bytes outside {-1, 0, 1, 2}
     for (int item = first_item; item < n_items; item += item_stride, ++icount) {
@@ -630,10 +631,10 @@ __global__ void __launch_bounds__(S8Shape<kNoE>::kThreads, 1) split8_kernel(cons
           const uint32_t ev = s8_and(ww, 0x77777777u), od = s8_and(ww >> 2, 0x77777777u);
           const uint32_t ev_hi = ev >> 16, od_hi = od >> 16;
           // code 00 -> 2, 01 -> 0 (missing), 10 -> 1, 11 -> 0;  e: code 01 -> 1
-          xs[4 * i + 0] = s8_prmt(0x00010002u, ev);
-          xs[4 * i + 1] = s8_prmt(0x00010002u, ev_hi);
-          xs[4 * i + 2] = s8_prmt(0x00010002u, od);
-          xs[4 * i + 3] = s8_prmt(0x00010002u, od_hi);
+          xs[4 * i + 0] = s8_prmt(x_lut, ev);
+          xs[4 * i + 1] = s8_prmt(x_lut, ev_hi);
+          xs[4 * i + 2] = s8_prmt(x_lut, od);
+          xs[4 * i + 3] = s8_prmt(x_lut, od_hi);
           if (!kNoE) {
             es[4 * i + 0] = s8_prmt(0x00000100u, ev);
             es[4 * i + 1] = s8_prmt(0x00000100u, ev_hi);

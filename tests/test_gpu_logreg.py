@@ -179,3 +179,43 @@ def test_approx_firth_on_packed_blocks_and_linear_residualisation(rg):
     with pytest.raises(NotImplementedError, match='host'):
         glow_b200.gwas.logistic_regression(res, phe, cov, pvalue_threshold=0.9)
     res.close()
+
+
+def test_int8_tensor_path_of_the_score_test(rg, monkeypatch):
+    """2-bit blocks run both contractions of the score test on the int8 tensor cores (pass 2 = the squared-call table with
+    mu^2 as the missing substitute).  At 100 000 samples: against the oracle on a subset, and against the FP64 DMMA path
+    (GLR_LOGREG_SPLIT8=0) on the whole block, both missing policies, a small block (sample range split) included."""
+    from glow_b200.gwas.log_reg import LogRegDeviceState
+    from glow_b200.engine import GenotypeBlock
+    N, G, P, K = 100_000, 700, 2, 8
+    f = rg.uniform(0.02, 0.5, (G, 1))
+    u = rg.random((G, N), dtype=np.float32)
+    states = (u > (1 - f)**2).astype(np.int8) + (u > (1 - f)**2 + 2 * f * (1 - f)).astype(np.int8)
+    states[rg.random((G, N), dtype=np.float32) < 0.01] = -1
+    states[5] = -1                                  # an all-missing variant
+    states[6] = 2                                   # a constant one
+    cov = pd.DataFrame(rg.standard_normal((N, K)) * 0.3)
+    Y = (rg.random((N, P)) < 0.3).astype(np.float64)
+    Y[rg.random((N, P)) < 0.05] = np.nan
+    C, mask, st = lo.prepare_state(pd.DataFrame(Y), cov)
+    packed = pack_plink(states.astype(np.int64))
+    eng = LogRegDeviceState(C, [st])
+    monkeypatch.setenv('GLR_LOGREG_SPLIT8', '0')
+    eng_dmma = LogRegDeviceState(C, [st])
+    monkeypatch.delenv('GLR_LOGREG_SPLIT8')
+    idx = np.array([0, 1, 127, 128, 300, 699])
+    for policy in ('mean', 'minus_one'):
+        got = eng.run(GenotypeBlock(packed, 'plink2', policy))
+        want = eng_dmma.run(GenotypeBlock(packed, 'plink2', policy))
+        ok = np.isfinite(want['chisq'])
+        assert np.array_equal(np.isfinite(got['chisq']), ok)
+        np.testing.assert_allclose(got['chisq'][ok], want['chisq'][ok], rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(got['pvalue'][ok], want['pvalue'][ok], rtol=1e-6, atol=1e-300)
+        X = states[idx].astype(np.float64)
+        ref = lo.block_score_test(orc.mean_substitute(X) if policy == 'mean' else X, C, mask, st)
+        _close({k: v[:, idx] for k, v in got.items()}, ref, f'int8 path {policy}')
+        small = eng.run(GenotypeBlock(packed[:100], 'plink2', policy))
+        for k in ('chisq', 'pvalue'):
+            assert np.array_equal(small[k], got[k][:, :100], equal_nan=True), k
+    eng.close()
+    eng_dmma.close()
