@@ -16,7 +16,7 @@
 //   epilogue: logreg_epilogue_kernel
 // The decode of packed genotypes (PLINK 2-bit / int8 states, optional mean substitution) is the same fused operand
 // load as in the linear path.
-// PLINK 2-bit blocks (no dropped samples, more than 384 samples) take both contractions on the int8 tensor cores instead
+// PLINK 2-bit blocks (more than 384 samples) take both contractions on the int8 tensor cores instead
 // (split8.cu, the linear path's kernel): pass 1 on the digit image of W with the genotype counts and the mean substitute
 // fused; pass 2 on the digit image of the gamma columns with the SQUARED-call table (00 -> 4, 10 -> 1) and mu^2 as the
 // missing substitute, because x^2 = xi^2 + mu^2 e when xi e = 0.  Exact integer accumulation, FP64 recombination:
@@ -503,7 +503,9 @@ int glr_logreg_run_block(glr_logreg_state* st, const glr_block_desc* b, double* 
   // 2-bit blocks: both contractions on the int8 tensor cores.  Pass 1 is the linear path's kernel on W (counts and mean
   // substitute fused); pass 2 is the same kernel with the squared-call table on the gamma columns and mu^2 as the
   // substitute: sum_s gamma_s (xi_s^2 + mu^2 e_s) = x^T Gamma x.
-  const bool use_s8 = st->s8 && b->format == GLR_FMT_PLINK2 && st->n_drop == 0;
+  // (dropped samples carry zero digits, and the mean substitute is taken over all genotype samples -- upstream of the drop
+  // in the reference: mean_substitute runs on the whole array -- so the fused counts are the right ones here)
+  const bool use_s8 = st->s8 && b->format == GLR_FMT_PLINK2;
   if (use_s8) {
     if (int rc = st->v1sq.ensure((size_t)ldS * 8)) return rc;
     if (int rc = st->s8_flags.ensure(2 * sizeof(int32_t))) return rc;

@@ -67,9 +67,10 @@ def test_all_formats_against_oracle(rg, N, G, P, K):
     eng.close()
 
 
-def test_loco_offsets_intersect_and_sources(rg):
+@pytest.mark.parametrize('N', [320, 1500])  # below / above the sample count from which 2-bit blocks take the int8 path
+def test_loco_offsets_intersect_and_sources(rg, N):
     import glow_b200
-    N, G, P, K = 320, 60, 2, 3
+    G, P, K = 60, 2, 3
     samples = [f's{i}' for i in range(N)]
     states = rg.integers(0, 3, (G, N))
     states[rg.random((G, N)) < 0.03] = -1
