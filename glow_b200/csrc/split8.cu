@@ -20,7 +20,7 @@
 // MMA shape.  The GENOTYPES are the A operand and live in tensor memory: TMEM lane = variant of a
 // 128-variant tile, 8 columns (32 packed int8) per K = 32 samples, written straight from the decode
 // registers with tcgen05.st.  The digit rows are the B operand (N = NC <= 128 rows: up to 18 columns
-// x 7 digits + a row of ones), K-major in shared memory with the 128-byte swizzle, streamed by bulk
+// x 5-7 digits + a row of ones), K-major in shared memory with the 128-byte swizzle, streamed by bulk
 // copies.  Two accumulators per tile, Dx = xi * digits^T and De = e * digits^T ([128 variants x NC],
 // int32) sit in TMEM columns [0, NC) and [128, 128 + NC); the A ring uses columns [256, 512).
 // Compared with keeping the genotypes in shared memory (B operand) this removes the decode's shared
@@ -37,19 +37,23 @@
 // the L2 and shared-memory traffic.  The leader (rank 0) issues the MMAs; the barriers it waits on collect arrivals from
 // both CTAs (remote mbarrier arrives), and tcgen05.commit multicasts the completions to both.
 //
-// CTA roles (416 threads, 1 CTA/SM, persistent over (128-variant tile, column block[, sample range]) work items):
-//   warps 0-3 : issue tcgen05.mma, stage g by warp g % 4 (converged warps, one elected lane); one tcgen05.commit per
+// CTA roles (S8Shape: 608 threads = 19 warps, 1 CTA/SM, persistent over (128-variant tile, column block[, sample range])
+// work items):
+//   warps 0-1 : issue tcgen05.mma, stage g by warp g % 2 (converged warps, one elected lane); one tcgen05.commit per
 //               stage frees the stage's buffers, a second one after the warp's last stage of the item publishes the
 //               accumulators (in the non-leader CTA of a pair they forward "my half of the digit stage has landed"
-//               instead).  One iteration of an issuer (three barrier waits, fence, election, 4-8 MMAs, commit) has a
-//               latency of several hundred cycles: two issuers sustained one stage per ~470 cycles, enough for the full
-//               form (512 cycles of MMAs per stage) but not for the optimistic one (256)
-//   warp 12   : TMEM allocation / deallocation; lane 0 streams the packed digit operand (pre-swizzled image, one bulk
-//               copy per stage)
-//   warps 4-11: decode.  Warp w owns TMEM lanes 32 (w % 4) ..; warps 4-7 take the even stages, warps
-//               8-11 the odd ones; a thread turns 32 bytes of its variant's row (128 samples) into 32 + 32
-//               TMEM words per stage.  All 8 warps run the epilogue (tcgen05.ld of the variant's digit
+//               instead)
+//   warps 2-17: decode, four groups of four warps.  Warp w owns TMEM lanes 32 (w % 4) ..; group g % 4 takes stage g; a
+//               thread turns 32 bytes of its variant's row (128 samples) into 32 + 32 TMEM words per stage.  One group's
+//               stage is a dependent chain of ~1 200 cycles (row segment -> decode -> TMEM slot -> tcgen05.st -> arrive):
+//               the groups overlap their chains.  All decode warps run the epilogue (tcgen05.ld of the variant's digit
 //               sums, FP64 recombination, coalesced store of S).
+//   warp 18   : TMEM allocation / deallocation; lane 0 streams the packed digit operand (pre-swizzled image, one bulk
+//               copy per stage)
+// Digits.  The first n_lo columns of a single-block image may carry fewer than 7 digits (Split8Params.n_lo / lo_digits);
+// the caller then certifies every result (xx_full_kernel in aux.cu) and re-runs a block on the 7-digit image when a bound
+// fails.  Split8Params.x_lut replaces the call values 2 / 1 by other small integers (4 / 1: the squared calls of the
+// logistic score test).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
