@@ -283,6 +283,10 @@ int glr_state_create(const glr_state_desc* d, glr_state** out) {
   if (const char* e = getenv("GLR_SPLIT")) st->force_split = atoi(e);
   st->s8_pair_mode = tri_knob(d->opt.split8_pair, "GLR_S8_PAIR");
   st->optimistic_mode = tri_knob(d->opt.optimistic_calls, "GLR_OPTIMISTIC");
+  {
+    const int qd = knob_int(d->opt.q_digits, "GLR_Q_DIGITS");
+    if (qd != 0 && (qd < 3 || qd > 7)) return fail(GLR_ERR_INVALID, "q_digits must be 0 (automatic) or 3..7");
+  }
 
   const int64_t N = st->N, Ng = st->Ng;
   const int K = st->K, P = st->P, C = st->C;

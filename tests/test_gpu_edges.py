@@ -242,6 +242,11 @@ def test_error_codes(rg):
     with pytest.raises(ValueError):  # lane out of range
         eng.submit(9, GenotypeBlock(X, 'f64'))
     eng.close()
+    from glow_b200.engine import DeviceState
+    st = orc.prepare_state(phe, cov)
+    with pytest.raises(ValueError, match='q_digits'):  # digit count outside 3..7
+        DeviceState(Q=st.Q, Y=st.y_state.Y[None], Y_mask=st.Y_mask, YdotY=st.y_state.YdotY[None], Y_scale=st.Y_scale, dof=st.dof,
+                    options={'q_digits': 9})
 
 
 def test_tensor_issue_rate_probe():
