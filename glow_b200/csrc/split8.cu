@@ -473,6 +473,9 @@ __global__ void __launch_bounds__(S8Shape<kNoE>::kThreads, 1) split8_kernel(cons
     uint32_t g0 = 0;
     int icount = 0;
     const uint32_t x_lut = p.x_lut ? p.x_lut : 0x00010002u;
+    // table of the missing-call indicator (code 01 -> 1), a run-time value so that it stays in ONE register: as a literal
+    // the compiler re-materialised it from a uniform register in front of every PRMT (32 extra moves per stage and warp)
+    const uint32_t e_lut = p.e_lut;
     uint32_t miss_seen = 0;  // kNoE: OR of the code-01 bits met
     uint32_t bad_seen = 0;   // int8 form: bits of bytes outside {-1, 0, 1, 2}
     for (int item = first_item; item < n_items; item += item_stride, ++icount) {
@@ -640,10 +643,10 @@ __global__ void __launch_bounds__(S8Shape<kNoE>::kThreads, 1) split8_kernel(cons
           xs[4 * i + 2] = s8_prmt(x_lut, od);
           xs[4 * i + 3] = s8_prmt(x_lut, od_hi);
           if (!kNoE) {
-            es[4 * i + 0] = s8_prmt(0x00000100u, ev);
-            es[4 * i + 1] = s8_prmt(0x00000100u, ev_hi);
-            es[4 * i + 2] = s8_prmt(0x00000100u, od);
-            es[4 * i + 3] = s8_prmt(0x00000100u, od_hi);
+            es[4 * i + 0] = s8_prmt(e_lut, ev);
+            es[4 * i + 1] = s8_prmt(e_lut, ev_hi);
+            es[4 * i + 2] = s8_prmt(e_lut, od);
+            es[4 * i + 3] = s8_prmt(e_lut, od_hi);
           }
         }
         S8_T(d1);
@@ -898,6 +901,7 @@ void launch_split8(Split8Params p, int sm_count, cudaStream_t st) {
   static long long zero[160][3][8];
   cudaMemcpyToSymbol(g_s8_prof, zero, sizeof(zero));
 #endif
+  p.e_lut = 0x00000100u;
   using Kern = void (*)(const Split8Params);
   const unsigned n_threads = no_e ? S8Shape<true>::kThreads : S8Shape<false>::kThreads;
   auto pick = [&](bool pr) -> Kern {
