@@ -57,8 +57,8 @@ def test_ctypes_structs_match_header_layout():
                           _capi.BlockDesc.row_stride_bytes.offset]
     assert sizes[8:] == [ctypes.sizeof(_capi.Options), _capi.StateDesc.opt.offset, _capi.Options.q_digits.offset,
                          _capi.Timing.path.offset]
-    o = _capi.make_options({'split8': 'force', 'split8_pair': 'off', 'sample_split': 3})
-    assert (o.split8, o.split8_pair, o.mask_sparse, o.sample_split) == (_capi.FORCE, _capi.OFF, _capi.AUTO, 3)
+    o = _capi.make_options({'split8': 'force', 'split8_pair': 'off', 'sample_split': 3, 'q_digits': 7})
+    assert (o.split8, o.split8_pair, o.mask_sparse, o.sample_split, o.q_digits) == (_capi.FORCE, _capi.OFF, _capi.AUTO, 3, 7)
     with pytest.raises(ValueError):
         _capi.make_options({'nope': 1})
 
