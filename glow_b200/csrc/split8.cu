@@ -624,10 +624,14 @@ __global__ void __launch_bounds__(S8Shape<kNoE>::kThreads, 1) split8_kernel(cons
         // decode into registers first, THEN wait for the TMEM slot: the slot frees up when the MMAs of stage g - 4
         // complete, and the hand-off back to the issuer must not include the decode arithmetic
         uint32_t xs[32], es[kNoE ? 1 : 32];
+        if (p.fused_counts) {  // (uniform) the count of code 00 is only needed for the fused moments
+#pragma unroll
+          for (int i = 0; i < kS8Words; ++i)
+            n00 += __popc(~(w[i] | (w[i] << 1)) & 0xAAAAAAAAu);  // both bits of a code clear (left shift: FMA pipe, not ALU)
+        }
 #pragma unroll
         for (int i = 0; i < kS8Words; ++i) {
           const uint32_t ww = w[i];
-          n00 += __popc(~(ww | (ww << 1)) & 0xAAAAAAAAu);  // both bits of a code clear (left shift: FMA pipe, not ALU)
           // code 01 (low bit set, high bit clear) at the even bit positions; the odd ones are masked once, at the end
           if (kNoE) miss_seen |= ww & ~(ww >> 1);
           // PRMT selectors: nibble n of `ev` = code 2n (bit 2 is a stray bit of the neighbouring code: the table
