@@ -67,7 +67,7 @@ struct Split8Params {
   int32_t* z_ws;         // n_split > 1: zero-initialised by the launcher, [n_cb][2][NC][ldS] int32 partial digit sums
   int32_t* n00_ws;       // n_split > 1: [ldS] int32 code-00 counts
   uint32_t x_lut;        // 2-bit code -> genotype value, one byte per code (0 = the default 0x00010002: 00 -> 2, 10 -> 1);
-                         // 0x00010004 contracts the SQUARED calls (logistic score test: sum gamma x^2), PLINK2 form only
+                         // 0x00010004 contracts the SQUARED calls (logistic score test: sum gamma x^2); the int8-states form knows these two tables
   uint32_t e_lut;        // 2-bit code -> missing-call indicator (0x00000100), set by launch_split8
   int32_t* flags;        // [2] device ints: [0] |= 1 when the optimistic form met a missing call,
                          //                  [1] += number of missing calls of the block (full form, fused_counts)

@@ -16,7 +16,7 @@
 //   epilogue: logreg_epilogue_kernel
 // The decode of packed genotypes (PLINK 2-bit / int8 states, optional mean substitution) is the same fused operand
 // load as in the linear path.
-// PLINK 2-bit blocks (more than 384 samples) take both contractions on the int8 tensor cores instead
+// PLINK 2-bit blocks and 4-byte aligned int8 genotype states (more than 384 samples) take both contractions on the int8 tensor cores instead
 // (split8.cu, the linear path's kernel): pass 1 on the digit image of W with the genotype counts and the mean substitute
 // fused; pass 2 on the digit image of the gamma columns with the SQUARED-call table (00 -> 4, 10 -> 1) and mu^2 as the
 // missing substitute, because x^2 = xi^2 + mu^2 e when xi e = 0.  Exact integer accumulation, FP64 recombination:
@@ -439,7 +439,10 @@ int glr_logreg_state_create(const glr_logreg_desc* d, glr_logreg_state** out) {
   return 0;
 }
 
-int glr_logreg_run_block(glr_logreg_state* st, const glr_block_desc* b, double* chisq, double* pvalue) {
+}  // extern "C"
+
+// allow_s8 = false: second run of an int8 block whose values turned out not to be genotype states (see below)
+static int logreg_run_block(glr_logreg_state* st, const glr_block_desc* b, double* chisq, double* pvalue, bool allow_s8) {
   if (!st || !b) return api_fail(GLR_ERR_INVALID, "null argument");
   if (b->format < GLR_FMT_F64 || b->format > GLR_FMT_PLINK2) return api_fail(GLR_ERR_INVALID, "unknown genotype format");
   if (b->contig < 0 || b->contig >= st->C) return api_fail(GLR_ERR_INVALID, "contig index out of range");
@@ -505,7 +508,10 @@ int glr_logreg_run_block(glr_logreg_state* st, const glr_block_desc* b, double* 
   // substitute: sum_s gamma_s (xi_s^2 + mu^2 e_s) = x^T Gamma x.
   // (dropped samples carry zero digits, and the mean substitute is taken over all genotype samples -- upstream of the drop
   // in the reference: mean_substitute runs on the whole array -- so the fused counts are the right ones here)
-  const bool use_s8 = st->s8 && b->format == GLR_FMT_PLINK2;
+  // int8 genotype states take the same kernels when the rows are 4-byte aligned; the kernel checks every byte and a block
+  // with a value outside {-1, 0, 1, 2} is run again on the FP64 path (any int8 value is legal there)
+  const bool i8_ok = b->format == GLR_FMT_I8 && ((reinterpret_cast<uintptr_t>(d_geno) | (uintptr_t)b->row_stride_bytes) & 3) == 0;
+  const bool use_s8 = st->s8 && allow_s8 && (b->format == GLR_FMT_PLINK2 || i8_ok);
   if (use_s8) {
     if (int rc = st->v1sq.ensure((size_t)ldS * 8)) return rc;
     if (int rc = st->s8_flags.ensure(2 * sizeof(int32_t))) return rc;
@@ -609,8 +615,16 @@ int glr_logreg_run_block(glr_logreg_state* st, const glr_block_desc* b, double* 
   CUL(cudaGetLastError());
   CUL(cudaMemcpyAsync(chisq, d_chi, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
   CUL(cudaMemcpyAsync(pvalue, d_p, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
+  int32_t h_flags[2] = {0, 0};
+  if (use_s8 && b->format == GLR_FMT_I8)
+    CUL(cudaMemcpyAsync(h_flags, st->s8_flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
   CUL(cudaStreamSynchronize(s));
+  if (h_flags[0] & 2) return logreg_run_block(st, b, chisq, pvalue, false);
   return 0;
 }
 
+extern "C" {
+int glr_logreg_run_block(glr_logreg_state* st, const glr_block_desc* b, double* chisq, double* pvalue) {
+  return logreg_run_block(st, b, chisq, pvalue, true);
+}
 }  // extern "C"

@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(S8Shape<kNoE>::kThreads, 1) split8_kernel(cons
     // table of the missing-call indicator (code 01 -> 1), a run-time value so that it stays in ONE register: as a literal
     // the compiler re-materialised it from a uniform register in front of every PRMT (32 extra moves per stage and warp)
     const uint32_t e_lut = p.e_lut;
+    const bool sq = p.x_lut == 0x00010004u;  // int8 states: the same table, applied arithmetically
     uint32_t miss_seen = 0;  // kNoE: OR of the code-01 bits met
     uint32_t bad_seen = 0;   // int8 form: bits of bytes outside {-1, 0, 1, 2}
     for (int item = first_item; item < n_items; item += item_stride, ++icount) {
@@ -605,7 +606,9 @@ __global__ void __launch_bounds__(S8Shape<kNoE>::kThreads, 1) split8_kernel(cons
                 // anything but -1, 0, 1, 2: a value above 2 (bits 2..6, or bits 0 and 1 together), a negative one other than -1
                 bad_seen |= (u & 0xFCFCFCFCu) | (u & (u >> 1) & 0x01010101u) | (u & (e * 0xFFu));
                 n00 += __popc(u & 0x02020202u);                          // number of alternate-homozygous calls
-                xs8[4 * h + j] = u & 0x03030303u;
+                uint32_t xv = u & 0x03030303u;
+                if (sq) xv += xv & 0x02020202u;                          // squared calls: 0, 1, 2 -> 0, 1, 4
+                xs8[4 * h + j] = xv;
                 es8[4 * h + j] = e;
                 if (kNoE) miss_seen |= e;
               }

@@ -218,5 +218,15 @@ def test_int8_tensor_path_of_the_score_test(rg, monkeypatch):
         small = eng.run(GenotypeBlock(packed[:100], 'plink2', policy))
         for k in ('chisq', 'pvalue'):
             assert np.array_equal(small[k], got[k][:, :100], equal_nan=True), k
+        # the same calls as int8 genotype states: same kernels, same bits
+        got8 = eng.run(GenotypeBlock(states, 'i8', policy))
+        for k in ('chisq', 'pvalue'):
+            assert np.array_equal(got8[k], got[k], equal_nan=True), k
+    # int8 values that are not genotype states: detected in the kernel, the block is run again on the FP64 path
+    wild = states[7:71].copy()                      # (not the degenerate rows 5 and 6)
+    wild[3, 10] = 3
+    wild[63, N - 1] = -2
+    ref = lo.block_score_test(wild.astype(np.float64), C, mask, st)
+    _close(eng.run(GenotypeBlock(wild, 'i8', 'minus_one')), ref, 'int8 values outside the state range')
     eng.close()
     eng_dmma.close()
